@@ -1,0 +1,5 @@
+"""oracle -- CPU checker for the bhmm HMM hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package.  The product package (bhmm_b200/) never does.
+"""
