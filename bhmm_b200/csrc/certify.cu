@@ -1,0 +1,84 @@
+// bhmm_b200/csrc/certify.cu -- certification of chain hand-overs and the deterministic E-step reduction.
+//
+// Time-chunking is only allowed to change results below the stated tolerance.  A chain that does not
+// start its trajectory is started from a warmed-up filter; afterwards its hand-over vector (the alpha at
+// the frame before the chain, or the beta at the frame after it) is compared, component by component and
+// RELATIVELY, with the value the neighbouring chain actually computed.  Chains that disagree by more than
+// `tol` are listed and re-run from the exact neighbour value (Chains.exact = 1) until the list is empty;
+// in the worst case (a non-mixing model) this degenerates to the sequential recursion, never to a wrong
+// answer.  The reference has no counterpart (it is serial in t, _hidden.c:41-63).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+__global__ void k_certify(Chains ch, int n_total, int N, int dir, const double* __restrict__ hand_used,
+                          const double* __restrict__ hand_end, double tol, int* __restrict__ fail_list,
+                          unsigned long long* __restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_total) return;
+    int nb;
+    if (dir > 0) {
+        if (ch.t0[c] == 0) return;             // starts its trajectory: exact by construction
+        nb = c - 1;
+    } else {
+        if (ch.t0[c] + ch.len[c] >= ch.T[c]) return;   // ends its trajectory: exact by construction
+        nb = c + 1;
+    }
+    const double* u = hand_used + (long long)c * N;
+    const double* v = hand_end + (long long)nb * N;
+    double worst = 0.0;
+    for (int i = 0; i < N; ++i) worst = fmax(worst, rel_mismatch(u[i], v[i]));
+    atomicMax(out + 1, (unsigned long long)__double_as_longlong(worst));   // non-negative doubles order like their bits
+    if (worst > tol) {
+        const unsigned long long slot = atomicAdd(out, 1ULL);
+        fail_list[slot] = c;
+    }
+}
+
+// stats = [loglik | gamma0 (N) | C (N*N) | sum gamma (N) | sum gamma d (N) | sum gamma d^2 (N)]
+// partial rows are [C' (N*N) | gamma0 | sum gamma | sum gamma d | sum gamma d^2]; C = A o C'.
+__global__ void k_finalize_stats(const double* __restrict__ partials, int grid, const double* __restrict__ chain_ll,
+                                 int n_chains, const double* __restrict__ A, int N, double* __restrict__ stats)
+{
+    __shared__ double red[256];
+    const int nstat = N * N + 4 * N;
+    for (int k = threadIdx.x; k < nstat; k += blockDim.x) {
+        double s = 0.0;
+        for (int b = 0; b < grid; ++b) s += partials[(long long)b * nstat + k];
+        if (k < N * N) stats[1 + N + k] = A[k] * s;
+        else if (k < N * N + N) stats[1 + (k - N * N)] = s;
+        else stats[1 + k] = s;
+    }
+    // log-likelihood: fixed partition + fixed tree => deterministic
+    const int per = (n_chains + blockDim.x - 1) / blockDim.x;
+    double s = 0.0;
+    const int lo = threadIdx.x * per, hi = min(n_chains, lo + per);
+    for (int c = lo; c < hi; ++c) s += chain_ll[c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) stats[0] = red[0];
+}
+
+}  // namespace
+
+int launch_certify(const Chains& ch, int n_total, int N, int dir, const double* hand_used, const double* hand_end,
+                   double tol, int* fail_list, unsigned long long* out, cudaStream_t st)
+{
+    cudaMemsetAsync(out, 0, 2 * sizeof(unsigned long long), st);
+    if (n_total <= 0) return BHMM_OK;
+    k_certify<<<(n_total + 127) / 128, 128, 0, st>>>(ch, n_total, N, dir, hand_used, hand_end, tol, fail_list, out);
+    return BHMM_OK;
+}
+
+int launch_finalize_stats(const double* partials, int grid, const double* chain_ll, int n_chains, const double* A,
+                          int N, double* stats, cudaStream_t st)
+{
+    k_finalize_stats<<<1, 256, 0, st>>>(partials, grid, chain_ll, n_chains, A, N, stats);
+    return BHMM_OK;
+}

@@ -1,0 +1,403 @@
+// bhmm_b200/csrc/engine.cu -- C ABI, part 2: the batched, device-resident engine (bhmm_b200_batch_*).
+//
+// All trajectories of a data set are concatenated in device memory ("rows"); one call runs a whole E-step,
+// Viterbi pass or Gibbs hidden-path sweep over every trajectory.  This replaces the per-trajectory Python loops
+// of MaximumLikelihoodEstimator.fit (maximum_likelihood.py:383-385), compute_viterbi_paths (:332-352) and
+// BayesianHMMSampler._updateHiddenStateTrajectories (bayesian_sampling.py:283-291).
+#include <algorithm>
+#include <cstring>
+
+#include "host_common.h"
+#include "../../include/bhmm_b200.h"
+
+struct bhmm_b200_batch {
+    int K = 0, N = 0;
+    long long rows = 0;
+    std::vector<long long> offsets;
+    int chunk = 0, warm_f = 0, warm_b = 0;
+    HostPlan plan, segplan;
+    Arena arena;
+    bool carved = false;
+    char* cw_base = nullptr;    // where the chain work (tables, hand-over vectors) is carved
+    // carved device pointers
+    ChainWork w;
+    Chains seg{};
+    unsigned char* seg_map = nullptr;
+    int* seg_enter = nullptr;
+    long long* d_offsets = nullptr;
+    double* d_A = nullptr;
+    double* d_pi = nullptr;
+    double* d_mu = nullptr;
+    double* d_sigma = nullptr;
+    double* d_alpha = nullptr;
+    unsigned char* d_F = nullptr;
+    double* d_partials = nullptr;
+    int stats_grid = 0;
+    int* d_err = nullptr;
+    Arena disc;                 // B staging + Bt for the discrete model (sized on first use)
+    RunInfo info;
+};
+
+namespace {
+
+constexpr int SEG_FRAMES = 256;   // frames per segment of the path chase
+
+size_t batch_layout(bhmm_b200_batch* b, char* base)
+{
+    const int N = b->N;
+    const int n = b->plan.n, ns = b->segplan.n;
+    Carver cv;
+    const size_t o_offs = cv.add<long long>(b->K + 1);
+    const size_t o_cw = cv.add<char>(chainwork_bytes(n, N));
+    const size_t o_srow = cv.add<long long>(ns), o_slen = cv.add<int>(ns), o_st0 = cv.add<int>(ns), o_sT = cv.add<int>(ns);
+    const size_t o_smap = cv.add<unsigned char>((size_t)ns * N);
+    const size_t o_sent = cv.add<int>(ns);
+    const size_t o_A = cv.add<double>((size_t)N * N), o_pi = cv.add<double>(N), o_mu = cv.add<double>(N),
+                 o_sg = cv.add<double>(N);
+    b->stats_grid = backward_stats_grid(N, n);
+    const size_t o_part = cv.add<double>((size_t)b->stats_grid * ((size_t)N * N + 4 * N));
+    const size_t o_err = cv.add<int>(4);
+    const size_t o_alpha = cv.add<double>((size_t)b->rows * N);
+    const size_t o_F = cv.add<unsigned char>((size_t)b->rows * N * (N > 256 ? 2 : 1));
+    if (base) {
+        b->d_offsets = (long long*)(base + o_offs);
+        b->w = ChainWork();
+        // chain tables are uploaded by chainwork_setup into base + o_cw
+        b->seg.row0 = (const long long*)(base + o_srow);
+        b->seg.len = (const int*)(base + o_slen);
+        b->seg.t0 = (const int*)(base + o_st0);
+        b->seg.T = (const int*)(base + o_sT);
+        b->seg.n = ns;
+        b->seg_map = (unsigned char*)(base + o_smap);
+        b->seg_enter = (int*)(base + o_sent);
+        b->d_A = (double*)(base + o_A);
+        b->d_pi = (double*)(base + o_pi);
+        b->d_mu = (double*)(base + o_mu);
+        b->d_sigma = (double*)(base + o_sg);
+        b->d_partials = (double*)(base + o_part);
+        b->d_err = (int*)(base + o_err);
+        b->d_alpha = (double*)(base + o_alpha);
+        b->d_F = (unsigned char*)(base + o_F);
+        b->cw_base = base + o_cw;
+    }
+    return cv.off + 256;
+}
+
+int batch_carve(bhmm_b200_batch* b, cudaStream_t st)
+{
+    if (b->carved) return BHMM_OK;
+    const size_t need = batch_layout(b, nullptr);
+    RC_TRY(b->arena.ensure(need));
+    batch_layout(b, b->arena.base);
+    RC_TRY(chainwork_setup(b->w, b->plan, b->N, b->warm_f, b->cw_base, st));
+    const int ns = b->segplan.n;
+    CUDA_TRY(cudaMemcpyAsync(b->d_offsets, b->offsets.data(), sizeof(long long) * (b->K + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync((void*)b->seg.row0, b->segplan.row0.data(), sizeof(long long) * ns, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync((void*)b->seg.len, b->segplan.len.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync((void*)b->seg.t0, b->segplan.t0.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync((void*)b->seg.T, b->segplan.T.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->carved = true;
+    return BHMM_OK;
+}
+
+void batch_plan(bhmm_b200_batch* b, int chunk, int warm)
+{
+    const int w = warm > 0 ? warm : auto_warm(b->N);
+    b->chunk = chunk > 0 ? chunk : auto_chunk(b->rows, b->N, w);
+    b->warm_f = b->warm_b = w;
+    build_plan(b->offsets.data(), b->K, b->chunk, b->plan);
+    build_plan(b->offsets.data(), b->K, SEG_FRAMES, b->segplan);
+    b->carved = false;
+}
+
+int upload_small(double* dst, const double* src, size_t n, cudaStream_t st)
+{
+    CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    return BHMM_OK;
+}
+
+void begin_info(bhmm_b200_batch* b)
+{
+    b->info = RunInfo();
+    b->info.chains = b->plan.n;
+    b->info.chunk = b->chunk;
+    b->info.warm = b->warm_f;
+}
+
+int prepare_discrete(bhmm_b200_batch* b, const double* B, int M, Emission& em, cudaStream_t st)
+{
+    const int N = b->N;
+    RC_TRY(b->disc.ensure(sizeof(double) * 2 * (size_t)N * M + 512));
+    double* stage = (double*)b->disc.base;
+    double* Bt = stage + (((size_t)N * M + 31) & ~(size_t)31);
+    CUDA_TRY(cudaMemcpyAsync(stage, B, sizeof(double) * (size_t)N * M, cudaMemcpyHostToDevice, st));
+    RC_TRY(launch_transpose(stage, N, M, Bt, st));
+    LAUNCHED(1);
+    em.Bt = Bt;
+    em.M = M;
+    return BHMM_OK;
+}
+
+// forward + (backward & statistics with whole-pass retry) + finalize
+int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, const double* pi, double* d_gamma,
+                 double* d_stats, double* d_Bnum, cudaStream_t st)
+{
+    const int N = b->N;
+    RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
+    RC_TRY(upload_small(b->d_pi, pi, N, st));
+    b->w.ch.warm = b->warm_f;
+    RC_TRY(run_forward(b->w, em, emkind, N, b->d_A, b->d_pi, b->d_alpha, b->info, st));
+    if (b->info.fix_f > 0) b->warm_f = std::min(std::max(b->plan.maxT, 1), b->warm_f * 2);   // adapt for the next call
+
+    for (int attempt = 0;; ++attempt) {
+        BwdArgs a{};
+        a.ch = b->w.ch;
+        a.ch.list = nullptr; a.ch.n = b->w.n_total; a.ch.exact = 0; a.ch.warm = b->warm_b;
+        a.em = em; a.N = N; a.grid = b->stats_grid; a.A = b->d_A;
+        a.alpha = b->d_alpha; a.gamma = d_gamma; a.Bnum = d_Bnum; a.partials = b->d_partials;
+        a.hand_used = b->w.hu_b; a.hand_end = b->w.he_b;
+        if (d_Bnum) CUDA_TRY(cudaMemsetAsync(d_Bnum, 0, sizeof(double) * (size_t)N * em.M, st));
+        RC_TRY(launch_backward_team(a, emkind, true, st));
+        LAUNCHED(1);
+        if (!b->w.chunked) break;
+        const long long nfail = certify_sync(b->w, N, -1, &b->info.worst_b, st);
+        if (nfail < 0) { bhmm_set_error(BHMM_ERR_CUDA, cudaGetErrorString(cudaGetLastError())); return BHMM_ERR_CUDA; }
+        if (nfail == 0) break;
+        // statistics of a failed pass cannot be patched chain by chain: widen the warm-up and redo the pass.
+        // warm_b >= longest trajectory makes every chain start from the exact end condition, so this terminates.
+        if (b->warm_b >= b->plan.maxT) { bhmm_set_error(BHMM_ERR_NOT_CERTIFIED, "backward hand-overs not certified"); return BHMM_ERR_NOT_CERTIFIED; }
+        b->warm_b = std::min(b->plan.maxT, b->warm_b * 2);
+        b->info.fix_b += 1;
+        b->info.rerun += (double)b->w.n_total;
+        if (attempt > 40) return BHMM_ERR_NOT_CERTIFIED;
+    }
+    RC_TRY(launch_finalize_stats(b->d_partials, b->stats_grid, b->w.chain_ll, b->w.n_total, b->d_A, N, d_stats, st));
+    LAUNCHED(1);
+    b->info.warm = std::max(b->warm_f, b->warm_b);
+    return BHMM_OK;
+}
+
+int finish_stream(cudaStream_t st)
+{
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { bhmm_set_error(BHMM_ERR_CUDA, cudaGetErrorString(e)); return BHMM_ERR_CUDA; }
+    return BHMM_OK;
+}
+
+int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, const double* pi, const double* d_u,
+                 unsigned long long seed, unsigned long long sweep, int* d_path, long long* d_counts, double* d_sums,
+                 double* loglik_host, cudaStream_t st)
+{
+    const int N = b->N;
+    if (N > 256) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "sampling supports N <= 256"); return BHMM_ERR_UNSUPPORTED; }
+    RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
+    RC_TRY(upload_small(b->d_pi, pi, N, st));
+    b->w.ch.warm = b->warm_f;
+    RC_TRY(run_forward(b->w, em, emkind, N, b->d_A, b->d_pi, b->d_alpha, b->info, st));
+    if (b->info.fix_f > 0) b->warm_f = std::min(std::max(b->plan.maxT, 1), b->warm_f * 2);
+    CUDA_TRY(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
+    if (d_u) RC_TRY(launch_sample_table(b->d_alpha, b->d_A, d_u, b->d_offsets, b->K, N, b->rows, b->d_F, b->d_err, st));
+    else RC_TRY(launch_sample_table_philox(b->d_alpha, b->d_A, seed, sweep, b->d_offsets, b->K, N, b->rows, b->d_F, b->d_err, st));
+    RC_TRY(launch_chase(b->d_F, b->seg, N, b->seg_map, b->seg_enter, d_path, st));
+    LAUNCHED(4);
+    CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(long long) * ((size_t)N * N + 2 * N), st));
+    if (d_sums) CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * N, st));
+    RC_TRY(launch_path_stats(d_path, d_sums ? em.obs : nullptr, b->d_offsets, b->K, N, b->rows, d_counts,
+                             d_counts + (size_t)N * N, d_counts + (size_t)N * N + N, d_sums, d_sums ? d_sums + N : nullptr,
+                             st));
+    LAUNCHED(1);
+    std::vector<double> ll(b->w.n_total);
+    int err = 0;
+    CUDA_TRY(cudaMemcpyAsync(ll.data(), b->w.chain_ll, sizeof(double) * b->w.n_total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RC_TRY(finish_stream(st));
+    if (err) { bhmm_set_error(err, "sample_path: no state could be drawn"); return err; }
+    double s = 0.0;
+    for (double v : ll) s += v;
+    if (loglik_host) *loglik_host = s;
+    return BHMM_OK;
+}
+
+}  // namespace
+
+extern "C" int bhmm_b200_stats_len_gaussian(int N) { return 1 + N + N * N + 3 * N; }
+extern "C" int bhmm_b200_stats_len_discrete(int N) { return 1 + N + N * N + 3 * N; }
+
+extern "C" int bhmm_b200_batch_create(bhmm_b200_batch** out, const long long* offsets, int K, int N, int chunk,
+                                      int warm)
+{
+    bhmm_set_error(BHMM_OK, "");
+    if (!out || !offsets || K < 1 || N < 1 || N > 1024) { bhmm_set_error(BHMM_ERR_INVALID, "bad batch arguments"); return BHMM_ERR_INVALID; }
+    for (int k = 0; k < K; ++k)
+        if (offsets[k + 1] <= offsets[k] || offsets[k + 1] - offsets[k] > 2000000000LL) {
+            bhmm_set_error(BHMM_ERR_INVALID, "trajectories must be non-empty and shorter than 2e9 frames");
+            return BHMM_ERR_INVALID;
+        }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        bhmm_set_error(BHMM_ERR_CUDA, "no CUDA device available (bhmm_b200 has no CPU fallback)");
+        return BHMM_ERR_CUDA;
+    }
+    bhmm_b200_batch* b = new bhmm_b200_batch();
+    b->K = K; b->N = N;
+    b->offsets.assign(offsets, offsets + K + 1);
+    b->rows = offsets[K] - offsets[0];
+    if (offsets[0] != 0) { delete b; bhmm_set_error(BHMM_ERR_INVALID, "offsets[0] must be 0"); return BHMM_ERR_INVALID; }
+    batch_plan(b, chunk, warm);
+    *out = b;
+    return BHMM_OK;
+}
+
+extern "C" void bhmm_b200_batch_destroy(bhmm_b200_batch* b)
+{
+    if (!b) return;
+    b->arena.release();
+    b->disc.release();
+    delete b;
+}
+
+extern "C" int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm)
+{
+    if (!b) return BHMM_ERR_INVALID;
+    batch_plan(b, chunk, warm);
+    return BHMM_OK;
+}
+
+extern "C" size_t bhmm_b200_batch_workspace_bytes(const bhmm_b200_batch* b)
+{
+    return batch_layout(const_cast<bhmm_b200_batch*>(b), nullptr);
+}
+
+extern "C" int bhmm_b200_batch_attach_workspace(bhmm_b200_batch* b, void* d_workspace, size_t bytes)
+{
+    if (!b || !d_workspace) return BHMM_ERR_INVALID;
+    b->arena.release();
+    b->arena.base = (char*)d_workspace;
+    b->arena.cap = bytes;
+    b->arena.owned = false;
+    b->carved = false;
+    return BHMM_OK;
+}
+
+extern "C" void bhmm_b200_batch_info(const bhmm_b200_batch* b, double info[8])
+{
+    info[0] = b->info.chains; info[1] = b->info.chunk; info[2] = b->info.warm; info[3] = b->info.fix_f;
+    info[4] = b->info.fix_b; info[5] = b->info.worst_f; info[6] = b->info.worst_b; info[7] = b->info.rerun;
+}
+
+extern "C" int bhmm_b200_estep_gaussian(bhmm_b200_batch* b, const double* d_obs, const double* A, const double* pi,
+                                        const double* means, const double* sigmas, int ignore_outliers,
+                                        double* d_gamma, double* d_stats, void* stream)
+{
+    bhmm_set_error(BHMM_OK, "");
+    cudaStream_t st = (cudaStream_t)stream;
+    RC_TRY(batch_carve(b, st));
+    begin_info(b);
+    RC_TRY(upload_small(b->d_mu, means, b->N, st));
+    RC_TRY(upload_small(b->d_sigma, sigmas, b->N, st));
+    Emission em{};
+    em.obs = d_obs; em.mu = b->d_mu; em.sigma = b->d_sigma; em.ignore_outliers = ignore_outliers;
+    RC_TRY(estep_common(b, em, EM_GAUSS, A, pi, d_gamma, d_stats, nullptr, st));
+    return finish_stream(st);
+}
+
+extern "C" int bhmm_b200_estep_discrete(bhmm_b200_batch* b, const int* d_obs, const double* A, const double* pi,
+                                        const double* B, int M, int ignore_outliers, double* d_gamma,
+                                        double* d_stats, double* d_Bnum, void* stream)
+{
+    bhmm_set_error(BHMM_OK, "");
+    cudaStream_t st = (cudaStream_t)stream;
+    RC_TRY(batch_carve(b, st));
+    begin_info(b);
+    Emission em{};
+    em.sym = d_obs; em.ignore_outliers = ignore_outliers;
+    RC_TRY(prepare_discrete(b, B, M, em, st));
+    RC_TRY(estep_common(b, em, EM_DISC, A, pi, d_gamma, d_stats, d_Bnum, st));
+    return finish_stream(st);
+}
+
+static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, const double* pi,
+                          int* d_path, cudaStream_t st)
+{
+    const int N = b->N;
+    RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
+    RC_TRY(upload_small(b->d_pi, pi, N, st));
+    VitArgs a{};
+    a.em = em; a.N = N; a.K = b->K; a.offsets = b->d_offsets; a.A = b->d_A; a.pi = b->d_pi;
+    a.backptr = b->d_F; a.path = d_path;
+    RC_TRY(launch_viterbi_team(a, emkind, st));
+    LAUNCHED(1);
+    return finish_stream(st);
+}
+
+extern "C" int bhmm_b200_viterbi_gaussian(bhmm_b200_batch* b, const double* d_obs, const double* A, const double* pi,
+                                          const double* means, const double* sigmas, int ignore_outliers,
+                                          int* d_path, void* stream)
+{
+    bhmm_set_error(BHMM_OK, "");
+    cudaStream_t st = (cudaStream_t)stream;
+    RC_TRY(batch_carve(b, st));
+    begin_info(b);
+    RC_TRY(upload_small(b->d_mu, means, b->N, st));
+    RC_TRY(upload_small(b->d_sigma, sigmas, b->N, st));
+    Emission em{};
+    em.obs = d_obs; em.mu = b->d_mu; em.sigma = b->d_sigma; em.ignore_outliers = ignore_outliers;
+    return viterbi_common(b, em, EM_GAUSS, A, pi, d_path, st);
+}
+
+extern "C" int bhmm_b200_viterbi_discrete(bhmm_b200_batch* b, const int* d_obs, const double* A, const double* pi,
+                                          const double* B, int M, int ignore_outliers, int* d_path, void* stream)
+{
+    bhmm_set_error(BHMM_OK, "");
+    cudaStream_t st = (cudaStream_t)stream;
+    RC_TRY(batch_carve(b, st));
+    begin_info(b);
+    Emission em{};
+    em.sym = d_obs; em.ignore_outliers = ignore_outliers;
+    RC_TRY(prepare_discrete(b, B, M, em, st));
+    return viterbi_common(b, em, EM_DISC, A, pi, d_path, st);
+}
+
+extern "C" int bhmm_b200_gibbs_gaussian(bhmm_b200_batch* b, const double* d_obs, const double* A, const double* pi,
+                                        const double* means, const double* sigmas, int ignore_outliers,
+                                        const double* d_u, unsigned long long seed, unsigned long long sweep,
+                                        int* d_path, long long* d_counts, double* d_sums, double* loglik_host,
+                                        void* stream)
+{
+    bhmm_set_error(BHMM_OK, "");
+    cudaStream_t st = (cudaStream_t)stream;
+    RC_TRY(batch_carve(b, st));
+    begin_info(b);
+    RC_TRY(upload_small(b->d_mu, means, b->N, st));
+    RC_TRY(upload_small(b->d_sigma, sigmas, b->N, st));
+    Emission em{};
+    em.obs = d_obs; em.mu = b->d_mu; em.sigma = b->d_sigma; em.ignore_outliers = ignore_outliers;
+    return gibbs_common(b, em, EM_GAUSS, A, pi, d_u, seed, sweep, d_path, d_counts, d_sums, loglik_host, st);
+}
+
+extern "C" int bhmm_b200_gibbs_discrete(bhmm_b200_batch* b, const int* d_obs, const double* A, const double* pi,
+                                        const double* B, int M, int ignore_outliers, const double* d_u,
+                                        unsigned long long seed, unsigned long long sweep, int* d_path,
+                                        long long* d_counts, double* loglik_host, void* stream)
+{
+    bhmm_set_error(BHMM_OK, "");
+    cudaStream_t st = (cudaStream_t)stream;
+    RC_TRY(batch_carve(b, st));
+    begin_info(b);
+    Emission em{};
+    em.sym = d_obs; em.ignore_outliers = ignore_outliers;
+    RC_TRY(prepare_discrete(b, B, M, em, st));
+    return gibbs_common(b, em, EM_DISC, A, pi, d_u, seed, sweep, d_path, d_counts, nullptr, loglik_host, st);
+}
+
+extern "C" int bhmm_b200_path_symbol_histogram(const int* d_path, const int* d_obs, long long rows, int N, int M,
+                                               long long* d_hist, void* stream)
+{
+    bhmm_set_error(BHMM_OK, "");
+    RC_TRY(launch_symbol_histogram(d_path, d_obs, rows, N, M, d_hist, (cudaStream_t)stream));
+    LAUNCHED(1);
+    return finish_stream((cudaStream_t)stream);
+}

@@ -1,0 +1,92 @@
+// bhmm_b200/csrc/host_common.h -- host-side plumbing shared by capi.cu (literal API) and engine.cu (batched engine).
+#pragma once
+#include <atomic>
+#include <mutex>
+#include <vector>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+extern std::atomic<unsigned long long> g_launches;
+extern double g_cert_tol;
+#define LAUNCHED(n) (g_launches.fetch_add((unsigned long long)(n), std::memory_order_relaxed))
+
+#define RC_TRY(expr)                        \
+    do {                                    \
+        int rc_ = (expr);                   \
+        if (rc_ != BHMM_OK) { bhmm_set_error(rc_, #expr); return rc_; } \
+    } while (0)
+
+// Grow-only device buffer carved into aligned pieces.  Either owned (cudaMalloc) or attached (caller memory).
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0;
+    bool owned = true;
+    int ensure(size_t bytes);
+    void release();
+};
+
+struct Carver {
+    size_t off = 0;
+    template <typename T>
+    size_t add(size_t n)
+    {
+        off = (off + 255) & ~(size_t)255;
+        const size_t o = off;
+        off += n * sizeof(T);
+        return o;
+    }
+};
+
+// Chain table on the host: trajectories cut into chains of `chunk` frames, ordered by (trajectory, t0).
+struct HostPlan {
+    std::vector<long long> row0;
+    std::vector<int> len, t0, T;
+    int n = 0;
+    int maxT = 0;
+    bool chunked = false;       // some chain does not start its trajectory
+};
+void build_plan(const long long* offsets, int K, int chunk, HostPlan& p);
+int auto_warm(int N);
+int auto_chunk(long long rows, int N, int warm);
+
+// Device scratch that belongs to one plan.
+struct ChainWork {
+    Chains ch{};                 // full table (list = NULL, n = all chains)
+    int n_total = 0;
+    bool chunked = false;
+    double* chain_ll = nullptr;
+    double* hu_f = nullptr;      // forward hand-over used / end
+    double* he_f = nullptr;
+    double* hu_b = nullptr;      // backward hand-over used / end
+    double* he_b = nullptr;
+    int* fail_list = nullptr;
+    unsigned long long* cert_out = nullptr;   // device [n_fail, worst bits]
+};
+size_t chainwork_bytes(int n_chains, int N);
+// carve ChainWork out of `base` (device) and upload the plan; returns bytes used
+int chainwork_setup(ChainWork& w, const HostPlan& p, int N, int warm, char* base, cudaStream_t st);
+
+struct RunInfo {
+    double chains = 0, chunk = 0, warm = 0, fix_f = 0, fix_b = 0, worst_f = 0, worst_b = 0, rerun = 0;
+};
+
+// forward over all chains + certification with exact fix-up sweeps.  alpha may be NULL.
+int run_forward(ChainWork& w, const Emission& em, int emkind, int N, const double* dA, const double* dpi,
+                double* d_alpha, RunInfo& info, cudaStream_t st);
+// literal backward (beta written) + certification with exact fix-up sweeps.
+int run_backward(ChainWork& w, const Emission& em, int emkind, int N, const double* dA, double* d_beta,
+                 RunInfo& info, cudaStream_t st);
+// certification read-back: returns number of failing chains (or <0 on CUDA error), updates worst
+long long certify_sync(ChainWork& w, int N, int dir, double* worst, cudaStream_t st);
+
+// glibc srand()/rand() restatement (TYPE_3, r[i] = r[i-31] + r[i-3]); reproduces the reference's uniforms
+struct GlibcRand {
+    uint32_t ring[34];
+    long pos = 0;               // index of the next r[] to produce
+    GlibcRand() { seed(1); }
+    void seed(unsigned int s);
+    int next();                 // like rand(): 31-bit
+    double uniform() { return (double)next() / (2147483647.0 + 1.0); }
+};

@@ -1,0 +1,93 @@
+// bhmm_b200/csrc/kernels.h -- internal launch interface between the C ABI (capi.cu) and the kernels.
+#pragma once
+#include "common.cuh"
+
+struct FwdArgs {
+    Chains ch;
+    Emission em;
+    int N;
+    int cpb;                 // chains per block (filled by the launcher)
+    const double* A;         // (N,N) row-major, device
+    const double* pi;        // (N), device
+    double* alpha;           // (rows,N) row-major output, or NULL
+    double* chain_ll;        // per chain: sum of log c_t over the chain's own frames
+    double* hand_used;       // (n_chains_total, N): alpha_{t0-1} the chain was started from
+    double* hand_end;        // (n_chains_total, N): the chain's own last alpha row
+};
+
+struct BwdArgs {
+    Chains ch;
+    Emission em;
+    int N;
+    int cpb;
+    int grid;                // STATS: number of blocks (= rows of `partials`)
+    const double* A;
+    double* beta;            // literal backward: (rows,N) output
+    const double* alpha;     // STATS: (rows,N) forward variables
+    double* gamma;           // STATS: optional (rows,N) state probabilities output
+    double* Bnum;            // STATS + EM_DISC: (N,M) B-numerator, accumulated with atomics
+    double* partials;        // STATS: (grid, N*N+4N) per-block partial statistics
+    double* hand_used;       // (n_chains_total, N): beta_e the chain entered with (e = first frame after the chain)
+    double* hand_end;        // (n_chains_total, N): the chain's own beta at its first frame
+};
+
+struct VitArgs {
+    Emission em;
+    int N;
+    int cpb;
+    int K;                   // trajectories
+    const long long* offsets;  // (K+1) row offsets, device
+    const double* A;
+    const double* pi;
+    void* backptr;           // (rows, N) uint8 (N <= 256) or uint16
+    int* path;               // (rows) int32 output
+};
+
+void team_shape(int N, int* threads, int* cpb);
+int launch_forward_team(const FwdArgs& a, int em, cudaStream_t st);
+int launch_backward_team(const BwdArgs& a, int em, bool stats, cudaStream_t st);
+int backward_stats_grid(int N, int n_chains);
+int launch_viterbi_team(const VitArgs& a, int em, cudaStream_t st);
+
+// ---- frame-parallel kernels (frame_kernels.cu)
+int launch_gaussian_pobs(const double* obs, const double* mu, const double* sigma, int N, long long rows,
+                         int ignore_outliers, double* pobs, cudaStream_t st);
+int launch_discrete_pobs(const int* sym, const double* Bt, int N, int M, long long rows, int ignore_outliers,
+                         double* pobs, cudaStream_t st);
+int launch_state_probabilities(const double* alpha, const double* beta, int N, long long rows, double* gamma,
+                               cudaStream_t st);
+// column sums of a (rows,N) table; scratch holds blocks*N doubles
+int launch_state_counts(const double* gamma, int N, long long rows, double* counts, double* scratch, int* blocks,
+                        cudaStream_t st);
+int state_counts_blocks(long long rows);
+// literal transition_counts for ONE trajectory of T frames; scratch holds blocks*N*N doubles
+int launch_transition_counts(const double* alpha, const double* beta, const double* A, const double* pobs, int N,
+                             int T, double* C, double* scratch, cudaStream_t st);
+int transition_counts_blocks(int T);
+int launch_update_pout(const int* sym, const double* w, long long rows, int N, int M, double* pout, cudaStream_t st);
+int launch_transpose(const double* in, int R, int Cc, double* out, cudaStream_t st);
+
+// ---- certification of chain hand-overs (certify.cu)
+// dir = +1 forward (chain c against c-1), -1 backward (chain c against c+1).
+// out[0] = number of failing chains, out[1] = bits of the largest mismatch seen; fail_list receives the ids.
+int launch_certify(const Chains& ch, int n_total, int N, int dir, const double* hand_used, const double* hand_end,
+                   double tol, int* fail_list, unsigned long long* out, cudaStream_t st);
+// deterministic reduction of the E-step: stats = [loglik | gamma0 (N) | C (N*N) | sum gamma | sum gamma d | sum gamma d^2]
+int launch_finalize_stats(const double* partials, int grid, const double* chain_ll, int n_chains, const double* A,
+                          int N, double* stats, cudaStream_t st);
+
+// ---- forward-filter / backward-sample and path statistics (sample_kernels.cu)
+// choice table F[row][s'] = state drawn at `row` given the next frame's state s' and the frame's uniform.
+int launch_sample_table(const double* alpha, const double* A, const double* u, const long long* offsets, int K,
+                        int N, long long rows, unsigned char* F, int* err, cudaStream_t st);
+// philox variant: uniforms generated on device from (seed, row)
+int launch_sample_table_philox(const double* alpha, const double* A, unsigned long long seed, unsigned long long ctr,
+                               const long long* offsets, int K, int N, long long rows, unsigned char* F, int* err,
+                               cudaStream_t st);
+// segment table `seg` has the chain-table layout (row0, len, t0, T), ordered by (trajectory, t0)
+int launch_chase(const unsigned char* F, const Chains& seg, int N, unsigned char* seg_map, int* seg_enter, int* path,
+                 cudaStream_t st);
+int launch_path_stats(const int* path, const double* obs, const long long* offsets, int K, int N, long long rows,
+                      long long* Cint, long long* n0, long long* cnt, double* so, double* soo, cudaStream_t st);
+int launch_symbol_histogram(const int* path, const int* sym, long long rows, int N, int M, long long* hist,
+                            cudaStream_t st);

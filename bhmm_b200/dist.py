@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing: trajectories are independent given the model (maximum_likelihood.py:383-385,
+bayesian_sampling.py:288-290), so they are partitioned across ranks -- contiguous blocks balanced by frame count, one
+block per GPU, resident for the whole fit -- and the only exchange per iteration is ONE sum-all-reduce of the packed
+sufficient statistics (1 + N + N^2 + 3N doubles; plus the N x M B-numerator for discrete models).  The reference
+has no counterpart (single process).  One process per GPU; torch.distributed (NCCL on GPUs, gloo in CPU tests) is
+the transport."""
+import numpy as np
+
+
+def _td():
+    import torch.distributed as td
+    return td
+
+
+def initialized():
+    td = _td()
+    return td.is_available() and td.is_initialized()
+
+
+def rank():
+    return _td().get_rank() if initialized() else 0
+
+
+def world_size():
+    return _td().get_world_size() if initialized() else 1
+
+
+def shard_bounds(lengths, r, world):
+    """Contiguous block [lo, hi) of trajectories for rank r, cut where the cumulative frame count crosses
+    r/world of the total.  Deterministic, covers every trajectory exactly once; a rank may get an empty block
+    when there are fewer trajectories than ranks."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    K = len(lengths)
+    if world <= 1:
+        return 0, K
+    cum = np.concatenate([[0], np.cumsum(lengths)])
+    total = cum[-1]
+    # boundary b (1..world-1): first trajectory index whose start offset is >= b*total/world (rounded to nearest)
+    cuts = [0]
+    for b in range(1, world):
+        target = total * b / float(world)
+        k = int(np.searchsorted(cum, target, side='left'))
+        if k > 0 and k <= K and (target - cum[k - 1]) < (cum[min(k, K)] - target):
+            k -= 1
+        cuts.append(min(max(k, cuts[-1]), K))
+    cuts.append(K)
+    return cuts[r], cuts[r + 1]
+
+
+def allreduce_sum(tensor):
+    """In-place sum over ranks of a (device) tensor; identity when torch.distributed is not initialised."""
+    if initialized() and world_size() > 1:
+        _td().all_reduce(tensor, op=_td().ReduceOp.SUM)
+    return tensor

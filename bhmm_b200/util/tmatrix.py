@@ -1,0 +1,120 @@
+"""Transition-matrix M-step helpers (host, N x N): the part of bhmm/estimators/_tmatrix_disconnected.py the EM and
+Gibbs iterations reach, written without msmtools (which the reference imports for every one of these).
+
+Parity status: the NON-reversible estimator (C / rowsum on weakly connected sets, _tmatrix_disconnected.py:106-115)
+is pinned by tests/golden/em_*.npz.  The reversible estimator is a from-scratch fixed-point iteration of the
+detailed-balance MLE; the reference delegates it to an absent, un-pinned msmtools, so it is PARITY-UNPINNED
+ and tested only through its defining properties.
+"""
+import numpy as np
+from scipy.sparse import csr_matrix
+from scipy.sparse.csgraph import connected_components
+
+
+def connected_sets(C, mincount_connectivity=0, strong=True):
+    """Connected sets of the count graph, largest first (_tmatrix_disconnected.py:27-43)."""
+    Cconn = np.array(C, dtype=float)
+    Cconn[np.where(Cconn <= mincount_connectivity)] = 0
+    n, labels = connected_components(csr_matrix(Cconn > 0), directed=True, connection='strong' if strong else 'weak')
+    sets = [np.where(labels == k)[0] for k in range(n)]
+    sets.sort(key=lambda s: -len(s))
+    return sets
+
+
+def is_connected(C, mincount_connectivity=0, strong=True):
+    return len(connected_sets(C, mincount_connectivity=mincount_connectivity, strong=strong)) == 1
+
+
+def is_transition_matrix(T, tol=1e-10):
+    T = np.asarray(T)
+    return bool(T.ndim == 2 and T.shape[0] == T.shape[1] and np.all(T >= -tol)
+                and np.allclose(T.sum(axis=1), 1.0, atol=1e-8))
+
+
+def stationary_vector(P):
+    """Stationary distribution of a connected stochastic matrix (dense eigen-decomposition)."""
+    P = np.asarray(P, dtype=float)
+    if P.shape[0] == 1:
+        return np.ones(1)
+    w, v = np.linalg.eig(P.T)
+    k = np.argmax(w.real)
+    mu = np.abs(v[:, k].real)
+    return mu / mu.sum()
+
+
+def stationary_distribution(P, C=None, mincount_connectivity=0):
+    """Stationary distribution, weighting disconnected sets by their counts (_tmatrix_disconnected.py:229-251)."""
+    if C is None:
+        if is_connected(P, strong=True):
+            return stationary_vector(P)
+        raise ValueError('Computing stationary distribution for disconnected matrix. Need count matrix.')
+    n = np.shape(C)[0]
+    ctot = np.sum(C)
+    pi = np.zeros(n)
+    for s in connected_sets(C, mincount_connectivity=mincount_connectivity, strong=False):
+        w = np.sum(C[s, :]) / ctot
+        pi[s] = w * stationary_vector(P[s, :][:, s])
+    return pi / np.sum(pi)
+
+
+def is_reversible(P):
+    """Detailed balance on every weakly connected set (_tmatrix_disconnected.py:211-226)."""
+    P = np.asarray(P, dtype=float)
+    for s in connected_sets(P, strong=False):
+        Ps = P[s, :][:, s]
+        if not is_transition_matrix(Ps):
+            return False
+        pi = stationary_vector(Ps)
+        X = pi[:, None] * Ps
+        if not np.allclose(X, X.T):
+            return False
+    return True
+
+
+def transition_matrix_reversible(C, maxiter=1000000, maxerr=1e-12):
+    """Reversible maximum-likelihood transition matrix of a strongly connected count matrix by the classical
+    fixed-point iteration x_ij <- (c_ij + c_ji) / (c_i / x_i + c_j / x_j).  PARITY-UNPINNED (see module doc)."""
+    C = np.asarray(C, dtype=float)
+    Csym = C + C.T
+    ci = C.sum(axis=1)
+    X = Csym.copy()
+    X /= X.sum()
+    pi_old = X.sum(axis=1)
+    for _ in range(int(maxiter)):
+        xi = X.sum(axis=1)
+        q = ci / xi
+        denom = q[:, None] + q[None, :]
+        X = np.where(denom > 0, Csym / np.where(denom > 0, denom, 1.0), 0.0)
+        X /= X.sum()
+        pi_new = X.sum(axis=1)
+        if np.max(np.abs(pi_new - pi_old)) < maxerr:
+            break
+        pi_old = pi_new
+    return X / X.sum(axis=1)[:, None]
+
+
+def estimate_P(C, reversible=True, fixed_statdist=None, maxiter=1000000, maxerr=1e-8, mincount_connectivity=0):
+    """Full transition matrix for general connectivity (_tmatrix_disconnected.py:68-123)."""
+    C = np.array(C, dtype=float)
+    n = C.shape[0]
+    P = np.eye(n, dtype=np.float64)
+    if fixed_statdist is not None:
+        raise NotImplementedError('estimation with a fixed stationary distribution is not part of the hot path')
+    if reversible:
+        for s in connected_sets(C, mincount_connectivity=mincount_connectivity, strong=True):
+            mask = np.zeros(n, dtype=bool)
+            mask[s] = True
+            if C[np.ix_(mask, ~mask)].sum() > np.finfo(C.dtype).eps:
+                raise NotImplementedError('partially reversible estimation (transient sets) is not implemented; '
+                                          'use reversible=False')
+            if s.size > 1:
+                I = np.ix_(mask, mask)
+                P[I] = transition_matrix_reversible(C[I], maxiter=maxiter, maxerr=maxerr)
+    else:
+        for s in connected_sets(C, mincount_connectivity=mincount_connectivity, strong=False):
+            I = np.ix_(s, s)
+            Csub = C[I]
+            zero_rows = np.where(Csub.sum(axis=1) == 0)[0]
+            Csub[zero_rows, zero_rows] = 1.0
+            P[I] = Csub / Csub.sum(axis=1)[:, None]
+    return P

@@ -1,0 +1,172 @@
+/*
+ * include/bhmm_b200.h -- C ABI of libbhmm_b200.so, the B200 (sm_100a) implementation of the bhmm HMM
+ * dynamic-programming hot path.
+ *
+ * Plain C: pointers and sizes only, no torch / numpy types.  Three groups of entry points:
+ *
+ *  (1) HOST-pointer drop-ins.  Same argument lists, layouts (C-contiguous float64, (T,N) time-major, int32 paths)
+ *      and meaning as the functions the reference's Cython wrappers bind, so a maintainer can point
+ *      bhmm/hidden/impl_c/hidden.pyx at them by changing the `cdef extern` block.  They copy
+ *      the inputs to the GPU, run the kernels, copy the outputs back and return when the host arrays are valid.
+ *
+ *        reference symbol (bhmm/hidden/impl_c/_hidden.h)           replacement
+ *        ---------------------------------------------------------------------------------------------
+ *        double _forward(alpha,A,pobs,pi,N,T)            :10-16    bhmm_b200_forward
+ *        void   _backward(beta,A,pobs,N,T)               :18-23    bhmm_b200_backward
+ *        void   _computeGamma(gamma,alpha,beta,N,T)      :25-30    bhmm_b200_state_probabilities
+ *               (dead in C; live numpy code is bhmm/hidden/api.py:133-188)
+ *        (numpy) state_counts, bhmm/hidden/api.py:191-211          bhmm_b200_state_counts
+ *        int    _compute_transition_counts(C,A,pobs,alpha,beta,N,T) :38-45   bhmm_b200_transition_counts
+ *        int    _compute_viterbi(path,A,pobs,pi,N,T)     :47-52    bhmm_b200_viterbi
+ *        int    _sample_path(path,alpha,A,pobs,N,T)      :54-60    bhmm_b200_sample_path
+ *        void   set_seed(seed)                           :63       bhmm_b200_set_seed
+ *        void   _p_obs(o,mus,sigmas,N,T,p)   output_models/impl_c/_gaussian.h:5   bhmm_b200_gaussian_p_obs
+ *        void   _update_pout(obs,weights,T,N,M,pout)  output_models/impl_c/_discrete.c:1  bhmm_b200_discrete_update_pout
+ *
+ *      Functions that return double/void in the reference keep that shape; their status is read with
+ *      bhmm_b200_last_error().  Nothing here ever calls exit() (the reference does, _hidden.c:299-304).
+ *
+ *  (2) DEVICE-pointer variants (suffix _dev) of the same functions for callers whose arrays already live in
+ *      GPU memory (torch tensors: pass tensor.data_ptr()).  `stream` is a cudaStream_t passed as void*.
+ *
+ *  (3) The batched, device-resident engine (bhmm_b200_batch_*): all trajectories of a data set stay on the GPU,
+ *      one call runs a whole E-step (emission + forward + backward + statistics), a Viterbi pass or a Gibbs
+ *      hidden-path sweep over every trajectory.  This is what MaximumLikelihoodEstimator._forward_backward
+ *      (maximum_likelihood.py:221-282) and BayesianHMMSampler._updateHiddenStateTrajectories
+ *      (bayesian_sampling.py:283-331) loop over, one trajectory at a time, in the reference.
+ *
+ * There is no CPU fallback: every entry point fails with BHMM_B200_ERR_CUDA when no device is usable.
+ */
+#ifndef BHMM_B200_H
+#define BHMM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BHMM_B200_OK 0
+#define BHMM_B200_ERR_INVALID 1
+#define BHMM_B200_ERR_NO_MEM 2         /* == _BHMM_ERR_NO_MEM (bhmm/hidden/impl_c/_hidden.h:5) -> MemoryError */
+#define BHMM_B200_ERR_SAMPLE 3         /* no state could be drawn (p not normalisable) */
+#define BHMM_B200_ERR_CUDA 4
+#define BHMM_B200_ERR_UNSUPPORTED 5
+#define BHMM_B200_ERR_NOT_CERTIFIED 6  /* chain hand-overs could not be certified (never observed) */
+
+/* ---- library state ------------------------------------------------------------------------------ */
+int bhmm_b200_last_error(void);                 /* status of the last call made by this thread */
+const char* bhmm_b200_last_error_string(void);
+const char* bhmm_b200_version(void);
+int bhmm_b200_device_count(void);
+/* Counters of kernels launched by this library since load (bench.py reports them as gpu_launches). */
+unsigned long long bhmm_b200_launch_count(void);
+/* Time-chunking policy of the literal API: frames per chain and warm-up frames (0 = automatic). */
+void bhmm_b200_set_chunking(int chunk, int warm);
+/* Relative hand-over tolerance used by the certification (default 1e-13). */
+void bhmm_b200_set_certify_tolerance(double tol);
+/* Diagnostics of the last chunked call: info[0]=chains, [1]=chunk, [2]=warm, [3]=fix-up sweeps (fwd),
+ * [4]=fix-up sweeps (bwd), [5]=largest hand-over mismatch fwd, [6]= ... bwd, [7]=chains re-run. */
+void bhmm_b200_last_info(double info[8]);
+
+/* ---- (1) host-pointer drop-ins ------------------------------------------------------------------ */
+double bhmm_b200_forward(double* alpha, const double* A, const double* pobs, const double* pi, int N, int T);
+void bhmm_b200_backward(double* beta, const double* A, const double* pobs, int N, int T);
+int bhmm_b200_state_probabilities(double* gamma, const double* alpha, const double* beta, int N, int T);
+int bhmm_b200_state_counts(double* counts, const double* gamma, int N, int T);
+int bhmm_b200_transition_counts(double* C, const double* A, const double* pobs, const double* alpha,
+                                const double* beta, int N, int T);
+int bhmm_b200_viterbi(int* path, const double* A, const double* pobs, const double* pi, int N, int T);
+/* Uniforms come from the library's restatement of glibc srand()/rand() (r = rand()/(RAND_MAX+1.0)), so a
+ * given seed reproduces the reference's draws; pobs is accepted and ignored like in the reference. */
+int bhmm_b200_sample_path(int* path, const double* alpha, const double* A, const double* pobs, int N, int T);
+void bhmm_b200_set_seed(int seed);              /* seed >= 0: srand(seed); seed < 0: srand(time(NULL)) */
+/* Same with caller-supplied uniforms in draw order (u[0] is used for t = T-1). */
+int bhmm_b200_sample_path_u(int* path, const double* alpha, const double* A, const double* u, int N, int T);
+/* Fills n uniforms of the emulated glibc stream after srand(seed) (does not touch the library's stream). */
+void bhmm_b200_glibc_uniforms(int seed, long n, double* u);
+
+void bhmm_b200_gaussian_p_obs(const double* o, const double* mus, const double* sigmas, int N, int T, double* p);
+/* p_obs followed by the outlier rule of OutputModel._handle_outliers (outputmodel.py:119-131). */
+int bhmm_b200_gaussian_p_obs_outliers(const double* o, const double* mus, const double* sigmas, int N, int T,
+                                      int ignore_outliers, double* p);
+int bhmm_b200_discrete_p_obs(const int* obs, const double* B, int N, int M, int T, int ignore_outliers, double* p);
+void bhmm_b200_discrete_update_pout(const int* obs, const double* weights, int T, int N, int M, double* pout);
+
+/* ---- (2) device-pointer variants ---------------------------------------------------------------- */
+int bhmm_b200_forward_dev(double* d_alpha, const double* d_A, const double* d_pobs, const double* d_pi, int N,
+                          int T, double* logprob_host, void* stream);
+int bhmm_b200_backward_dev(double* d_beta, const double* d_A, const double* d_pobs, int N, int T, void* stream);
+int bhmm_b200_state_probabilities_dev(double* d_gamma, const double* d_alpha, const double* d_beta, int N, int T,
+                                      void* stream);
+int bhmm_b200_state_counts_dev(double* d_counts, const double* d_gamma, int N, int T, void* stream);
+int bhmm_b200_transition_counts_dev(double* d_C, const double* d_A, const double* d_pobs, const double* d_alpha,
+                                    const double* d_beta, int N, int T, void* stream);
+int bhmm_b200_viterbi_dev(int* d_path, const double* d_A, const double* d_pobs, const double* d_pi, int N, int T,
+                          void* stream);
+int bhmm_b200_sample_path_dev(int* d_path, const double* d_alpha, const double* d_A, const double* d_u, int N,
+                              int T, void* stream);
+int bhmm_b200_gaussian_p_obs_dev(const double* d_o, const double* d_mus, const double* d_sigmas, int N, int T,
+                                 int ignore_outliers, double* d_p, void* stream);
+int bhmm_b200_discrete_p_obs_dev(const int* d_obs, const double* d_B, int N, int M, int T, int ignore_outliers,
+                                 double* d_p, void* stream);
+
+/* ---- (3) batched device-resident engine --------------------------------------------------------- */
+typedef struct bhmm_b200_batch bhmm_b200_batch;
+
+/* offsets: host array of K+1 row offsets of the concatenated trajectories (offsets[0]=0, offsets[K]=rows).
+ * chunk / warm: frames per chain and warm-up frames (0 = automatic).  Scratch memory (forward variables,
+ * chain tables, partial statistics) is allocated by the library unless a workspace is attached. */
+int bhmm_b200_batch_create(bhmm_b200_batch** out, const long long* offsets, int K, int N, int chunk, int warm);
+void bhmm_b200_batch_destroy(bhmm_b200_batch* b);
+int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm);
+size_t bhmm_b200_batch_workspace_bytes(const bhmm_b200_batch* b);
+int bhmm_b200_batch_attach_workspace(bhmm_b200_batch* b, void* d_workspace, size_t bytes);
+/* info[0]=chains, [1]=chunk, [2]=warm, [3]=fwd fix-up sweeps, [4]=bwd fix-up sweeps, [5]=worst fwd mismatch,
+ * [6]=worst bwd mismatch, [7]=chains re-run, of the last engine call on this batch. */
+void bhmm_b200_batch_info(const bhmm_b200_batch* b, double info[8]);
+int bhmm_b200_stats_len_gaussian(int N);        /* 1 + N + N*N + 3N */
+int bhmm_b200_stats_len_discrete(int N);        /* 1 + N + N*N + N  (B-numerator is separate) */
+
+/* One Baum-Welch E-step over all trajectories (maximum_likelihood.py:383-385 + :271-282 + the data passes of
+ * OutputModel.estimate).  d_obs: device (rows) float64.  A, pi, means, sigmas: HOST arrays.
+ * d_stats (device, bhmm_b200_stats_len_gaussian(N) doubles) receives
+ *    [ loglik | gamma0_sum (N) | C (N*N) | sum_t gamma (N) | sum_t gamma*(o-mu) (N) | sum_t gamma*(o-mu)^2 (N) ]
+ * with mu the CURRENT means (shifted moments; the host M-step recentres them, see estimators/).
+ * d_gamma: optional device (rows,N) output of the state probabilities (NULL to keep them on chip). */
+int bhmm_b200_estep_gaussian(bhmm_b200_batch* b, const double* d_obs, const double* A, const double* pi,
+                             const double* means, const double* sigmas, int ignore_outliers, double* d_gamma,
+                             double* d_stats, void* stream);
+/* Discrete output model: d_obs device (rows) int32, B host (N,M).  d_stats = [loglik|gamma0|C|sum gamma];
+ * d_Bnum device (N,M) receives the B numerator sum_t gamma[t,i]*[o_t == m] (_update_pout). */
+int bhmm_b200_estep_discrete(bhmm_b200_batch* b, const int* d_obs, const double* A, const double* pi,
+                             const double* B, int M, int ignore_outliers, double* d_gamma, double* d_stats,
+                             double* d_Bnum, void* stream);
+/* Viterbi paths of all trajectories (maximum_likelihood.py:332-352); d_path device (rows) int32. */
+int bhmm_b200_viterbi_gaussian(bhmm_b200_batch* b, const double* d_obs, const double* A, const double* pi,
+                               const double* means, const double* sigmas, int ignore_outliers, int* d_path,
+                               void* stream);
+int bhmm_b200_viterbi_discrete(bhmm_b200_batch* b, const int* d_obs, const double* A, const double* pi,
+                               const double* B, int M, int ignore_outliers, int* d_path, void* stream);
+/* One Gibbs hidden-path sweep (bayesian_sampling.py:283-331): emission + forward + backward sampling of every
+ * trajectory, then the path statistics of generic_hmm.py:297-334,398-431.  Uniforms: d_u (device, one per row,
+ * u[row] is the draw of that frame) or, when d_u is NULL, device Philox4x32-10 keyed by (seed, sweep).
+ * d_counts (device int64): [ C (N*N) | n0 (N) | frames per state (N) ];  d_sums (device float64, may be NULL for
+ * discrete): [ sum o (N) | sum o^2 (N) ] per state. */
+int bhmm_b200_gibbs_gaussian(bhmm_b200_batch* b, const double* d_obs, const double* A, const double* pi,
+                             const double* means, const double* sigmas, int ignore_outliers, const double* d_u,
+                             unsigned long long seed, unsigned long long sweep, int* d_path, long long* d_counts,
+                             double* d_sums, double* loglik_host, void* stream);
+int bhmm_b200_gibbs_discrete(bhmm_b200_batch* b, const int* d_obs, const double* A, const double* pi,
+                             const double* B, int M, int ignore_outliers, const double* d_u,
+                             unsigned long long seed, unsigned long long sweep, int* d_path, long long* d_counts,
+                             double* loglik_host, void* stream);
+/* Per-state symbol histogram of sampled paths (DiscreteOutputModel.sample's bincount, discrete.py:240-245):
+ * d_hist (device int64, N*M) += [path==i][obs==m]. */
+int bhmm_b200_path_symbol_histogram(const int* d_path, const int* d_obs, long long rows, int N, int M,
+                                    long long* d_hist, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHMM_B200_H */

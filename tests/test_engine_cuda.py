@@ -1,0 +1,219 @@
+"""Parity of the batched, device-resident engine (TrajectoryBatch -> bhmm_b200_batch_* C ABI) against the CPU
+oracle and the reference fixtures: fused E-step statistics, EM iterations, batched Viterbi and the Gibbs
+hidden-path sweep.  float64 within 1e-10 relative, integer outputs bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+@pytest.fixture(scope='module')
+def eng():
+    import torch
+    assert torch.cuda.is_available()
+    import bhmm_b200.engine as e
+    return e
+
+
+def oracle_stats_gaussian(oracle, obs, A, pi, means, sigmas):
+    st = oracle.estep_gaussian(obs, A, pi, means, sigmas)
+    wd = sum(g.T.dot(o) for g, o in zip(st['gammas'], obs)) - means * st['wsum']
+    wdd = np.zeros(len(means))
+    for g, o in zip(st['gammas'], obs):
+        d = o[:, None] - means[None, :]
+        wdd += (g * d * d).sum(axis=0)
+    return st, wd, wdd
+
+
+def em_obs(g):
+    return [g['obs%d' % k] for k in range(len(g['lengths']))]
+
+
+@pytest.mark.parametrize('chunk,warm', [(0, 0), (200, 150), (64, 4), (5000, 10)])
+def test_estep_gaussian_statistics(eng, oracle_port, golden, chunk, warm):
+    g = golden('em_gauss3')
+    obs = em_obs(g)
+    A, pi, means, sigmas = g['A0'], g['pi0'], g['means0'], g['sigmas0']
+    batch = eng.TrajectoryBatch(obs, 3, chunk=chunk, warm=warm)
+    st = eng.unpack_stats(batch.estep_gaussian(A, pi, means, sigmas).cpu().numpy(), 3)
+    ref, wd, wdd = oracle_stats_gaussian(oracle_port, obs, A, pi, means, sigmas)
+    assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])
+    np.testing.assert_allclose(st['gamma0'], ref['gamma0'], rtol=RTOL)
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=RTOL)
+    np.testing.assert_allclose(st['wsum'], ref['wsum'], rtol=RTOL)
+    np.testing.assert_allclose(st['wd'], wd, rtol=1e-9, atol=1e-9 * np.abs(wd).max())
+    np.testing.assert_allclose(st['wdd'], wdd, rtol=RTOL)
+    info = batch.info()
+    if chunk == 64:
+        assert info['chains'] > 4 and (info['fixups_fwd'] + info['fixups_bwd']) >= 1
+    # gamma on request
+    import torch
+    gam = torch.zeros((batch.rows, 3), dtype=torch.float64, device='cuda')
+    batch.estep_gaussian(A, pi, means, sigmas, gamma_out=gam)
+    gam = gam.cpu().numpy()
+    ref_gamma = np.concatenate(ref['gammas'])
+    assert np.max(np.abs(gam - ref_gamma)) <= RTOL
+    batch.close()
+
+
+def test_em_iterations_match_reference_estimator(eng, golden):
+    """6 Baum-Welch iterations from the fixture's initial model reproduce MaximumLikelihoodEstimator.fit
+    (log-likelihood history, A, pi, means, sigmas within 1e-10; Viterbi paths identical)."""
+    from bhmm_b200.estimators import MaximumLikelihoodEstimator
+    from bhmm_b200.hmm import HMM
+    from bhmm_b200.output_models import GaussianOutputModel
+    g = golden('em_gauss3')
+    obs = em_obs(g)
+    init = HMM(g['pi0'], g['A0'], GaussianOutputModel(3, means=g['means0'], sigmas=g['sigmas0']))
+    est = MaximumLikelihoodEstimator(obs, 3, initial_model=init, reversible=False, stationary=False,
+                                     accuracy=-np.inf, maxit=6)
+    model = est.fit()
+    np.testing.assert_allclose(est.likelihoods, g['likelihoods'], rtol=RTOL)
+    np.testing.assert_allclose(model.transition_matrix, g['A'], rtol=RTOL)
+    np.testing.assert_allclose(model.initial_distribution, g['pi'], rtol=RTOL, atol=1e-300)
+    np.testing.assert_allclose(model.output_model.means, g['means'], rtol=RTOL)
+    np.testing.assert_allclose(model.output_model.sigmas, g['sigmas'], rtol=RTOL)
+    np.testing.assert_allclose(est.count_matrix, g['count_matrix'], rtol=1e-9)
+    np.testing.assert_allclose(est.initial_count, g['initial_count'], rtol=1e-9, atol=1e-300)
+    for k in range(len(obs)):
+        assert np.array_equal(model.hidden_state_trajectories[k], g['viterbi%d' % k])
+
+
+def test_em_discrete_matches_reference_estimator(eng, golden):
+    from bhmm_b200.estimators import MaximumLikelihoodEstimator
+    from bhmm_b200.hmm import HMM
+    from bhmm_b200.output_models import DiscreteOutputModel
+    g = golden('em_discrete')
+    obs = em_obs(g)
+    init = HMM(g['pi0'], g['A0'], DiscreteOutputModel(g['B0']))
+    est = MaximumLikelihoodEstimator(obs, 4, initial_model=init, reversible=False, stationary=False,
+                                     accuracy=-np.inf, maxit=4, output='discrete')
+    model = est.fit()
+    np.testing.assert_allclose(est.likelihoods, g['likelihoods'], rtol=RTOL)
+    np.testing.assert_allclose(model.transition_matrix, g['A'], rtol=RTOL)
+    np.testing.assert_allclose(model.output_model.output_probabilities, g['B'], rtol=1e-9, atol=1e-300)
+    for k in range(len(obs)):
+        assert np.array_equal(model.hidden_state_trajectories[k], g['viterbi%d' % k])
+
+
+@pytest.mark.parametrize('N,K,T', [(2, 3, 50), (10, 6, 3000), (20, 3, 900), (32, 4, 1500), (40, 2, 500), (100, 2, 260)])
+def test_estep_random_models(eng, oracle_port, N, K, T):
+    rng = np.random.default_rng(N * 7 + K)
+    X = rng.random((N, N)) ** 2 + 1e-3
+    A = X / X.sum(axis=1)[:, None]
+    pi = rng.random(N) + 0.01
+    pi /= pi.sum()
+    means, sigmas = np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
+    obs = []
+    for k in range(K):
+        Tk = T - 37 * k
+        s = rng.integers(0, N, size=Tk)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(Tk))
+    batch = eng.TrajectoryBatch(obs, N, chunk=max(64, T // 7), warm=0)
+    st = eng.unpack_stats(batch.estep_gaussian(A, pi, means, sigmas).cpu().numpy(), N)
+    ref, wd, wdd = oracle_stats_gaussian(oracle_port, obs, A, pi, means, sigmas)
+    assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])
+    np.testing.assert_allclose(st['gamma0'], ref['gamma0'], rtol=RTOL, atol=1e-300)
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9, atol=1e-12 * ref['C'].max())
+    np.testing.assert_allclose(st['wsum'], ref['wsum'], rtol=RTOL)
+    np.testing.assert_allclose(st['wdd'], wdd, rtol=1e-9)
+    # batched Viterbi vs the oracle, trajectory by trajectory
+    paths = batch.split(batch.viterbi_gaussian(A, pi, means, sigmas).cpu().numpy())
+    mism = 0
+    for o, p in zip(obs, paths):
+        ref_p = oracle_port.viterbi(A, oracle_port.gaussian_p_obs(o, means, sigmas), pi)
+        mism += int(np.sum(ref_p != p))
+    # emission values come from CUDA's exp (<= 1-2 ulp from glibc's): paths agree unless a comparison is tied to
+    # the last bit, which these seeded cases do not hit
+    assert mism == 0
+    batch.close()
+
+
+def test_estep_discrete_statistics(eng, oracle_port):
+    rng = np.random.default_rng(12)
+    N, M, K, T = 7, 40, 5, 2000
+    X = rng.random((N, N)) ** 2 + 1e-2
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    B = rng.random((N, M)) ** 3 + 1e-4
+    B /= B.sum(axis=1)[:, None]
+    obs = [rng.integers(0, M, size=T - 11 * k).astype(np.int32) for k in range(K)]
+    batch = eng.TrajectoryBatch(obs, N, chunk=300, warm=0)
+    stats, Bnum = batch.estep_discrete(A, pi, B)
+    st = eng.unpack_stats(stats.cpu().numpy(), N)
+    ref = oracle_port.estep_discrete(obs, A, pi, B)
+    assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9)
+    np.testing.assert_allclose(st['gamma0'], ref['gamma0'], rtol=RTOL)
+    np.testing.assert_allclose(Bnum.cpu().numpy(), ref['Bnum'], rtol=1e-9)
+    paths = batch.split(batch.viterbi_discrete(A, pi, B).cpu().numpy())
+    for o, p in zip(obs, paths):
+        assert np.array_equal(p, oracle_port.viterbi(A, oracle_port.discrete_p_obs(o, B), pi))   # exact gather
+    batch.close()
+
+
+def test_gibbs_sweep_reproduces_reference_paths(eng, oracle_port, golden):
+    """With the reference's uniforms (glibc stream, re-seeded for every trajectory like
+    bayesian_sampling.py:288-290 does on the first sweep) the sampled paths and their integer statistics are
+    identical to the fixture."""
+    import torch
+    g = golden('gibbs_gauss3')
+    K = len(g['lengths'])
+    obs = [g['obs%d' % k] for k in range(K)]
+    batch = eng.TrajectoryBatch(obs, 3, chunk=128, warm=0)
+    u_rows = np.concatenate([oracle_port.glibc_uniforms(int(g['seed']), int(L))[::-1] for L in g['lengths']])
+    u_dev = torch.from_numpy(np.ascontiguousarray(u_rows)).cuda()
+    path, counts, sums, ll = batch.gibbs_gaussian(g['A'], g['pi'], g['means'], g['sigmas'], uniforms=u_dev)
+    paths = batch.split(path.cpu().numpy())
+    for k in range(K):
+        assert np.array_equal(paths[k], g['path%d' % k])
+    c = batch.unpack_counts(counts)
+    assert np.array_equal(c['C'], g['count_matrix'].astype(np.int64))
+    assert np.array_equal(c['n0'], g['count_init'])
+    sums = sums.cpu().numpy()
+    for i in range(3):
+        n = int(g['obs_in_state_n%d' % i])
+        assert c['count'][i] == n
+        np.testing.assert_allclose(sums[i] / n, float(g['obs_in_state_mean%d' % i]), rtol=1e-11)
+    ll_ref = sum(oracle_port.forward(g['A'], oracle_port.gaussian_p_obs(o, g['means'], g['sigmas']), g['pi'])[0] for o in obs)
+    assert abs(ll - ll_ref) <= RTOL * abs(ll_ref)
+    batch.close()
+
+
+def test_gibbs_philox_is_distributionally_correct(eng, oracle_port):
+    """Device Philox draws: the sampled paths follow P(S | O, model): compare state occupancies and transition
+    counts, averaged over sweeps, with the smoothed expectations (sum gamma, Baum-Welch C)."""
+    rng = np.random.default_rng(21)
+    N, K, T = 3, 8, 4000
+    A = np.array([[0.95, 0.03, 0.02], [0.04, 0.9, 0.06], [0.02, 0.05, 0.93]])
+    pi = np.array([0.3, 0.3, 0.4])
+    means, sigmas = np.array([-2.0, 0.0, 2.0]), np.array([1.0, 1.2, 1.0])
+    obs = []
+    for k in range(K):
+        s = np.zeros(T, dtype=int)
+        for t in range(1, T):
+            s[t] = rng.choice(N, p=A[s[t - 1]])
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    batch = eng.TrajectoryBatch(obs, N)
+    ref = oracle_port.estep_gaussian(obs, A, pi, means, sigmas)
+    sweeps = 60
+    occ = np.zeros(N)
+    Cs = np.zeros((N, N))
+    seen = set()
+    for s in range(sweeps):
+        path, counts, sums, ll = batch.gibbs_gaussian(A, pi, means, sigmas, seed=1234, sweep=s)
+        c = batch.unpack_counts(counts)
+        occ += c['count']
+        Cs += c['C']
+        seen.add(hash(path[:2000].cpu().numpy().tobytes()))
+    assert len(seen) == sweeps                     # different sweeps give different paths
+    occ /= sweeps
+    Cs /= sweeps
+    np.testing.assert_allclose(occ, ref['wsum'], rtol=0.02)
+    np.testing.assert_allclose(Cs, ref['C'], rtol=0.08, atol=3.0)
+    p2, c2, _, _ = batch.gibbs_gaussian(A, pi, means, sigmas, seed=1234, sweep=7)
+    p2 = p2.cpu().numpy().copy()
+    p3, _, _, _ = batch.gibbs_gaussian(A, pi, means, sigmas, seed=1234, sweep=7)
+    assert np.array_equal(p2, p3.cpu().numpy())    # same (seed, sweep) -> same paths
+    batch.close()
