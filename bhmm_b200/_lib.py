@@ -21,7 +21,7 @@ class CudaUnavailableError(RuntimeError):
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        "bhmm_b200: %s is missing.  Build the CUDA extension first (python -m bhmm_b200.build, needs nvcc); "
+        "bhmm_b200: %s is missing.  Build the CUDA extension first (python bhmm_b200/build.py, needs nvcc); "
         "this package has no CPU fallback." % LIB_PATH)
 
 lib = C.CDLL(LIB_PATH)
@@ -80,6 +80,8 @@ _proto('bhmm_b200_batch_replan', C.c_int, _vp, C.c_int, C.c_int)
 _proto('bhmm_b200_batch_workspace_bytes', C.c_size_t, _vp)
 _proto('bhmm_b200_batch_attach_workspace', C.c_int, _vp, _vp, C.c_size_t)
 _proto('bhmm_b200_batch_info', None, _vp, _dp)
+_proto('bhmm_b200_batch_set_profiling', C.c_int, _vp, C.c_int)
+_proto('bhmm_b200_batch_kernel_ms', None, _vp, _dp)
 _proto('bhmm_b200_stats_len_gaussian', C.c_int, C.c_int)
 _proto('bhmm_b200_stats_len_discrete', C.c_int, C.c_int)
 _proto('bhmm_b200_estep_gaussian', C.c_int, _vp, _vp, _dp, _dp, _dp, _dp, C.c_int, _vp, _vp, _vp)

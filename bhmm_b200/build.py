@@ -1,7 +1,7 @@
 """Build libbhmm_b200.so (hand-written sm_100a CUDA kernels + C ABI) in-tree with nvcc.
 
-    python -m bhmm_b200.build            # incremental
-    python -m bhmm_b200.build --force
+    python bhmm_b200/build.py            # incremental
+    python bhmm_b200/build.py --force
 
 The shared library lands next to this file (bhmm_b200/libbhmm_b200.so) so that it travels with the source
 tree; it is git-ignored.  nvcc cross-compiles for sm_100a without a GPU.

@@ -36,6 +36,10 @@ struct bhmm_b200_batch {
     int* d_err = nullptr;
     Arena disc;                 // B staging + Bt for the discrete model (sized on first use)
     RunInfo info;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool profile = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double kernel_ms[4] = {0, 0, 0, 0};   // forward (incl. certification), backward+statistics kernel, whole call, unused
 };
 
 namespace {
@@ -147,7 +151,9 @@ int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     b->w.ch.warm = b->warm_f;
+    if (b->profile) cudaEventRecord(b->ev[0], st);
     RC_TRY(run_forward(b->w, em, emkind, N, b->d_A, b->d_pi, b->d_alpha, b->info, st));
+    if (b->profile) cudaEventRecord(b->ev[1], st);
     if (b->info.fix_f > 0) b->warm_f = std::min(std::max(b->plan.maxT, 1), b->warm_f * 2);   // adapt for the next call
 
     for (int attempt = 0;; ++attempt) {
@@ -158,8 +164,10 @@ int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
         a.alpha = b->d_alpha; a.gamma = d_gamma; a.Bnum = d_Bnum; a.partials = b->d_partials;
         a.hand_used = b->w.hu_b; a.hand_end = b->w.he_b;
         if (d_Bnum) CUDA_TRY(cudaMemsetAsync(d_Bnum, 0, sizeof(double) * (size_t)N * em.M, st));
+        if (b->profile) cudaEventRecord(b->ev[2], st);
         RC_TRY(launch_backward_team(a, emkind, true, st));
         LAUNCHED(1);
+        if (b->profile) cudaEventRecord(b->ev[3], st);
         if (!b->w.chunked) break;
         const long long nfail = certify_sync(b->w, N, -1, &b->info.worst_b, st);
         if (nfail < 0) { bhmm_set_error(BHMM_ERR_CUDA, cudaGetErrorString(cudaGetLastError())); return BHMM_ERR_CUDA; }
@@ -184,6 +192,16 @@ int finish_stream(cudaStream_t st)
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { bhmm_set_error(BHMM_ERR_CUDA, cudaGetErrorString(e)); return BHMM_ERR_CUDA; }
     return BHMM_OK;
+}
+
+void collect_times(bhmm_b200_batch* b)
+{
+    if (!b->profile) return;
+    float f = 0.f, g = 0.f, t = 0.f;
+    cudaEventElapsedTime(&f, b->ev[0], b->ev[1]);
+    cudaEventElapsedTime(&g, b->ev[2], b->ev[3]);
+    cudaEventElapsedTime(&t, b->ev[0], b->ev[3]);
+    b->kernel_ms[0] = f; b->kernel_ms[1] = g; b->kernel_ms[2] = t;
 }
 
 int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, const double* pi, const double* d_u,
@@ -256,6 +274,7 @@ extern "C" void bhmm_b200_batch_destroy(bhmm_b200_batch* b)
     if (!b) return;
     b->arena.release();
     b->disc.release();
+    for (int k = 0; k < 4; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
     delete b;
 }
 
@@ -282,6 +301,21 @@ extern "C" int bhmm_b200_batch_attach_workspace(bhmm_b200_batch* b, void* d_work
     return BHMM_OK;
 }
 
+extern "C" int bhmm_b200_batch_set_profiling(bhmm_b200_batch* b, int on)
+{
+    if (!b) return BHMM_ERR_INVALID;
+    if (on && !b->ev[0])
+        for (int k = 0; k < 4; ++k)
+            if (cudaEventCreate(&b->ev[k]) != cudaSuccess) return BHMM_ERR_CUDA;
+    b->profile = on != 0;
+    return BHMM_OK;
+}
+
+extern "C" void bhmm_b200_batch_kernel_ms(const bhmm_b200_batch* b, double ms[4])
+{
+    for (int k = 0; k < 4; ++k) ms[k] = b->kernel_ms[k];
+}
+
 extern "C" void bhmm_b200_batch_info(const bhmm_b200_batch* b, double info[8])
 {
     info[0] = b->info.chains; info[1] = b->info.chunk; info[2] = b->info.warm; info[3] = b->info.fix_f;
@@ -301,7 +335,9 @@ extern "C" int bhmm_b200_estep_gaussian(bhmm_b200_batch* b, const double* d_obs,
     Emission em{};
     em.obs = d_obs; em.mu = b->d_mu; em.sigma = b->d_sigma; em.ignore_outliers = ignore_outliers;
     RC_TRY(estep_common(b, em, EM_GAUSS, A, pi, d_gamma, d_stats, nullptr, st));
-    return finish_stream(st);
+    RC_TRY(finish_stream(st));
+    collect_times(b);
+    return BHMM_OK;
 }
 
 extern "C" int bhmm_b200_estep_discrete(bhmm_b200_batch* b, const int* d_obs, const double* A, const double* pi,
@@ -316,7 +352,9 @@ extern "C" int bhmm_b200_estep_discrete(bhmm_b200_batch* b, const int* d_obs, co
     em.sym = d_obs; em.ignore_outliers = ignore_outliers;
     RC_TRY(prepare_discrete(b, B, M, em, st));
     RC_TRY(estep_common(b, em, EM_DISC, A, pi, d_gamma, d_stats, d_Bnum, st));
-    return finish_stream(st);
+    RC_TRY(finish_stream(st));
+    collect_times(b);
+    return BHMM_OK;
 }
 
 static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, const double* pi,

@@ -320,7 +320,7 @@ __global__ void k_backward_team(const BwdArgs a)
                     }
                 }
             }
-            b_own = bnew;
+            if (on) b_own = bnew;     // teams that have not started yet keep their initial vector
         }
         __syncthreads();
     }

@@ -54,11 +54,28 @@ class TrajectoryBatch(object):
     """
 
     def __init__(self, observations, nstates, device=None, chunk=0, warm=0):
+        first = np.asarray(observations[0])
+        host_dtype = np.int32 if np.issubdtype(first.dtype, np.integer) else np.float64
+        lengths = [len(o) for o in observations]
+        if len(lengths) == 0 or min(lengths) <= 0:
+            raise ValueError('every trajectory needs at least one frame')
+        cat = np.concatenate([np.asarray(o, dtype=host_dtype) for o in observations])
+        self._setup(cat, lengths, nstates, device, chunk, warm)
+
+    @classmethod
+    def from_concatenated(cls, rows, lengths, nstates, device=None, chunk=0, warm=0):
+        """Build from one concatenated per-frame array (numpy, or a torch tensor that may already live on the GPU)
+        and the list of trajectory lengths."""
+        self = cls.__new__(cls)
+        self._setup(rows, lengths, nstates, device, chunk, warm)
+        return self
+
+    def _setup(self, cat, lengths, nstates, device, chunk, warm):
         torch = _torch()
         self.torch = torch
         self.N = int(nstates)
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-        lengths = np.array([len(o) for o in observations], dtype=np.int64)
+        lengths = np.asarray(lengths, dtype=np.int64)
         if len(lengths) == 0 or np.any(lengths <= 0):
             raise ValueError('every trajectory needs at least one frame')
         self.K = len(lengths)
@@ -66,12 +83,14 @@ class TrajectoryBatch(object):
         self.offsets = np.zeros(self.K + 1, dtype=np.int64)
         np.cumsum(lengths, out=self.offsets[1:])
         self.rows = int(self.offsets[-1])
-        first = np.asarray(observations[0])
-        self.discrete = np.issubdtype(first.dtype, np.integer)
-        host_dtype = np.int32 if self.discrete else np.float64
-        cat = np.concatenate([np.asarray(o, dtype=host_dtype) for o in observations])
+        if not torch.is_tensor(cat):
+            cat = torch.from_numpy(np.ascontiguousarray(cat))
+        if cat.numel() != self.rows:
+            raise ValueError('concatenated observations have %d frames, lengths sum to %d' % (cat.numel(), self.rows))
+        self.discrete = not cat.dtype.is_floating_point
         with torch.cuda.device(self.device):
-            self.obs = torch.from_numpy(cat).to(self.device)
+            self.obs = cat.to(device=self.device, dtype=torch.int32 if self.discrete else torch.float64).contiguous().clone() \
+                if cat.is_cuda else cat.to(device=self.device, dtype=torch.int32 if self.discrete else torch.float64)
             self._handle = C.c_void_p()
             rc = lib.bhmm_b200_batch_create(C.byref(self._handle), self.offsets.ctypes.data_as(C.POINTER(C.c_longlong)),
                                             self.K, self.N, int(chunk), int(warm))
@@ -114,6 +133,16 @@ class TrajectoryBatch(object):
         lib.bhmm_b200_batch_info(self._handle, dptr(info))
         return dict(chains=int(info[0]), chunk=int(info[1]), warm=int(info[2]), fixups_fwd=int(info[3]),
                     fixups_bwd=int(info[4]), worst_fwd=float(info[5]), worst_bwd=float(info[6]), rerun=int(info[7]))
+
+    def set_profiling(self, on=True):
+        """Record CUDA events around the forward and the backward+statistics kernels of every E-step."""
+        check(lib.bhmm_b200_batch_set_profiling(self._handle, int(bool(on))))
+
+    def kernel_ms(self):
+        """Device times of the last E-step: dict(forward, backward_stats, span) in milliseconds."""
+        ms = np.zeros(4)
+        lib.bhmm_b200_batch_kernel_ms(self._handle, dptr(ms))
+        return dict(forward=float(ms[0]), backward_stats=float(ms[1]), span=float(ms[2]))
 
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)

@@ -125,6 +125,10 @@ int bhmm_b200_batch_attach_workspace(bhmm_b200_batch* b, void* d_workspace, size
 /* info[0]=chains, [1]=chunk, [2]=warm, [3]=fwd fix-up sweeps, [4]=bwd fix-up sweeps, [5]=worst fwd mismatch,
  * [6]=worst bwd mismatch, [7]=chains re-run, of the last engine call on this batch. */
 void bhmm_b200_batch_info(const bhmm_b200_batch* b, double info[8]);
+/* Per-kernel device timing of the E-step (CUDA events on the launching stream): ms[0] = forward kernel incl.
+ * certification, ms[1] = backward+statistics kernel, ms[2] = from the first to the last of those events. */
+int bhmm_b200_batch_set_profiling(bhmm_b200_batch* b, int on);
+void bhmm_b200_batch_kernel_ms(const bhmm_b200_batch* b, double ms[4]);
 int bhmm_b200_stats_len_gaussian(int N);        /* 1 + N + N*N + 3N */
 int bhmm_b200_stats_len_discrete(int N);        /* 1 + N + N*N + N  (B-numerator is separate) */
 

@@ -49,7 +49,8 @@ def _f64(a):
 def build(ref=True):
     """Compile liboracle.so (and _ref/libbhmm_ref.so when the reference checkout exists)."""
     targets = ["all"] + (["ref"] if ref else [])
-    subprocess.run(["make", "-s", "-C", _HERE] + targets, check=True)
+    # make's chatter must not reach stdout (bench.py prints exactly one JSON line there)
+    subprocess.run(["make", "-s", "-C", _HERE] + targets, check=True, stdout=subprocess.DEVNULL)
 
 
 def have_reference_lib():

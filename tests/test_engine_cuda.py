@@ -107,7 +107,7 @@ def test_estep_random_models(eng, oracle_port, N, K, T):
     means, sigmas = np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
     obs = []
     for k in range(K):
-        Tk = T - 37 * k
+        Tk = T - (T // 9) * k
         s = rng.integers(0, N, size=Tk)
         obs.append(means[s] + sigmas[s] * rng.standard_normal(Tk))
     batch = eng.TrajectoryBatch(obs, N, chunk=max(64, T // 7), warm=0)
