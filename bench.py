@@ -259,6 +259,7 @@ def run_ours(args):
     batch = TrajectoryBatch.from_concatenated(O.reshape(-1), [T] * K, N, chunk=args.chunk, warm=args.warm)
     del O
     batch.set_profiling(True)
+    lane_family = batch.uses_lane_kernels
     pi0, A0, m0, s0 = ts.perturbed_initial_model(A, means, N)
     model = (A0, pi0, m0, s0)
 
@@ -334,6 +335,7 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
         ab = algorithmic_bytes_per_frame(N)
+        family = 'lane<N=%d,EM_GAUSS>' % N if lane_family else 'team<EM_GAUSS>'
         dom = 'backward_stats' if kms['backward_stats'] >= kms['forward'] else 'forward'
         dom_ms = kms[dom] / args.steps
         # the dominant kernel also walks the warm-up frames; only the chain's own frames count as algorithmic bytes
@@ -367,7 +369,7 @@ def run_ours(args):
                              % (rows * 8 / 1e9, rows * N * 8 / 1e9),
                        'certification': {'fixups_fwd': info['fixups_fwd'], 'fixups_bwd': info['fixups_bwd'],
                                          'worst_fwd': info['worst_fwd'], 'worst_bwd': info['worst_bwd']}},
-            'roofline': {'bound': 'hbm', 'kernel': 'k_backward_team<EM_GAUSS,STATS>' if dom == 'backward_stats' else 'k_forward_team<EM_GAUSS>',
+            'roofline': {'bound': 'hbm', 'kernel': ('k_backward_stats_%s' if dom == 'backward_stats' else 'k_forward_%s') % family,
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_frame': ab[dom], 'kernel_ms': dom_ms,

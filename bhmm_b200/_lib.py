@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbhmm_b200.so')
+LIB_PATH = os.environ.get('BHMM_B200_LIB') or os.path.join(_HERE, 'libbhmm_b200.so')   # override: tuning variants
 
 OK, ERR_INVALID, ERR_NO_MEM, ERR_SAMPLE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_CERTIFIED = range(7)
 
@@ -77,6 +77,7 @@ _proto('bhmm_b200_discrete_p_obs_dev', C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_
 _proto('bhmm_b200_batch_create', C.c_int, C.POINTER(_vp), _llp, C.c_int, C.c_int, C.c_int, C.c_int)
 _proto('bhmm_b200_batch_destroy', None, _vp)
 _proto('bhmm_b200_batch_replan', C.c_int, _vp, C.c_int, C.c_int)
+_proto('bhmm_b200_batch_uses_lane_kernels', C.c_int, _vp)
 _proto('bhmm_b200_batch_workspace_bytes', C.c_size_t, _vp)
 _proto('bhmm_b200_batch_attach_workspace', C.c_int, _vp, _vp, C.c_size_t)
 _proto('bhmm_b200_batch_info', None, _vp, _dp)

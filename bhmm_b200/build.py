@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_obj')
 LIB = os.path.join(HERE, 'libbhmm_b200.so')
-SOURCES = ['team_kernels.cu', 'frame_kernels.cu', 'certify.cu', 'sample_kernels.cu', 'capi.cu', 'engine.cu']
+SOURCES = ['lane_inst_a.cu', 'lane_inst_b.cu', 'lane_inst_c.cu', 'lane_inst_d.cu', 'lane_inst_e.cu', 'lane_inst_f.cu',
+           'lane_dispatch.cu', 'team_kernels.cu', 'frame_kernels.cu', 'certify.cu', 'sample_kernels.cu', 'capi.cu', 'engine.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -34,7 +35,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), libname=None):
+    """Compile and link.  `defines` (e.g. ['-DLANE_MINB_F=6']) and `libname` build a tuning variant next to the
+    default library (its objects go to a separate directory)."""
+    global OBJ, LIB
+    if libname:
+        OBJ = os.path.join(CSRC, '_obj_' + libname)
+        LIB = os.path.join(HERE, 'lib%s.so' % libname)
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
     headers.append(os.path.join(os.path.dirname(HERE), 'include', 'bhmm_b200.h'))
@@ -48,7 +55,7 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', s, '-o', o]
+        cmd = [nvcc] + NVCC_FLAGS + list(defines) + ['-c', s, '-o', o]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         with open(o + '.log', 'w') as fh:
             fh.write(' '.join(cmd) + '\n' + r.stdout)
@@ -58,7 +65,7 @@ def build(force=False, verbose=False):
             print(r.stdout)
         return o
 
-    with ThreadPoolExecutor(max_workers=min(6, max(1, len(jobs)))) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(OBJ, s.replace('.cu', '.o')) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
@@ -70,4 +77,9 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith('-D')]
+    name = None
+    for a in sys.argv[1:]:
+        if a.startswith('--name='):
+            name = a.split('=', 1)[1]
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs, libname=name))

@@ -2,6 +2,7 @@
 // literal per-function API (host-pointer drop-ins and their device-pointer variants).  See include/bhmm_b200.h.
 #include <algorithm>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <ctime>
 
@@ -97,6 +98,36 @@ int auto_chunk(long long rows, int N, int warm)
     return (int)std::min<long long>(c, 1 << 30);
 }
 
+int auto_warm_lane(int N)
+{
+    if (g_warm_override > 0) return g_warm_override;
+    return std::min(8192, std::max(64, 32 * N));
+}
+
+int auto_chunk_lane(long long rows, int N, int warm)
+{
+    // one thread per chain; ~8 resident warps per SM (register-limited) fill the machine once
+    if (g_chunk_override > 0) return g_chunk_override;
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    (void)N;
+    const long long target = (long long)sms * 8 * 32;
+    long long c = (rows + target - 1) / target;
+    c = std::max<long long>(c, 2LL * warm);
+    c = std::max<long long>(c, 64);
+    return (int)std::min<long long>(c, 1 << 30);
+}
+
+int adapt_warm(int current, double need, bool failed, int warm_min, int warm_cap)
+{
+    double target = 1.3 * need;
+    if (failed) target = std::max(target, current + 32.0);
+    else target = std::max(target, 0.9 * current);
+    int w = (int)std::ceil(target / 32.0) * 32;
+    w = std::max(w, warm_min);
+    return std::min(w, std::max(warm_cap, 1));
+}
+
 size_t chainwork_bytes(int n, int N)
 {
     Carver cv;
@@ -105,7 +136,7 @@ size_t chainwork_bytes(int n, int N)
     cv.add<double>(n);
     for (int k = 0; k < 4; ++k) cv.add<double>((size_t)n * N);
     cv.add<int>(n);
-    cv.add<unsigned long long>(2);
+    cv.add<unsigned long long>(4);
     return cv.off + 256;
 }
 
@@ -123,7 +154,8 @@ int chainwork_setup(ChainWork& w, const HostPlan& p, int N, int warm, char* base
     w.hu_b = (double*)(base + cv.add<double>((size_t)n * N));
     w.he_b = (double*)(base + cv.add<double>((size_t)n * N));
     w.fail_list = (int*)(base + cv.add<int>(n));
-    w.cert_out = (unsigned long long*)(base + cv.add<unsigned long long>(2));
+    w.cert_out = (unsigned long long*)(base + cv.add<unsigned long long>(4));
+    w.warm_cap = std::max(1, p.maxT);
     CUDA_TRY(cudaMemcpyAsync(row0, p.row0.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(len, p.len.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(t0, p.t0.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
@@ -132,7 +164,7 @@ int chainwork_setup(ChainWork& w, const HostPlan& p, int N, int warm, char* base
     // but make it explicit
     CUDA_TRY(cudaStreamSynchronize(st));
     w.ch.row0 = row0; w.ch.len = len; w.ch.t0 = t0; w.ch.T = T;
-    w.ch.list = nullptr; w.ch.n = n; w.ch.warm = warm; w.ch.exact = 0;
+    w.ch.list = nullptr; w.ch.n = n; w.ch.warm = warm; w.ch.exact = 0; w.ch.warmv = nullptr;
     w.n_total = n;
     w.chunked = p.chunked;
     return BHMM_OK;
@@ -144,74 +176,77 @@ int chainwork_setup(ChainWork& w, const HostPlan& p, int N, int warm, char* base
 long long certify_sync(ChainWork& w, int N, int dir, double* worst, cudaStream_t st)
 {
     if (!g_pinned_cert) {
-        if (cudaMallocHost(&g_pinned_cert, 2 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+        if (cudaMallocHost(&g_pinned_cert, 4 * sizeof(unsigned long long)) != cudaSuccess) return -1;
     }
     Chains full = w.ch;
     full.list = nullptr;
     full.n = w.n_total;
+    full.warmv = nullptr;
     launch_certify(full, w.n_total, N, dir, dir > 0 ? w.hu_f : w.hu_b, dir > 0 ? w.he_f : w.he_b, g_cert_tol,
                    w.fail_list, w.cert_out, st);
     LAUNCHED(1);
-    if (cudaMemcpyAsync(g_pinned_cert, w.cert_out, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) !=
+    if (cudaMemcpyAsync(g_pinned_cert, w.cert_out, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) !=
         cudaSuccess)
         return -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
     double wv;
     memcpy(&wv, &g_pinned_cert[1], sizeof(double));
     if (worst) *worst = std::max(*worst, wv);
+    double& need = dir > 0 ? w.need_f : w.need_b;
+    need = std::max(need, (double)g_pinned_cert[2]);       // callers reset it at the start of a pass
     return (long long)g_pinned_cert[0];
+}
+
+int run_chains_certified(ChainWork& w, int N, int dir, const ChainLauncher& launch, RunInfo& info, cudaStream_t st)
+{
+    Chains all = w.ch;
+    all.list = nullptr; all.n = w.n_total; all.exact = 0;
+    all.warmv = nullptr;
+    (dir > 0 ? w.need_f : w.need_b) = 0.0;
+    RC_TRY(launch(all, st));
+    LAUNCHED(1);
+    if (!w.chunked) return BHMM_OK;
+    double& worst = dir > 0 ? info.worst_f : info.worst_b;
+    double& sweeps = dir > 0 ? info.fix_f : info.fix_b;
+    for (int sweep = 0;; ++sweep) {
+        const long long nfail = certify_sync(w, N, dir, &worst, st);
+        if (nfail < 0) { bhmm_set_error(BHMM_ERR_CUDA, cudaGetErrorString(cudaGetLastError())); return BHMM_ERR_CUDA; }
+        if (nfail == 0) break;
+        if (sweep > w.n_total + 2) { bhmm_set_error(BHMM_ERR_NOT_CERTIFIED, "chain hand-overs not certified"); return BHMM_ERR_NOT_CERTIFIED; }
+        Chains some = all;
+        some.list = w.fail_list; some.n = (int)nfail; some.exact = 1;
+        RC_TRY(launch(some, st));
+        LAUNCHED(1);
+        sweeps += 1;
+        info.rerun += (double)nfail;
+    }
+    return BHMM_OK;
 }
 
 int run_forward(ChainWork& w, const Emission& em, int emkind, int N, const double* dA, const double* dpi,
                 double* d_alpha, RunInfo& info, cudaStream_t st)
 {
     FwdArgs a{};
-    a.ch = w.ch;
-    a.ch.list = nullptr; a.ch.n = w.n_total; a.ch.exact = 0;
     a.em = em; a.N = N; a.A = dA; a.pi = dpi; a.alpha = d_alpha;
     a.chain_ll = w.chain_ll; a.hand_used = w.hu_f; a.hand_end = w.he_f;
-    RC_TRY(launch_forward_team(a, emkind, st));
-    LAUNCHED(1);
-    if (!w.chunked) return BHMM_OK;
-    for (int sweep = 0;; ++sweep) {
-        const long long nfail = certify_sync(w, N, +1, &info.worst_f, st);
-        if (nfail < 0) { bhmm_set_error(BHMM_ERR_CUDA, cudaGetErrorString(cudaGetLastError())); return BHMM_ERR_CUDA; }
-        if (nfail == 0) break;
-        if (sweep > w.n_total + 2) { bhmm_set_error(BHMM_ERR_NOT_CERTIFIED, "forward hand-overs not certified"); return BHMM_ERR_NOT_CERTIFIED; }
+    return run_chains_certified(w, N, +1, [&](const Chains& ch, cudaStream_t s2) {
         FwdArgs b = a;
-        b.ch.list = w.fail_list; b.ch.n = (int)nfail; b.ch.exact = 1;
-        RC_TRY(launch_forward_team(b, emkind, st));
-        LAUNCHED(1);
-        info.fix_f += 1;
-        info.rerun += (double)nfail;
-    }
-    return BHMM_OK;
+        b.ch = ch;
+        return launch_forward_team(b, emkind, s2);
+    }, info, st);
 }
 
 int run_backward(ChainWork& w, const Emission& em, int emkind, int N, const double* dA, double* d_beta,
                  RunInfo& info, cudaStream_t st)
 {
     BwdArgs a{};
-    a.ch = w.ch;
-    a.ch.list = nullptr; a.ch.n = w.n_total; a.ch.exact = 0;
     a.em = em; a.N = N; a.A = dA; a.beta = d_beta;
     a.hand_used = w.hu_b; a.hand_end = w.he_b;
-    RC_TRY(launch_backward_team(a, emkind, false, st));
-    LAUNCHED(1);
-    if (!w.chunked) return BHMM_OK;
-    for (int sweep = 0;; ++sweep) {
-        const long long nfail = certify_sync(w, N, -1, &info.worst_b, st);
-        if (nfail < 0) { bhmm_set_error(BHMM_ERR_CUDA, cudaGetErrorString(cudaGetLastError())); return BHMM_ERR_CUDA; }
-        if (nfail == 0) break;
-        if (sweep > w.n_total + 2) { bhmm_set_error(BHMM_ERR_NOT_CERTIFIED, "backward hand-overs not certified"); return BHMM_ERR_NOT_CERTIFIED; }
+    return run_chains_certified(w, N, -1, [&](const Chains& ch, cudaStream_t s2) {
         BwdArgs b = a;
-        b.ch.list = w.fail_list; b.ch.n = (int)nfail; b.ch.exact = 1;
-        RC_TRY(launch_backward_team(b, emkind, false, st));
-        LAUNCHED(1);
-        info.fix_b += 1;
-        info.rerun += (double)nfail;
-    }
-    return BHMM_OK;
+        b.ch = ch;
+        return launch_backward_team(b, emkind, false, s2);
+    }, info, st);
 }
 
 // ------------------------------------------------------------------------------------------------

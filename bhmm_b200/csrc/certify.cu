@@ -12,6 +12,10 @@
 
 namespace {
 
+// Besides pass / fail the kernel estimates how long a warm-up each hand-over NEEDS: the mismatch decays geometrically
+// with the warm-up length (m ~ rho^w), so w' = w log(tol) / log(m) frames would have sufficed.  The maximum over all
+// chains (out[2]) lets the host keep the warm-up a safety factor above the need instead of discovering it by failing
+// (a failed backward pass costs a whole extra pass).
 __global__ void k_certify(Chains ch, int n_total, int N, int dir, const double* __restrict__ hand_used,
                           const double* __restrict__ hand_end, double tol, int* __restrict__ fail_list,
                           unsigned long long* __restrict__ out)
@@ -35,6 +39,13 @@ __global__ void k_certify(Chains ch, int n_total, int N, int dir, const double* 
         const unsigned long long slot = atomicAdd(out, 1ULL);
         fail_list[slot] = c;
     }
+    // warm-up actually available to this chain (it is cut short at the trajectory's ends, where the start is exact)
+    const int avail = dir > 0 ? ch.t0[c] : ch.T[c] - (ch.t0[c] + ch.len[c]);
+    const int w = min(ch.warmv ? ch.warmv[c] : ch.warm, avail);
+    double need = 0.0;
+    if (worst >= 0.5) need = 2.0 * w + 32.0;
+    else if (worst > 0.0) need = w * log(tol) / log(worst);
+    atomicMax(out + 2, (unsigned long long)need);
 }
 
 // stats = [loglik | gamma0 (N) | C (N*N) | sum gamma (N) | sum gamma d (N) | sum gamma d^2 (N)]
@@ -70,7 +81,7 @@ __global__ void k_finalize_stats(const double* __restrict__ partials, int grid, 
 int launch_certify(const Chains& ch, int n_total, int N, int dir, const double* hand_used, const double* hand_end,
                    double tol, int* fail_list, unsigned long long* out, cudaStream_t st)
 {
-    cudaMemsetAsync(out, 0, 2 * sizeof(unsigned long long), st);
+    cudaMemsetAsync(out, 0, 4 * sizeof(unsigned long long), st);
     if (n_total <= 0) return BHMM_OK;
     k_certify<<<(n_total + 127) / 128, 128, 0, st>>>(ch, n_total, N, dir, hand_used, hand_end, tol, fail_list, out);
     return BHMM_OK;

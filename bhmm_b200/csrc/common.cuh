@@ -48,7 +48,8 @@ struct Chains {
     const int* T;           // length of the trajectory the chain belongs to
     const int* list;        // optional indirection: run only chains list[0..n) (fix-up passes); may be NULL
     int n;                  // number of chains to run
-    int warm;               // warm-up frames
+    int warm;               // warm-up frames (used when warmv is NULL)
+    const int* warmv;       // optional per-chain warm-up lengths, adapted by the certification (certify.cu)
     int exact;              // 1: fix-up pass, start from the recorded exact hand-over vector instead of warming up
 };
 

@@ -5,6 +5,7 @@
 // of MaximumLikelihoodEstimator.fit (maximum_likelihood.py:383-385), compute_viterbi_paths (:332-352) and
 // BayesianHMMSampler._updateHiddenStateTrajectories (bayesian_sampling.py:283-291).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "host_common.h"
@@ -14,7 +15,10 @@ struct bhmm_b200_batch {
     int K = 0, N = 0;
     long long rows = 0;
     std::vector<long long> offsets;
-    int chunk = 0, warm_f = 0, warm_b = 0;
+    int chunk = 0, warm_f = 0, warm_b = 0, warm_min = 32;
+    bool lane = false;          // small-N fast path (lane_kernels.cuh) instead of the team family
+    double* d_g0buf = nullptr;
+    int partial_rows = 0;
     HostPlan plan, segplan;
     Arena arena;
     bool carved = false;
@@ -59,9 +63,14 @@ size_t batch_layout(bhmm_b200_batch* b, char* base)
     const size_t o_A = cv.add<double>((size_t)N * N), o_pi = cv.add<double>(N), o_mu = cv.add<double>(N),
                  o_sg = cv.add<double>(N);
     b->stats_grid = backward_stats_grid(N, n);
-    const size_t o_part = cv.add<double>((size_t)b->stats_grid * ((size_t)N * N + 4 * N));
+    b->partial_rows = std::max(b->stats_grid, lane_blocks(n));
+    const size_t o_part = cv.add<double>((size_t)b->partial_rows * ((size_t)N * N + 4 * N));
+    const size_t o_g0 = cv.add<double>((size_t)n * N);
     const size_t o_err = cv.add<int>(4);
-    const size_t o_alpha = cv.add<double>((size_t)b->rows * N);
+    // forward variables: row-major (rows,N), or interleaved [chain/32][frame][state/2][chain%32] double2 (lane family)
+    size_t alpha_doubles = (size_t)b->rows * N;
+    if (b->lane) alpha_doubles = std::max(alpha_doubles, (size_t)((n + 31) / 32) * b->chunk * ((N + 1) / 2) * 64);
+    const size_t o_alpha = cv.add<double>(alpha_doubles);
     const size_t o_F = cv.add<unsigned char>((size_t)b->rows * N * (N > 256 ? 2 : 1));
     if (base) {
         b->d_offsets = (long long*)(base + o_offs);
@@ -79,6 +88,7 @@ size_t batch_layout(bhmm_b200_batch* b, char* base)
         b->d_mu = (double*)(base + o_mu);
         b->d_sigma = (double*)(base + o_sg);
         b->d_partials = (double*)(base + o_part);
+        b->d_g0buf = (double*)(base + o_g0);
         b->d_err = (int*)(base + o_err);
         b->d_alpha = (double*)(base + o_alpha);
         b->d_F = (unsigned char*)(base + o_F);
@@ -107,9 +117,10 @@ int batch_carve(bhmm_b200_batch* b, cudaStream_t st)
 
 void batch_plan(bhmm_b200_batch* b, int chunk, int warm)
 {
-    const int w = warm > 0 ? warm : auto_warm(b->N);
-    b->chunk = chunk > 0 ? chunk : auto_chunk(b->rows, b->N, w);
+    const int w = warm > 0 ? warm : (b->lane ? auto_warm_lane(b->N) : auto_warm(b->N));
+    b->chunk = chunk > 0 ? chunk : (b->lane ? auto_chunk_lane(b->rows, b->N, w) : auto_chunk(b->rows, b->N, w));
     b->warm_f = b->warm_b = w;
+    b->warm_min = warm > 0 ? warm : 32;       // an explicit warm-up length is a floor for the adaptation
     build_plan(b->offsets.data(), b->K, b->chunk, b->plan);
     build_plan(b->offsets.data(), b->K, SEG_FRAMES, b->segplan);
     b->carved = false;
@@ -144,44 +155,73 @@ int prepare_discrete(bhmm_b200_batch* b, const double* B, int M, Emission& em, c
 }
 
 // forward + (backward & statistics with whole-pass retry) + finalize
-int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, const double* pi, double* d_gamma,
-                 double* d_stats, double* d_Bnum, cudaStream_t st)
+int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, const double* pi, const double* mu,
+                 const double* sigma, double* d_gamma, double* d_stats, double* d_Bnum, cudaStream_t st)
 {
     const int N = b->N;
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     b->w.ch.warm = b->warm_f;
+    LaneArgs la{};
+    LaneHostParams hp{A, pi, mu, sigma};
+    if (b->lane) {
+        la.obs = em.obs; la.sym = em.sym; la.Bt = em.Bt; la.M = em.M; la.ignore_outliers = em.ignore_outliers;
+        la.alpha_il = b->d_alpha; la.Lmax = b->chunk; la.alpha_rm = nullptr;
+        la.chain_ll = b->w.chain_ll; la.g0buf = b->d_g0buf; la.partials = b->d_partials;
+        la.Bnum = d_Bnum; la.gamma = d_gamma;
+    }
     if (b->profile) cudaEventRecord(b->ev[0], st);
-    RC_TRY(run_forward(b->w, em, emkind, N, b->d_A, b->d_pi, b->d_alpha, b->info, st));
+    if (b->lane) {
+        la.hand_used = b->w.hu_f; la.hand_end = b->w.he_f;
+        RC_TRY(run_chains_certified(b->w, N, +1, [&](const Chains& ch, cudaStream_t s2) {
+            LaneArgs x = la;
+            x.ch = ch;
+            return launch_lane(x, hp, N, emkind, LANE_FORWARD, s2);
+        }, b->info, st));
+    } else {
+        RC_TRY(run_forward(b->w, em, emkind, N, b->d_A, b->d_pi, b->d_alpha, b->info, st));
+    }
     if (b->profile) cudaEventRecord(b->ev[1], st);
-    if (b->info.fix_f > 0) b->warm_f = std::min(std::max(b->plan.maxT, 1), b->warm_f * 2);   // adapt for the next call
+    if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT);
 
+    b->w.need_b = 0.0;
     for (int attempt = 0;; ++attempt) {
-        BwdArgs a{};
-        a.ch = b->w.ch;
-        a.ch.list = nullptr; a.ch.n = b->w.n_total; a.ch.exact = 0; a.ch.warm = b->warm_b;
-        a.em = em; a.N = N; a.grid = b->stats_grid; a.A = b->d_A;
-        a.alpha = b->d_alpha; a.gamma = d_gamma; a.Bnum = d_Bnum; a.partials = b->d_partials;
-        a.hand_used = b->w.hu_b; a.hand_end = b->w.he_b;
+        Chains all = b->w.ch;
+        all.list = nullptr; all.n = b->w.n_total; all.exact = 0; all.warm = b->warm_b; all.warmv = nullptr;
         if (d_Bnum) CUDA_TRY(cudaMemsetAsync(d_Bnum, 0, sizeof(double) * (size_t)N * em.M, st));
         if (b->profile) cudaEventRecord(b->ev[2], st);
-        RC_TRY(launch_backward_team(a, emkind, true, st));
+        if (b->lane) {
+            LaneArgs x = la;
+            x.ch = all; x.hand_used = b->w.hu_b; x.hand_end = b->w.he_b;
+            RC_TRY(launch_lane(x, hp, N, emkind, LANE_BACKWARD_STATS, st));
+        } else {
+            BwdArgs a{};
+            a.ch = all;
+            a.em = em; a.N = N; a.grid = b->stats_grid; a.A = b->d_A;
+            a.alpha = b->d_alpha; a.gamma = d_gamma; a.Bnum = d_Bnum; a.partials = b->d_partials;
+            a.hand_used = b->w.hu_b; a.hand_end = b->w.he_b;
+            RC_TRY(launch_backward_team(a, emkind, true, st));
+        }
         LAUNCHED(1);
         if (b->profile) cudaEventRecord(b->ev[3], st);
         if (!b->w.chunked) break;
         const long long nfail = certify_sync(b->w, N, -1, &b->info.worst_b, st);
         if (nfail < 0) { bhmm_set_error(BHMM_ERR_CUDA, cudaGetErrorString(cudaGetLastError())); return BHMM_ERR_CUDA; }
-        if (nfail == 0) break;
-        // statistics of a failed pass cannot be patched chain by chain: widen the warm-up and redo the pass.
-        // warm_b >= longest trajectory makes every chain start from the exact end condition, so this terminates.
+        if (nfail == 0) { b->warm_b = adapt_warm(b->warm_b, b->w.need_b, false, b->warm_min, b->plan.maxT); break; }
+        // statistics of a failed pass cannot be patched chain by chain: lengthen the warm-up (at least +32 frames, up to
+        // the longest trajectory, which is an exact start) and redo the pass.
         if (b->warm_b >= b->plan.maxT) { bhmm_set_error(BHMM_ERR_NOT_CERTIFIED, "backward hand-overs not certified"); return BHMM_ERR_NOT_CERTIFIED; }
-        b->warm_b = std::min(b->plan.maxT, b->warm_b * 2);
+        b->warm_b = adapt_warm(b->warm_b, b->w.need_b, true, b->warm_min, b->plan.maxT);
         b->info.fix_b += 1;
         b->info.rerun += (double)b->w.n_total;
-        if (attempt > 40) return BHMM_ERR_NOT_CERTIFIED;
     }
-    RC_TRY(launch_finalize_stats(b->d_partials, b->stats_grid, b->w.chain_ll, b->w.n_total, b->d_A, N, d_stats, st));
+    const int prow = b->lane ? lane_blocks(b->w.n_total) : b->stats_grid;
+    RC_TRY(launch_finalize_stats(b->d_partials, prow, b->w.chain_ll, b->w.n_total, b->d_A, N, d_stats, st));
     LAUNCHED(1);
+    if (b->lane) {
+        RC_TRY(launch_add_gamma0(b->w.ch, b->w.n_total, N, b->d_g0buf, d_stats, st));
+        LAUNCHED(1);
+    }
     b->info.warm = std::max(b->warm_f, b->warm_b);
     return BHMM_OK;
 }
@@ -204,7 +244,8 @@ void collect_times(bhmm_b200_batch* b)
     b->kernel_ms[0] = f; b->kernel_ms[1] = g; b->kernel_ms[2] = t;
 }
 
-int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, const double* pi, const double* d_u,
+int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, const double* pi, const double* mu,
+                 const double* sigma, const double* d_u,
                  unsigned long long seed, unsigned long long sweep, int* d_path, long long* d_counts, double* d_sums,
                  double* loglik_host, cudaStream_t st)
 {
@@ -213,8 +254,21 @@ int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     b->w.ch.warm = b->warm_f;
-    RC_TRY(run_forward(b->w, em, emkind, N, b->d_A, b->d_pi, b->d_alpha, b->info, st));
-    if (b->info.fix_f > 0) b->warm_f = std::min(std::max(b->plan.maxT, 1), b->warm_f * 2);
+    if (b->lane) {
+        LaneArgs la{};
+        LaneHostParams hp{A, pi, mu, sigma};
+        la.obs = em.obs; la.sym = em.sym; la.Bt = em.Bt; la.M = em.M; la.ignore_outliers = em.ignore_outliers;
+        la.alpha_rm = b->d_alpha; la.Lmax = b->chunk; la.chain_ll = b->w.chain_ll;
+        la.hand_used = b->w.hu_f; la.hand_end = b->w.he_f;
+        RC_TRY(run_chains_certified(b->w, N, +1, [&](const Chains& ch, cudaStream_t s2) {
+            LaneArgs x = la;
+            x.ch = ch;
+            return launch_lane(x, hp, N, emkind, LANE_FORWARD_ROWMAJOR, s2);
+        }, b->info, st));
+    } else {
+        RC_TRY(run_forward(b->w, em, emkind, N, b->d_A, b->d_pi, b->d_alpha, b->info, st));
+    }
+    if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT);
     CUDA_TRY(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
     if (d_u) RC_TRY(launch_sample_table(b->d_alpha, b->d_A, d_u, b->d_offsets, b->K, N, b->rows, b->d_F, b->d_err, st));
     else RC_TRY(launch_sample_table_philox(b->d_alpha, b->d_A, seed, sweep, b->d_offsets, b->K, N, b->rows, b->d_F, b->d_err, st));
@@ -261,6 +315,10 @@ extern "C" int bhmm_b200_batch_create(bhmm_b200_batch** out, const long long* of
     }
     bhmm_b200_batch* b = new bhmm_b200_batch();
     b->K = K; b->N = N;
+    {
+        const char* fam = getenv("BHMM_B200_FAMILY");     // "team" forces the general-N kernels (tests, comparisons)
+        b->lane = lane_supported(N, EM_GAUSS) && !(fam && strcmp(fam, "team") == 0);
+    }
     b->offsets.assign(offsets, offsets + K + 1);
     b->rows = offsets[K] - offsets[0];
     if (offsets[0] != 0) { delete b; bhmm_set_error(BHMM_ERR_INVALID, "offsets[0] must be 0"); return BHMM_ERR_INVALID; }
@@ -284,6 +342,8 @@ extern "C" int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm)
     batch_plan(b, chunk, warm);
     return BHMM_OK;
 }
+
+extern "C" int bhmm_b200_batch_uses_lane_kernels(const bhmm_b200_batch* b) { return b && b->lane ? 1 : 0; }
 
 extern "C" size_t bhmm_b200_batch_workspace_bytes(const bhmm_b200_batch* b)
 {
@@ -334,7 +394,7 @@ extern "C" int bhmm_b200_estep_gaussian(bhmm_b200_batch* b, const double* d_obs,
     RC_TRY(upload_small(b->d_sigma, sigmas, b->N, st));
     Emission em{};
     em.obs = d_obs; em.mu = b->d_mu; em.sigma = b->d_sigma; em.ignore_outliers = ignore_outliers;
-    RC_TRY(estep_common(b, em, EM_GAUSS, A, pi, d_gamma, d_stats, nullptr, st));
+    RC_TRY(estep_common(b, em, EM_GAUSS, A, pi, means, sigmas, d_gamma, d_stats, nullptr, st));
     RC_TRY(finish_stream(st));
     collect_times(b);
     return BHMM_OK;
@@ -351,7 +411,7 @@ extern "C" int bhmm_b200_estep_discrete(bhmm_b200_batch* b, const int* d_obs, co
     Emission em{};
     em.sym = d_obs; em.ignore_outliers = ignore_outliers;
     RC_TRY(prepare_discrete(b, B, M, em, st));
-    RC_TRY(estep_common(b, em, EM_DISC, A, pi, d_gamma, d_stats, d_Bnum, st));
+    RC_TRY(estep_common(b, em, EM_DISC, A, pi, nullptr, nullptr, d_gamma, d_stats, d_Bnum, st));
     RC_TRY(finish_stream(st));
     collect_times(b);
     return BHMM_OK;
@@ -413,7 +473,7 @@ extern "C" int bhmm_b200_gibbs_gaussian(bhmm_b200_batch* b, const double* d_obs,
     RC_TRY(upload_small(b->d_sigma, sigmas, b->N, st));
     Emission em{};
     em.obs = d_obs; em.mu = b->d_mu; em.sigma = b->d_sigma; em.ignore_outliers = ignore_outliers;
-    return gibbs_common(b, em, EM_GAUSS, A, pi, d_u, seed, sweep, d_path, d_counts, d_sums, loglik_host, st);
+    return gibbs_common(b, em, EM_GAUSS, A, pi, means, sigmas, d_u, seed, sweep, d_path, d_counts, d_sums, loglik_host, st);
 }
 
 extern "C" int bhmm_b200_gibbs_discrete(bhmm_b200_batch* b, const int* d_obs, const double* A, const double* pi,
@@ -428,7 +488,7 @@ extern "C" int bhmm_b200_gibbs_discrete(bhmm_b200_batch* b, const int* d_obs, co
     Emission em{};
     em.sym = d_obs; em.ignore_outliers = ignore_outliers;
     RC_TRY(prepare_discrete(b, B, M, em, st));
-    return gibbs_common(b, em, EM_DISC, A, pi, d_u, seed, sweep, d_path, d_counts, nullptr, loglik_host, st);
+    return gibbs_common(b, em, EM_DISC, A, pi, nullptr, nullptr, d_u, seed, sweep, d_path, d_counts, nullptr, loglik_host, st);
 }
 
 extern "C" int bhmm_b200_path_symbol_histogram(const int* d_path, const int* d_obs, long long rows, int N, int M,

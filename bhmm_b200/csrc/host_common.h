@@ -1,6 +1,7 @@
 // bhmm_b200/csrc/host_common.h -- host-side plumbing shared by capi.cu (literal API) and engine.cu (batched engine).
 #pragma once
 #include <atomic>
+#include <functional>
 #include <mutex>
 #include <vector>
 #include <stdint.h>
@@ -62,8 +63,13 @@ struct ChainWork {
     double* hu_b = nullptr;      // backward hand-over used / end
     double* he_b = nullptr;
     int* fail_list = nullptr;
-    unsigned long long* cert_out = nullptr;   // device [n_fail, worst bits]
+    unsigned long long* cert_out = nullptr;   // device [n_fail, worst bits, sum warm, count]
+    int warm_cap = 1;            // longest trajectory: a warm-up that long is an exact start
+    double need_f = 0, need_b = 0;   // certification's estimate of the warm-up the hardest hand-over needs
 };
+// next warm-up length from the current one and the certification's need estimate: 30 % above the need, decreasing by
+// at most 10 % per pass, a multiple of 32 frames
+int adapt_warm(int current, double need, bool failed, int warm_min, int warm_cap);
 size_t chainwork_bytes(int n_chains, int N);
 // carve ChainWork out of `base` (device) and upload the plan; returns bytes used
 int chainwork_setup(ChainWork& w, const HostPlan& p, int N, int warm, char* base, cudaStream_t st);
@@ -71,6 +77,13 @@ int chainwork_setup(ChainWork& w, const HostPlan& p, int N, int warm, char* base
 struct RunInfo {
     double chains = 0, chunk = 0, warm = 0, fix_f = 0, fix_b = 0, worst_f = 0, worst_b = 0, rerun = 0;
 };
+
+// Launch `launch(chains)` over all chains, then certify the hand-overs (dir = +1 forward, -1 backward) and re-run the
+// failing chains from the exact neighbour value (Chains.list / Chains.exact) until none fails.
+typedef std::function<int(const Chains& ch, cudaStream_t st)> ChainLauncher;
+int run_chains_certified(ChainWork& w, int N, int dir, const ChainLauncher& launch, RunInfo& info, cudaStream_t st);
+int auto_warm_lane(int N);
+int auto_chunk_lane(long long rows, int N, int warm);
 
 // forward over all chains + certification with exact fix-up sweeps.  alpha may be NULL.
 int run_forward(ChainWork& w, const Emission& em, int emkind, int N, const double* dA, const double* dpi,

@@ -43,6 +43,46 @@ struct VitArgs {
     int* path;               // (rows) int32 output
 };
 
+// ---- lane family (lane_kernels.cu): one thread per chain, N <= LANE_MAX_N
+constexpr int LANE_MAX_N = 16;
+template <int N>
+struct LaneParams {          // passed by value as a __grid_constant__ kernel parameter (constant-bank operands)
+    double A[N * N];
+    double pi[N];
+    double mu[N];
+    double isg[N];           // 1 / sigma
+    double nrm[N];           // 1 / (sqrt(2 pi) sigma)
+};
+struct LaneHostParams {      // HOST pointers
+    const double* A;
+    const double* pi;
+    const double* mu;
+    const double* sigma;
+};
+struct LaneArgs {
+    Chains ch;
+    const double* obs;       // EM_GAUSS: (rows)
+    const int* sym;          // EM_DISC : (rows)
+    const double* Bt;        // EM_DISC : (M,N)
+    int M;
+    int ignore_outliers;
+    double* alpha_il;        // interleaved forward variables: [chain/32][frame][state/2][chain%32] double2
+    int Lmax;                // frames per chain slot in alpha_il (= chunk)
+    double* alpha_rm;        // row-major (rows,N) forward variables (LANE_FORWARD_ROWMAJOR)
+    double* chain_ll;
+    double* hand_used;       // forward or backward hand-over buffers, depending on the kernel
+    double* hand_end;
+    double* g0buf;           // (n_chains, N): gamma at frame 0 of the chains that start a trajectory
+    double* partials;        // (blocks, N*N+4N)
+    double* Bnum;
+    double* gamma;           // optional (rows,N)
+};
+enum { LANE_FORWARD = 0, LANE_FORWARD_ROWMAJOR = 1, LANE_BACKWARD_STATS = 2 };
+bool lane_supported(int N, int em);
+int lane_blocks(int n_chains);
+int launch_lane(const LaneArgs& a, const LaneHostParams& hp, int N, int em, int what, cudaStream_t st);
+int launch_add_gamma0(const Chains& ch, int n_total, int N, const double* g0buf, double* stats, cudaStream_t st);
+
 void team_shape(int N, int* threads, int* cpb);
 int launch_forward_team(const FwdArgs& a, int em, cudaStream_t st);
 int launch_backward_team(const BwdArgs& a, int em, bool stats, cudaStream_t st);
@@ -69,7 +109,8 @@ int launch_transpose(const double* in, int R, int Cc, double* out, cudaStream_t 
 
 // ---- certification of chain hand-overs (certify.cu)
 // dir = +1 forward (chain c against c-1), -1 backward (chain c against c+1).
-// out[0] = number of failing chains, out[1] = bits of the largest mismatch seen; fail_list receives the ids.
+// out[0] = number of failing chains, out[1] = bits of the largest mismatch seen, out[2] = largest estimate of the
+// warm-up length a hand-over needs (frames); fail_list receives the ids of the failing chains.
 int launch_certify(const Chains& ch, int n_total, int N, int dir, const double* hand_used, const double* hand_end,
                    double tol, int* fail_list, unsigned long long* out, cudaStream_t st);
 // deterministic reduction of the E-step: stats = [loglik | gamma0 (N) | C (N*N) | sum gamma | sum gamma d | sum gamma d^2]

@@ -1,0 +1,54 @@
+// bhmm_b200/csrc/lane_dispatch.cu -- run-time dispatch of the lane family over the number of states.
+#include "common.cuh"
+#include "kernels.h"
+
+#define DECL(NN) int launch_lane_##NN(const LaneArgs&, const LaneHostParams&, int, int, cudaStream_t);
+DECL(1) DECL(2) DECL(3) DECL(4) DECL(5) DECL(6) DECL(7) DECL(8) DECL(9) DECL(10) DECL(11) DECL(12) DECL(13) DECL(14) DECL(15) DECL(16)
+#undef DECL
+
+namespace {
+constexpr int LANE_THREADS = 64;   // must match lane_kernels.cuh
+
+// gamma0 = sum over the chains that start a trajectory of their gamma at frame 0.  Fixed partition of the chains
+// over 256 threads and a fixed tree: deterministic.
+__global__ void k_add_gamma0(Chains ch, int n_total, int N, const double* __restrict__ g0buf, double* __restrict__ stats)
+{
+    __shared__ double red[256];
+    const int per = (n_total + 255) / 256;
+    const int lo = threadIdx.x * per, hi = min(n_total, lo + per);
+    for (int i = 0; i < N; ++i) {
+        double s = 0.0;
+        for (int c = lo; c < hi; ++c)
+            if (ch.t0[c] == 0) s += g0buf[(long long)c * N + i];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int w = 128; w > 0; w >>= 1) {
+            if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) stats[1 + i] += red[0];
+        __syncthreads();
+    }
+}
+}  // namespace
+
+int lane_blocks(int n_chains) { return (n_chains + LANE_THREADS - 1) / LANE_THREADS; }
+
+bool lane_supported(int N, int em) { return N >= 1 && N <= LANE_MAX_N && (em == EM_GAUSS || em == EM_DISC); }
+
+int launch_lane(const LaneArgs& a, const LaneHostParams& hp, int N, int em, int what, cudaStream_t st)
+{
+    switch (N) {
+#define CASE(NN) case NN: return launch_lane_##NN(a, hp, em, what, st);
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+        CASE(14) CASE(15) CASE(16)
+#undef CASE
+    }
+    return BHMM_ERR_UNSUPPORTED;
+}
+
+int launch_add_gamma0(const Chains& ch, int n_total, int N, const double* g0buf, double* stats, cudaStream_t st)
+{
+    k_add_gamma0<<<1, 256, 0, st>>>(ch, n_total, N, g0buf, stats);
+    return BHMM_OK;
+}

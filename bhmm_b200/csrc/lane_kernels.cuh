@@ -1,0 +1,632 @@
+// bhmm_b200/csrc/lane_kernels.cuh -- small-N fast path ("lane" family): ONE THREAD PER CHAIN.
+//
+// For N <= 16 hidden states a whole chain fits in one thread's registers: alpha / beta vectors are register
+// arrays indexed at compile time, the transition matrix and the emission constants are a __grid_constant__
+// kernel parameter, so every A[i][j] is a constant-bank operand of the FP64 FMA and the N x N matvec is N*N
+// back-to-back DFMAs with no loads, no shuffles and no barriers.  A warp carries 32 independent chains; the work
+// that is scalar per chain (normalisation, reciprocal, log-likelihood) costs one instruction for 32 chains
+// instead of one per 3 chains as in the team family (ncu, profiles/r1_v0_*: the team kernels are issue bound).
+//
+// Memory: the forward variables never leave the GPU in the fused E-step, so they are stored in a layout chosen
+// for coalescing, not the reference's (T,N): alpha_il[group][frame][pair][lane] as double2, where group = chain/32,
+// lane = chain%32, pair = state/2.  A warp's store of one state pair of one frame is 512 contiguous bytes.
+// Observations are read straight from the caller's concatenated array: each lane streams its own chain
+// (8 B per frame, 4 frames per 32 B sector, prefetched 8 frames ahead); L1 keeps the sector between uses.
+//
+// Emission: p_j = nrm_j * exp(-0.5 ((o - mu_j) * isg_j)^2) with exp() evaluated by fast_exp (Cody-Waite reduction
+// by ln 2 + degree-11 near-minimax polynomial, < 1 ulp, tools/gen_exp_poly.py); the log-likelihood is the sum of
+// log c_t, accumulated as a running mantissa product with integer exponent bookkeeping (one DMUL + integer ops per
+// frame instead of a log()).  Results agree with the reference to ~1e-13 relative (tests: 1e-10).
+//
+// Statistics: xi needs an N x N accumulator per chain, too many registers for N = 10.  Since only the SUM over
+// chains is wanted, the G lanes of a lane-group share the work: lane q accumulates rows [q*NH, (q+1)*NH) for all
+// G chains of its group, receiving the other chains' w vector and its rows of u, gamma (and the observation) by
+// warp shuffles.  gamma and xi are never written to memory unless a gamma buffer is requested.
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int LANE_THREADS = 64;
+constexpr unsigned FULL = 0xffffffffu;
+
+// build-time tunables (tools/build_variants.py sweeps them on the GPU box)
+#ifndef LANE_MINB_F
+#define LANE_MINB_F 4        // minimum resident blocks per SM asked of the compiler, forward kernel
+#endif
+#ifndef LANE_MINB_B
+#define LANE_MINB_B 4        // ... backward + statistics kernel
+#endif
+#ifndef LANE_ALPHA_MODE
+#define LANE_ALPHA_MODE 1    // backward kernel's read of the forward variables: 0 = streaming load + prefetch.global.L1
+#endif                       // of the next frame, 1 = plain load + prefetch, 2 = loaded one frame ahead into registers
+#ifndef LANE_PIPE_EMIS
+#define LANE_PIPE_EMIS 0     // emission of the NEXT frame is evaluated during the current step (independent work that
+#endif                       // fills the latency of the step's dependent chain: sums, reciprocals)
+#ifndef LANE_G_MID
+#define LANE_G_MID 4         // lanes sharing the xi accumulator rows for 9 <= N <= 12
+#endif
+
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// pairwise (tree) sum of a register array: depth log2(N) instead of N-1 dependent DADDs
+template <int N>
+__device__ __forceinline__ double tree_sum(const double (&v)[N])
+{
+    double t[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) t[j] = v[j];
+#pragma unroll
+    for (int w = 1; w < N; w <<= 1) {
+#pragma unroll
+        for (int j = 0; j + w < N; j += 2 * w) t[j] += t[j + w];
+    }
+    return t[0];
+}
+
+// exp() constants live in constant memory so that each one is a constant-bank operand of its DFMA (as 64-bit
+// literals they cost two UMOVs per use).  [0..9] = c11..c2 of the degree-11 polynomial (tools/gen_exp_poly.py),
+// [10] = log2(e), [11] = ln2 high part, [12] = ln2 low part (fdlibm split).
+__constant__ double EXPK[13] = {
+    0x1.af632a0f7e2cep-26, 0x1.28b4101c77212p-22, 0x1.71ddf56d8deb5p-19, 0x1.a01991a10d9aep-16,
+    0x1.a01a01b1461c5p-13, 0x1.6c16c1880029fp-10, 0x1.111111110f21ep-7,  0x1.555555554f0bap-5,
+    0x1.555555555555ap-3,  0x1.0000000000011p-1,
+    1.4426950408889634074, 6.93147180369123816490e-01, 1.90821492927058770002e-10};
+
+// Gaussian emission of one frame for all N states, evaluated "vertically": every stage of the exp() (range
+// reduction by ln 2, Horner steps, exponent insertion) is issued for all states before the next stage, so the N
+// dependent chains interleave and hide the FP64 latency.  exp(x) = 2^n exp(r), n = rint(x/ln2), |r| <= ln2/2,
+// degree-11 near-minimax polynomial (< 1 ulp).  The main path is branch free; states whose argument lies below
+// -708 (result denormal or zero) or is NaN are redone with the library exp() in a rarely taken tail.
+template <int N>
+__device__ __forceinline__ void emission_gauss(const LaneParams<N>& P, double o, int ignore_outliers, double (&p)[N])
+{
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    double x[N], t[N], r[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double d = (o - P.mu[j]) * P.isg[j];
+        x[j] = -0.5 * (d * d);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) t[j] = fma(x[j], EXPK[10], MAGIC);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double n = t[j] - MAGIC;
+        r[j] = fma(n, -EXPK[11], x[j]);
+        r[j] = fma(n, -EXPK[12], r[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(EXPK[0], r[j], EXPK[1]);
+#pragma unroll
+    for (int k = 2; k < 10; ++k) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], EXPK[k]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 1.0);
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 1.0);
+    bool tail = false;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const int ni = __double2loint(t[j]);
+        p[j] = __longlong_as_double(__double_as_longlong(p[j]) + ((long long)ni << 52)) * P.nrm[j];
+        tail |= !(x[j] >= -708.0);
+    }
+    if (tail) {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (!(x[j] >= -708.0)) p[j] = P.nrm[j] * exp(x[j]);
+    }
+    bool anynz = false;
+#pragma unroll
+    for (int j = 0; j < N; ++j) anynz |= (p[j] != 0.0);
+    if (ignore_outliers && !anynz) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) p[j] = 1.0;            // outputmodel.py:126-130
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void emission_disc(const LaneArgs& a, int sym, double (&p)[N])
+{
+    const double* src = a.Bt + (long long)sym * N;
+    bool anynz = false;
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[j] = __ldg(src + j); anynz |= (p[j] != 0.0); }
+    if (a.ignore_outliers && !anynz) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) p[j] = 1.0;
+    }
+}
+
+// log-likelihood accumulator: sum of log(c) kept as (integer exponent sum, mantissa product in [1,2)) plus a slow
+// path for zero / denormal / non-finite scaling factors (log(0) = -inf like the reference, _hidden.c:34,62).
+struct LogAcc {
+    double prod = 1.0;
+    long long esum = 0;
+    double slow = 0.0;
+    __device__ __forceinline__ void add(double c)
+    {
+        const int ec = (int)((__double_as_longlong(c) >> 52) & 0x7ff);
+        if (ec == 0 || ec == 0x7ff || c < 0.0) { slow += log(c); return; }
+        prod *= c;
+        const long long b = __double_as_longlong(prod);
+        esum += (long long)((b >> 52) & 0x7ff) - 1023;
+        prod = __longlong_as_double((b & 0x800fffffffffffffLL) | 0x3ff0000000000000LL);
+    }
+    __device__ __forceinline__ double value() const { return (double)esum * 0.693147180559945309417 + log(prod) + slow; }
+};
+
+__device__ __forceinline__ long long il_base(int c, int Lmax, int NP2)
+{
+    // index (in double2 units) of alpha_il[chain c][frame 0][pair 0]
+    return ((long long)(c >> 5) * Lmax * NP2 << 5) + (c & 31);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int N, int EM, bool ROWMAJOR>
+__global__ void __launch_bounds__(LANE_THREADS, LANE_MINB_F)
+k_forward_lane(const __grid_constant__ LaneParams<N> P, const LaneArgs a)
+{
+    constexpr int NP2 = (N + 1) / 2;
+    constexpr int PF = 4;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = idx < a.ch.n;
+    int c = 0, len = 0, t0 = 0, tstart = 0, mode = 0;        // mode 0: pi, 1: uniform warm-up, 2: exact vector
+    long long trow = 0;
+    if (have) {
+        c = a.ch.list ? a.ch.list[idx] : idx;
+        len = a.ch.len[c];
+        t0 = a.ch.t0[c];
+        trow = a.ch.row0[c] - t0;
+        if (t0 == 0) { tstart = 0; mode = 0; }
+        else if (a.ch.exact) { tstart = t0 - 1; mode = 2; }
+        else { tstart = max(0, t0 - (a.ch.warmv ? a.ch.warmv[c] : a.ch.warm)); mode = (tstart == 0) ? 0 : 1; }
+    }
+    const int maxpre = __reduce_max_sync(FULL, have ? (t0 - tstart) : 0);
+    const int total = maxpre + __reduce_max_sync(FULL, len);
+    const int tend = t0 + len;
+
+    double al[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) al[j] = 0.0;
+    if (have && mode == 2) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) al[j] = a.hand_end[(long long)(c - 1) * N + j];
+    }
+    LogAcc ll;
+    double2* il = reinterpret_cast<double2*>(a.alpha_il) + il_base(c, a.Lmax, NP2);
+
+    auto fetch = [&](int s) -> double {
+        int t = t0 - maxpre + s;
+        if (!have) return 0.0;
+        t = min(max(t, tstart), tend - 1);
+        if (EM == EM_GAUSS) return __ldg(a.obs + trow + t);
+        return __longlong_as_double((long long)__ldg(a.sym + trow + t));
+    };
+    // observations are fetched PF frames ahead into a rotating register ring (no unrolling: the loop body stays
+    // small enough for the instruction cache)
+    double ring[PF];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) ring[k] = fetch(k);
+    auto emission = [&](double rawv, double (&pv)[N]) {
+        if (EM == EM_GAUSS) emission_gauss<N>(P, rawv, a.ignore_outliers, pv);
+        else emission_disc<N>(a, (int)__double_as_longlong(rawv), pv);
+    };
+#if LANE_PIPE_EMIS
+    double pn[N];
+    emission(ring[0], pn);
+#endif
+
+    for (int s = 0; s < total; ++s) {
+        {
+            {
+                const double raw = ring[0];
+#pragma unroll
+                for (int k = 0; k + 1 < PF; ++k) ring[k] = ring[k + 1];
+                ring[PF - 1] = fetch(s + PF);
+                double p[N];
+#if LANE_PIPE_EMIS
+#pragma unroll
+                for (int j = 0; j < N; ++j) p[j] = pn[j];
+                emission(ring[0], pn);                       // next frame's emission: independent of this step
+#else
+                emission(raw, p);
+#endif
+                (void)raw;
+                const int t = t0 - maxpre + s;
+                const bool on = have && t >= tstart && t < tend;
+                if (on) {
+                    const bool init = (t == tstart);
+                    double v[N];
+                    if (init && mode == 2) {
+#pragma unroll
+                        for (int j = 0; j < N; ++j) v[j] = al[j];
+                    } else {
+                        if (init) {
+#pragma unroll
+                            for (int j = 0; j < N; ++j) v[j] = (mode == 0) ? P.pi[j] * p[j] : p[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < N; ++j) v[j] = al[0] * P.A[j];
+#pragma unroll
+                            for (int i = 1; i < N; ++i) {
+#pragma unroll
+                                for (int j = 0; j < N; ++j) v[j] = fma(al[i], P.A[i * N + j], v[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < N; ++j) v[j] *= p[j];
+                        }
+                    }
+                    const double csum = tree_sum<N>(v);
+                    const double rc = (csum != 0.0) ? 1.0 / csum : 1.0;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) al[j] = v[j] * rc;
+                    if (t >= t0) {
+                        ll.add(csum);
+                        if (ROWMAJOR) {
+                            double* dst = a.alpha_rm + (trow + t) * N;
+#pragma unroll
+                            for (int j = 0; j < N; ++j) dst[j] = al[j];
+                        } else {
+                            double2* dst = il + ((long long)(t - t0) * NP2 << 5);
+#pragma unroll
+                            for (int jp = 0; jp < NP2; ++jp)
+                                __stcs(dst + (jp << 5), make_double2(al[2 * jp], (2 * jp + 1 < N) ? al[2 * jp + 1] : 0.0));
+                        }
+                        if (t == tend - 1) {
+#pragma unroll
+                            for (int j = 0; j < N; ++j) a.hand_end[(long long)c * N + j] = al[j];
+                        }
+                    } else if (t == t0 - 1) {
+#pragma unroll
+                        for (int j = 0; j < N; ++j) a.hand_used[(long long)c * N + j] = al[j];
+                    }
+                }
+            }
+        }
+    }
+    if (have) a.chain_ll[c] = ll.value();
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward + sufficient statistics
+// ------------------------------------------------------------------------------------------------
+// value of arr[qsel*NH + ii] for a run-time qsel in [0,G): a chain of compile-time-indexed selects
+template <int N, int G, int NH>
+__device__ __forceinline__ double pick_row(const double (&arr)[N], int qsel, int ii)
+{
+    double v = arr[ii];
+#pragma unroll
+    for (int qq = 1; qq < G; ++qq)
+        if (qq * NH + ii < N) v = (qsel == qq) ? arr[qq * NH + ii] : v;
+    return v;
+}
+
+template <int N, int EM, int G>
+__global__ void __launch_bounds__(LANE_THREADS, LANE_MINB_B)
+k_backward_stats_lane(const __grid_constant__ LaneParams<N> P, const LaneArgs a)
+{
+    constexpr int NP2 = (N + 1) / 2;
+    constexpr int NH = (N + G - 1) / G;
+    constexpr int PF = 4;
+    constexpr int NSTAT = N * N + 4 * N;
+    __shared__ double red[(LANE_THREADS / 32) * NSTAT];
+
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int q = lane & (G - 1);
+    const bool have = idx < a.ch.n;
+    int c = 0, len = 0, t0 = 0, T = 0, e = 0, fs = 0, mode = 0;   // mode 0: beta = 1/N at fs, 2: exact vector at fs = e
+    long long trow = 0;
+    if (have) {
+        c = a.ch.list ? a.ch.list[idx] : idx;
+        len = a.ch.len[c];
+        t0 = a.ch.t0[c];
+        T = a.ch.T[c];
+        trow = a.ch.row0[c] - t0;
+        e = t0 + len;
+        if (e >= T) fs = T - 1;
+        else if (a.ch.exact) { fs = e; mode = 2; }
+        else fs = min(T - 1, e + (a.ch.warmv ? a.ch.warmv[c] : a.ch.warm) - 1);
+    }
+    const int maxpre = __reduce_max_sync(FULL, have ? (fs - (e - 1)) : 0);
+    const int total = maxpre + __reduce_max_sync(FULL, len);
+
+    double Cq[NH][N];
+    double sg[NH], sgd[NH], sgdd[NH], muq[NH];
+#pragma unroll
+    for (int ii = 0; ii < NH; ++ii) {
+        sg[ii] = sgd[ii] = sgdd[ii] = 0.0;
+        muq[ii] = pick_row<N, G, NH>(P.mu, q, ii);
+#pragma unroll
+        for (int j = 0; j < N; ++j) Cq[ii][j] = 0.0;
+    }
+    double bt[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) bt[j] = 0.0;
+    const double2* il = reinterpret_cast<const double2*>(a.alpha_il) + il_base(c, a.Lmax, NP2);
+
+    auto frame_of = [&](int s) -> int { return (e - 1) + maxpre - s; };
+    auto fetch = [&](int s) -> double {
+        int f = frame_of(s);
+        if (!have) return 0.0;
+        f = min(max(f, t0), T - 1);
+        if (EM == EM_GAUSS) return __ldg(a.obs + trow + f);
+        return __longlong_as_double((long long)__ldg(a.sym + trow + f));
+    };
+    double ring[PF];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) ring[k] = fetch(k);
+    auto emission = [&](double rawv, double (&pv)[N]) {
+        if (EM == EM_GAUSS) emission_gauss<N>(P, rawv, a.ignore_outliers, pv);
+        else emission_disc<N>(a, (int)__double_as_longlong(rawv), pv);
+    };
+    double pn[N];                   // emission of frame f+1, evaluated during the previous step
+#pragma unroll
+    for (int j = 0; j < N; ++j) pn[j] = 0.0;
+#if !LANE_PIPE_EMIS
+    double raw_next = 0.0;          // emission input of frame f+1
+#endif
+#if LANE_ALPHA_MODE == 2
+    double2 aln[NP2];               // forward variables of the next frame to emit, loaded one step ahead
+    {
+        const double2* src0 = il + ((long long)max(len - 1, 0) * NP2 << 5);
+#pragma unroll
+        for (int jp = 0; jp < NP2; ++jp) aln[jp] = have ? __ldcs(src0 + (jp << 5)) : make_double2(0.0, 0.0);
+    }
+#endif
+
+    for (int s = 0; s < total; ++s) {
+        {
+            {
+                const double raw = ring[0];                 // emission input of frame f
+#pragma unroll
+                for (int k = 0; k + 1 < PF; ++k) ring[k] = ring[k + 1];
+                ring[PF - 1] = fetch(s + PF);
+                const int f = frame_of(s);
+                double p[N];
+#if LANE_PIPE_EMIS
+#pragma unroll
+                for (int j = 0; j < N; ++j) p[j] = pn[j];
+                emission(raw, pn);                          // p_f, consumed by the next step (frame f-1)
+#else
+                emission(raw_next, p);
+#endif
+#if LANE_ALPHA_MODE == 2
+                double2 alc[NP2];
+#pragma unroll
+                for (int jp = 0; jp < NP2; ++jp) alc[jp] = aln[jp];
+                if (have && f - 1 >= t0 && f - 1 < e) {
+                    const double2* nxt = il + ((long long)(f - 1 - t0) * NP2 << 5);
+#pragma unroll
+                    for (int jp = 0; jp < NP2; ++jp) aln[jp] = __ldcs(nxt + (jp << 5));
+                }
+#endif
+                const bool on = have && f <= fs && f >= t0;
+                const bool init = on && f == fs;
+                const bool emit = on && f < e;
+                double w[N], u[N], gam[N];
+#pragma unroll
+                for (int j = 0; j < N; ++j) { w[j] = 0.0; u[j] = 0.0; gam[j] = 0.0; }
+                double o_f = 0.0;
+#if LANE_ALPHA_MODE != 2
+                if (have && f - 1 >= t0 && f - 1 < e) {
+                    const double2* nxt = il + ((long long)(f - 1 - t0) * NP2 << 5);
+#pragma unroll
+                    for (int jp = 0; jp < NP2; ++jp) prefetch_l1(nxt + (jp << 5));
+                }
+#endif
+                if (on) {
+                    double b[N];
+                    if (init) {
+                        if (mode == 2) {
+#pragma unroll
+                            for (int j = 0; j < N; ++j) b[j] = a.hand_end[(long long)(c + 1) * N + j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < N; ++j) b[j] = 1.0;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < N; ++j) w[j] = p[j] * bt[j];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) b[i] = P.A[i * N] * w[0];
+#pragma unroll
+                        for (int j = 1; j < N; ++j) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) b[i] = fma(P.A[i * N + j], w[j], b[i]);
+                        }
+                    }
+                    if (emit) {
+                        // gamma_f = alpha_f o b / S ; xi_f = (alpha_f / S) (x) w   with S = sum_i alpha_f,i b_i
+                        double al[N];
+#if LANE_ALPHA_MODE != 2
+                        const double2* src = il + ((long long)(f - t0) * NP2 << 5);
+#endif
+#pragma unroll
+                        for (int jp = 0; jp < NP2; ++jp) {
+#if LANE_ALPHA_MODE == 2
+                            const double2 v2 = alc[jp];
+#elif LANE_ALPHA_MODE == 1
+                            const double2 v2 = src[jp << 5];
+#else
+                            const double2 v2 = __ldcs(src + (jp << 5));
+#endif
+                            al[2 * jp] = v2.x;
+                            if (2 * jp + 1 < N) al[2 * jp + 1] = v2.y;
+                        }
+                        double gi[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) gi[i] = al[i] * b[i];
+                        const double S = tree_sum<N>(gi);
+                        const double rS = 1.0 / S;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            u[i] = al[i] * rS;
+                            gam[i] = u[i] * b[i];
+                        }
+                        if (EM == EM_GAUSS) o_f = raw;
+                        if (f == 0) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) a.g0buf[(long long)c * N + i] = gam[i];
+                        }
+                        if (a.gamma) {
+                            double* dst = a.gamma + (trow + f) * N;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) dst[i] = gam[i];
+                        }
+                        if (EM == EM_DISC && a.Bnum) {
+                            const int sy = (int)__double_as_longlong(raw);
+#pragma unroll
+                            for (int i = 0; i < N; ++i) atomicAdd(a.Bnum + (long long)i * a.M + sy, gam[i]);
+                        }
+                    }
+                    const double sb = tree_sum<N>(b);
+                    const double rsb = (sb != 0.0) ? 1.0 / sb : 1.0;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) bt[i] = b[i] * rsb;
+                    if (f == e) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) a.hand_used[(long long)c * N + i] = bt[i];
+                    }
+                    if (f == t0 && t0 > 0) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) a.hand_end[(long long)c * N + i] = bt[i];
+                    }
+#if !LANE_PIPE_EMIS
+                    raw_next = raw;
+#endif
+                }
+                // ---- statistics: lane q owns rows q*NH .. q*NH+NH-1 for every chain of its lane group
+#pragma unroll
+                for (int d = 0; d < G; ++d) {
+                    double ur[NH], gr[NH];
+                    double od;
+                    if (d == 0) {
+#pragma unroll
+                        for (int ii = 0; ii < NH; ++ii) {
+                            ur[ii] = pick_row<N, G, NH>(u, q, ii);
+                            gr[ii] = pick_row<N, G, NH>(gam, q, ii);
+                        }
+                        od = o_f;
+                    } else {
+                        // the partner lane^d owns rows (q^d)*NH..: send it those rows of my u and gamma, receive mine
+#pragma unroll
+                        for (int ii = 0; ii < NH; ++ii) {
+                            ur[ii] = __shfl_xor_sync(FULL, pick_row<N, G, NH>(u, q ^ d, ii), d);
+                            gr[ii] = __shfl_xor_sync(FULL, pick_row<N, G, NH>(gam, q ^ d, ii), d);
+                        }
+                        od = __shfl_xor_sync(FULL, o_f, d);
+                    }
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const double wj = (d == 0) ? w[j] : __shfl_xor_sync(FULL, w[j], d);
+#pragma unroll
+                        for (int ii = 0; ii < NH; ++ii) Cq[ii][j] = fma(ur[ii], wj, Cq[ii][j]);
+                    }
+#pragma unroll
+                    for (int ii = 0; ii < NH; ++ii) {
+                        sg[ii] += gr[ii];
+                        if (EM == EM_GAUSS) {
+                            const double dd = od - muq[ii];
+                            sgd[ii] = fma(gr[ii], dd, sgd[ii]);
+                            sgdd[ii] = fma(gr[ii], dd * dd, sgdd[ii]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- reduce over the lanes that own the same rows (lane bits >= log2 G), then over the block's warps
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+        for (int ii = 0; ii < NH; ++ii) {
+            sg[ii] += __shfl_xor_sync(FULL, sg[ii], off);
+            sgd[ii] += __shfl_xor_sync(FULL, sgd[ii], off);
+            sgdd[ii] += __shfl_xor_sync(FULL, sgdd[ii], off);
+#pragma unroll
+            for (int j = 0; j < N; ++j) Cq[ii][j] += __shfl_xor_sync(FULL, Cq[ii][j], off);
+        }
+    }
+    double* myred = red + (threadIdx.x >> 5) * NSTAT;
+    if (lane < G) {
+#pragma unroll
+        for (int ii = 0; ii < NH; ++ii) {
+            const int i = q * NH + ii;
+            if (i < N) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) myred[i * N + j] = Cq[ii][j];
+                myred[N * N + i] = 0.0;                       // gamma0 travels through g0buf
+                myred[N * N + N + i] = sg[ii];
+                myred[N * N + 2 * N + i] = sgd[ii];
+                myred[N * N + 3 * N + i] = sgdd[ii];
+            }
+        }
+    }
+    __syncthreads();
+    double* out = a.partials + (long long)blockIdx.x * NSTAT;
+    for (int k = threadIdx.x; k < NSTAT; k += blockDim.x) {
+        double v = 0.0;
+#pragma unroll
+        for (int wp = 0; wp < LANE_THREADS / 32; ++wp) v += red[wp * NSTAT + k];
+        out[k] = v;
+    }
+}
+
+template <int N>
+void fill_params(LaneParams<N>& P, const double* A, const double* pi, const double* mu, const double* sigma)
+{
+    for (int k = 0; k < N * N; ++k) P.A[k] = A[k];
+    for (int j = 0; j < N; ++j) {
+        P.pi[j] = pi ? pi[j] : 0.0;
+        P.mu[j] = mu ? mu[j] : 0.0;
+        const double s = sigma ? sigma[j] : 1.0;
+        P.isg[j] = 1.0 / s;
+        P.nrm[j] = 1.0 / (sqrt(2.0 * 3.14159265358979323846) * s);   // C of _gaussian.c:18
+    }
+}
+
+template <int N>
+constexpr int group_of()
+{
+    return N <= 5 ? 1 : (N <= 8 ? 2 : (N <= 12 ? LANE_G_MID : 8));
+}
+
+template <int N>
+int launch_lane_n(const LaneArgs& a, const LaneHostParams& hp, int em, int what, cudaStream_t st)
+{
+    LaneParams<N> P;
+    fill_params<N>(P, hp.A, hp.pi, hp.mu, hp.sigma);
+    const int blocks = (a.ch.n + LANE_THREADS - 1) / LANE_THREADS;
+    if (blocks <= 0) return BHMM_OK;
+    constexpr int G = group_of<N>();
+    if (what == LANE_FORWARD) {
+        if (em == EM_GAUSS) k_forward_lane<N, EM_GAUSS, false><<<blocks, LANE_THREADS, 0, st>>>(P, a);
+        else k_forward_lane<N, EM_DISC, false><<<blocks, LANE_THREADS, 0, st>>>(P, a);
+    } else if (what == LANE_FORWARD_ROWMAJOR) {
+        if (em == EM_GAUSS) k_forward_lane<N, EM_GAUSS, true><<<blocks, LANE_THREADS, 0, st>>>(P, a);
+        else k_forward_lane<N, EM_DISC, true><<<blocks, LANE_THREADS, 0, st>>>(P, a);
+    } else {
+        if (em == EM_GAUSS) k_backward_stats_lane<N, EM_GAUSS, G><<<blocks, LANE_THREADS, 0, st>>>(P, a);
+        else k_backward_stats_lane<N, EM_DISC, G><<<blocks, LANE_THREADS, 0, st>>>(P, a);
+    }
+    return BHMM_OK;
+}
+
+}  // namespace
+
+// one translation unit per group of N (compiled in parallel): lane_inst_*.cu
+#define LANE_INSTANTIATE(NN) \
+    int launch_lane_##NN(const LaneArgs& a, const LaneHostParams& hp, int em, int what, cudaStream_t st) \
+    { return launch_lane_n<NN>(a, hp, em, what, st); }

@@ -110,7 +110,7 @@ __global__ void k_forward_team(const FwdArgs a)
             trow = a.ch.row0[c] - t0;
             if (t0 == 0) { tstart = 0; mode = 0; }
             else if (a.ch.exact) { tstart = t0 - 1; mode = 2; }
-            else { tstart = max(0, t0 - a.ch.warm); mode = (tstart == 0) ? 0 : 1; }
+            else { tstart = max(0, t0 - (a.ch.warmv ? a.ch.warmv[c] : a.ch.warm)); mode = (tstart == 0) ? 0 : 1; }
         }
         const int npre = have ? (t0 - tstart) : 0;
         const int maxpre = block_max(npre);
@@ -224,7 +224,7 @@ __global__ void k_backward_team(const BwdArgs a)
             e = t0 + len;
             if (e >= T) { virt = true; fstart = STATS ? T : T - 1; }
             else if (a.ch.exact) { fstart = e; mode = 2; }
-            else { fstart = min(T - 1, e + a.ch.warm - 1); }
+            else { fstart = min(T - 1, e + (a.ch.warmv ? a.ch.warmv[c] : a.ch.warm) - 1); }
         }
         // literal backward emits frame f at step f; STATS emits frame f-1 at step f.
         const int flast = STATS ? t0 + 1 : t0;

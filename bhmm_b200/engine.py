@@ -134,6 +134,11 @@ class TrajectoryBatch(object):
         return dict(chains=int(info[0]), chunk=int(info[1]), warm=int(info[2]), fixups_fwd=int(info[3]),
                     fixups_bwd=int(info[4]), worst_fwd=float(info[5]), worst_bwd=float(info[6]), rerun=int(info[7]))
 
+    @property
+    def uses_lane_kernels(self):
+        """True when the small-N one-thread-per-chain kernels run (N <= 16), False for the general-N team kernels."""
+        return bool(lib.bhmm_b200_batch_uses_lane_kernels(self._handle))
+
     def set_profiling(self, on=True):
         """Record CUDA events around the forward and the backward+statistics kernels of every E-step."""
         check(lib.bhmm_b200_batch_set_profiling(self._handle, int(bool(on))))

@@ -120,6 +120,9 @@ typedef struct bhmm_b200_batch bhmm_b200_batch;
 int bhmm_b200_batch_create(bhmm_b200_batch** out, const long long* offsets, int K, int N, int chunk, int warm);
 void bhmm_b200_batch_destroy(bhmm_b200_batch* b);
 int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm);
+/* 1 when the batch runs the small-N one-thread-per-chain kernels (N <= 16), 0 for the general-N team kernels.
+ * The environment variable BHMM_B200_FAMILY=team forces the latter at creation time. */
+int bhmm_b200_batch_uses_lane_kernels(const bhmm_b200_batch* b);
 size_t bhmm_b200_batch_workspace_bytes(const bhmm_b200_batch* b);
 int bhmm_b200_batch_attach_workspace(bhmm_b200_batch* b, void* d_workspace, size_t bytes);
 /* info[0]=chains, [1]=chunk, [2]=warm, [3]=fwd fix-up sweeps, [4]=bwd fix-up sweeps, [5]=worst fwd mismatch,

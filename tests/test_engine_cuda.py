@@ -16,6 +16,17 @@ def eng():
     return e
 
 
+@pytest.fixture(autouse=True, params=['lane', 'team'])
+def family(request, monkeypatch):
+    """Every engine test runs twice: with the small-N one-thread-per-chain kernels (where N <= 16 allows) and with
+    the general-N team kernels forced (BHMM_B200_FAMILY is read when a batch is created)."""
+    if request.param == 'team':
+        monkeypatch.setenv('BHMM_B200_FAMILY', 'team')
+    else:
+        monkeypatch.delenv('BHMM_B200_FAMILY', raising=False)
+    return request.param
+
+
 def oracle_stats_gaussian(oracle, obs, A, pi, means, sigmas):
     st = oracle.estep_gaussian(obs, A, pi, means, sigmas)
     wd = sum(g.T.dot(o) for g, o in zip(st['gammas'], obs)) - means * st['wsum']
@@ -31,11 +42,12 @@ def em_obs(g):
 
 
 @pytest.mark.parametrize('chunk,warm', [(0, 0), (200, 150), (64, 4), (5000, 10)])
-def test_estep_gaussian_statistics(eng, oracle_port, golden, chunk, warm):
+def test_estep_gaussian_statistics(eng, oracle_port, golden, family, chunk, warm):
     g = golden('em_gauss3')
     obs = em_obs(g)
     A, pi, means, sigmas = g['A0'], g['pi0'], g['means0'], g['sigmas0']
     batch = eng.TrajectoryBatch(obs, 3, chunk=chunk, warm=warm)
+    assert batch.uses_lane_kernels == (family == 'lane')
     st = eng.unpack_stats(batch.estep_gaussian(A, pi, means, sigmas).cpu().numpy(), 3)
     ref, wd, wdd = oracle_stats_gaussian(oracle_port, obs, A, pi, means, sigmas)
     assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])

@@ -7,7 +7,8 @@ from bhmm_b200 import _lib
 from bhmm_b200.engine import TrajectoryBatch, unpack_stats
 from bhmm_b200.util import testsystems as ts
 
-for N, T in [(3, 700), (10, 900), (40, 300)]:
+import os
+for N, T in [(3, 700), (10, 900), (16, 300), (40, 300)]:
     pi, A, means, sigmas, O, S = ts.gaussian_observations(N, 3, T, seed=N)
     from bhmm_b200.output_models import GaussianOutputModel
     pobs = GaussianOutputModel(N, means=means, sigmas=sigmas).p_obs(O[0])
