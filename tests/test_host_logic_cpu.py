@@ -1,0 +1,96 @@
+"""Host-side logic that needs no GPU: M-step from sufficient statistics, transition-matrix helpers, trajectory
+sharding, synthetic test systems."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+
+def test_gaussian_mstep_from_shifted_moments_equals_reference_two_pass(oracle_port):
+    """GaussianOutputModel.estimate_from_statistics (shifted one-pass moments) == gaussian.py:214-272 (two passes)."""
+    from bhmm_b200.output_models import GaussianOutputModel
+    rng = np.random.default_rng(0)
+    N = 4
+    means0, sig0 = np.array([-3.0, -0.5, 0.7, 4.0]), np.array([0.6, 1.0, 0.8, 1.5])
+    obs = [rng.normal(size=T) * 3.0 for T in (500, 333)]
+    gammas = [rng.dirichlet(np.ones(N), size=len(o)) for o in obs]
+    ref_m, ref_s = orc.mstep_gaussian(obs, gammas)
+    wsum = sum(g.sum(axis=0) for g in gammas)
+    wd = sum((g * (o[:, None] - means0)).sum(axis=0) for g, o in zip(gammas, obs))
+    wdd = sum((g * (o[:, None] - means0) ** 2).sum(axis=0) for g, o in zip(gammas, obs))
+    om = GaussianOutputModel(N, means=means0, sigmas=sig0)
+    om.estimate_from_statistics(wsum, wd, wdd)
+    np.testing.assert_allclose(om.means, ref_m, rtol=1e-12)
+    np.testing.assert_allclose(om.sigmas, ref_s, rtol=1e-11)
+
+
+def test_discrete_mstep_and_estimate_P():
+    from bhmm_b200.output_models import DiscreteOutputModel
+    from bhmm_b200.util import tmatrix
+    Bnum = np.array([[1.0, 3.0, 0.0], [2.0, 2.0, 4.0]])
+    om = DiscreteOutputModel(np.full((2, 3), 1.0 / 3))
+    om.estimate_from_statistics(Bnum)
+    np.testing.assert_allclose(om.output_probabilities, orc.mstep_discrete(Bnum))
+    C = np.array([[5.0, 1.0, 0.0], [2.0, 6.0, 0.0], [0.0, 0.0, 0.0]])
+    P = tmatrix.estimate_P(C, reversible=False, mincount_connectivity=1e-16)
+    np.testing.assert_allclose(P[:2, :2], C[:2, :2] / C[:2, :2].sum(axis=1)[:, None])
+    assert P[2, 2] == 1.0 and tmatrix.is_transition_matrix(P)
+    assert not tmatrix.is_connected(C)
+    # reversible estimator (parity-unpinned): check its defining properties
+    Cr = np.array([[10.0, 2.0, 1.0], [3.0, 20.0, 4.0], [0.5, 5.0, 8.0]])
+    Pr = tmatrix.estimate_P(Cr, reversible=True, maxerr=1e-14)
+    assert tmatrix.is_transition_matrix(Pr) and tmatrix.is_reversible(Pr)
+    pi = tmatrix.stationary_distribution(Pr)
+    np.testing.assert_allclose(pi[:, None] * Pr, (pi[:, None] * Pr).T, atol=1e-10)
+    ll = lambda P: np.sum(Cr * np.log(P))
+    assert ll(Pr) <= ll(Cr / Cr.sum(axis=1)[:, None]) + 1e-9      # cannot beat the unconstrained MLE
+    assert ll(Pr) >= ll(0.5 * (Pr + np.full((3, 3), 1 / 3.0)))    # ... but beats a perturbed reversible-ish matrix
+
+
+def test_hmm_container_and_path_statistics(golden):
+    from bhmm_b200 import HMM, GaussianOutputModel
+    g = golden('gibbs_gauss3')
+    K = len(g['lengths'])
+    hm = HMM(g['pi'], g['A'], GaussianOutputModel(3, means=g['means'], sigmas=g['sigmas']))
+    hm.hidden_state_trajectories = [g['path%d' % k] for k in range(K)]
+    assert np.array_equal(hm.count_matrix(), g['count_matrix'])
+    assert np.array_equal(hm.count_init(), g['count_init'])
+    obs = [g['obs%d' % k] for k in range(K)]
+    for i in range(3):
+        oi = hm.collect_observations_in_state(obs, i)
+        assert len(oi) == int(g['obs_in_state_n%d' % i])
+        np.testing.assert_allclose(np.mean(oi), float(g['obs_in_state_mean%d' % i]), rtol=1e-13)
+    with pytest.raises(AssertionError):
+        hm.update(g['pi'], g['A'] * 2.0)
+
+
+def test_shard_bounds_partition_every_trajectory_once():
+    from bhmm_b200 import dist
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 4, 8):
+        for K in (1, 2, 7, 8, 100):
+            lengths = rng.integers(1, 1000, size=K)
+            cuts = [dist.shard_bounds(lengths, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == K
+            for (a, b), (c, d) in zip(cuts[:-1], cuts[1:]):
+                assert b == c and a <= b
+            if K >= 4 * world:
+                frames = [lengths[a:b].sum() for a, b in cuts]
+                assert max(frames) <= 2.0 * lengths.sum() / world + lengths.max()
+    assert dist.shard_bounds([10] * 8, 1, 2) == (4, 8)
+
+
+def test_testsystems_recipe():
+    from bhmm_b200.util import testsystems as ts
+    pi, A, means, sigmas, O, S = ts.gaussian_observations(5, 3, 2000, seed=4)
+    assert O.shape == (3, 2000) and S.max() < 5
+    np.testing.assert_allclose(A.sum(axis=1), 1.0)
+    np.testing.assert_allclose(pi @ A, pi, atol=1e-12)
+    np.testing.assert_allclose(means, np.linspace(-5, 5, 5))
+    lifetimes = 1.0 / (1.0 - np.diag(A))
+    np.testing.assert_allclose(lifetimes, np.exp(np.linspace(np.log(10), np.log(100), 5)), rtol=1e-10)
+    pi, A, B, Od, Sd = ts.discrete_observations(6, 40, 2, 500, seed=1)
+    assert Od.dtype == np.int32 and Od.max() < 40 and Od.min() >= 0
+    pi0, A0, m0, s0 = ts.perturbed_initial_model(A, np.linspace(-5, 5, 6), 6)
+    np.testing.assert_allclose(A0.sum(axis=1), 1.0)
+    assert not np.allclose(A0, A0.T)       # asymmetric on purpose: selects the non-reversible M-step
