@@ -118,12 +118,17 @@ int auto_chunk_lane(long long rows, int N, int warm)
     return (int)std::min<long long>(c, 1 << 30);
 }
 
-int adapt_warm(int current, double need, bool failed, int warm_min, int warm_cap)
+int adapt_warm(int current, double need, double worst, bool failed, int warm_min, int warm_cap)
 {
-    double target = 1.3 * need;
-    if (failed) target = std::max(target, current + 32.0);
-    else target = std::max(target, 0.9 * current);
-    int w = (int)std::ceil(target / 32.0) * 32;
+    // Keep the warm-up ~15 % above what the hardest hand-over needs.  `need` (= w log tol / log m) is only
+    // informative while the mismatch m is above the rounding-noise floor of two independently rounded filters
+    // (~1e-14); at the floor the warm-up is known to be more than enough, so it shrinks slowly until the mismatch
+    // becomes measurable again (still one decade below the tolerance).
+    double target;
+    if (failed) target = std::max(1.15 * need, current + 32.0);
+    else if (worst <= 1e-14) target = 0.95 * current;
+    else target = std::max(1.15 * need, 0.95 * current);
+    int w = (int)std::ceil(target / 16.0) * 16;
     w = std::max(w, warm_min);
     return std::min(w, std::max(warm_cap, 1));
 }

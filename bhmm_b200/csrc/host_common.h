@@ -67,9 +67,8 @@ struct ChainWork {
     int warm_cap = 1;            // longest trajectory: a warm-up that long is an exact start
     double need_f = 0, need_b = 0;   // certification's estimate of the warm-up the hardest hand-over needs
 };
-// next warm-up length from the current one and the certification's need estimate: 30 % above the need, decreasing by
-// at most 10 % per pass, a multiple of 32 frames
-int adapt_warm(int current, double need, bool failed, int warm_min, int warm_cap);
+// next warm-up length from the current one, the certification's need estimate and the largest mismatch of the pass
+int adapt_warm(int current, double need, double worst, bool failed, int warm_min, int warm_cap);
 size_t chainwork_bytes(int n_chains, int N);
 // carve ChainWork out of `base` (device) and upload the plan; returns bytes used
 int chainwork_setup(ChainWork& w, const HostPlan& p, int N, int warm, char* base, cudaStream_t st);

@@ -50,8 +50,9 @@ struct LaneParams {          // passed by value as a __grid_constant__ kernel pa
     double A[N * N];
     double pi[N];
     double mu[N];
-    double isg[N];           // 1 / sigma
-    double nrm[N];           // 1 / (sqrt(2 pi) sigma)
+    double isg[N];           // 1 / (sqrt(2) sigma)
+    double nrm[N];           // log(1 / (sqrt(2 pi) sigma))
+    double nrml[N];          // 1 / (sqrt(2 pi) sigma)   (comparison build LANE_FOLD_NRM=0 only)
 };
 struct LaneHostParams {      // HOST pointers
     const double* A;

@@ -44,6 +44,12 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef LANE_PIPE_EMIS
 #define LANE_PIPE_EMIS 0     // emission of the NEXT frame is evaluated during the current step (independent work that
 #endif                       // fills the latency of the step's dependent chain: sums, reciprocals)
+#ifndef LANE_FOLD_NRM
+#define LANE_FOLD_NRM 1      // Gaussian normalisation constant folded into the exponent's argument (one FMA less per state)
+#endif
+#ifndef LANE_CONST_SMEM
+#define LANE_CONST_SMEM 1    // model constants (A, mu, isg, nrm) are read from shared memory into vector registers (LDS
+#endif                       // broadcast) instead of the uniform datapath (LDCU / R2UR), whose 63 registers thrash at N=10
 #ifndef LANE_G_MID
 #define LANE_G_MID 4         // lanes sharing the xi accumulator rows for 9 <= N <= 12
 #endif
@@ -82,15 +88,21 @@ __constant__ double EXPK[13] = {
 // dependent chains interleave and hide the FP64 latency.  exp(x) = 2^n exp(r), n = rint(x/ln2), |r| <= ln2/2,
 // degree-11 near-minimax polynomial (< 1 ulp).  The main path is branch free; states whose argument lies below
 // -708 (result denormal or zero) or is NaN are redone with the library exp() in a rarely taken tail.
-template <int N>
-__device__ __forceinline__ void emission_gauss(const LaneParams<N>& P, double o, int ignore_outliers, double (&p)[N])
+template <int N, typename CV>
+__device__ __forceinline__ void emission_gauss(const CV& P, double o, int ignore_outliers, double (&p)[N])
 {
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
     double x[N], t[N], r[N];
+    // x = log(nrm) - ((o - mu) * isg/sqrt2)^2 in one FMA: the normalisation constant rides in the exponent's
+    // argument (same half-ulp rounding of x as without it) instead of costing a multiplication at the end
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const double d = (o - P.mu[j]) * P.isg[j];
-        x[j] = -0.5 * (d * d);
+#if LANE_FOLD_NRM
+        x[j] = fma(-d, d, P.nrm[j]);
+#else
+        x[j] = -(d * d);
+#endif
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) t[j] = fma(x[j], EXPK[10], MAGIC);
@@ -115,13 +127,16 @@ __device__ __forceinline__ void emission_gauss(const LaneParams<N>& P, double o,
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const int ni = __double2loint(t[j]);
-        p[j] = __longlong_as_double(__double_as_longlong(p[j]) + ((long long)ni << 52)) * P.nrm[j];
+        p[j] = __longlong_as_double(__double_as_longlong(p[j]) + ((long long)ni << 52));
+#if !LANE_FOLD_NRM
+        p[j] *= P.nrml[j];          // (comparison build only)
+#endif
         tail |= !(x[j] >= -708.0);
     }
     if (tail) {
 #pragma unroll
         for (int j = 0; j < N; ++j)
-            if (!(x[j] >= -708.0)) p[j] = P.nrm[j] * exp(x[j]);
+            if (!(x[j] >= -708.0)) p[j] = exp(x[j]);
     }
     bool anynz = false;
 #pragma unroll
@@ -163,6 +178,29 @@ struct LogAcc {
     __device__ __forceinline__ double value() const { return (double)esum * 0.693147180559945309417 + log(prod) + slow; }
 };
 
+// Power-of-two renormalisation: v *= 2^-shift with shift = (biased exponent of the largest component) - 1023, done
+// on the high words with integer instructions (exact, and off the FP64 pipe).  Components more than 2^-1022 below
+// the largest one (or denormal) are flushed to zero.  Returns false when the largest component is tiny (< 2^-959),
+// zero, negative or not finite: the caller then normalises by the sum like the reference does.
+template <int N>
+__device__ __forceinline__ bool scale_pow2(double (&v)[N], int& shift)
+{
+    int hmax = __double2hiint(v[0]);
+#pragma unroll
+    for (int j = 1; j < N; ++j) hmax = max(hmax, __double2hiint(v[j]));
+    const int e = hmax >> 20;
+    if (e < 64 || e >= 0x7ff) return false;
+    shift = e - 1023;
+    const int dh = shift << 20;
+    const int floor_e = max(shift, 0);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const int h = __double2hiint(v[j]);
+        v[j] = ((h >> 20) > floor_e) ? __hiloint2double(h - dh, __double2loint(v[j])) : 0.0;
+    }
+    return true;
+}
+
 __device__ __forceinline__ long long il_base(int c, int Lmax, int NP2)
 {
     // index (in double2 units) of alpha_il[chain c][frame 0][pair 0]
@@ -172,12 +210,50 @@ __device__ __forceinline__ long long il_base(int c, int Lmax, int NP2)
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// Every lane of a warp walks its own chain in lock step (frame index relative to the chain start is the same in all
+// lanes, so the interleaved stores coalesce).  Each step is dispatched on a warp-uniform vote to one of three code
+// paths: CHAIN (every lane is inside its chain: straight-line code, no predicates), WARM (every lane is warming up:
+// no stores, no likelihood) and GENERAL (mixed lanes, first frames, hand-over frames).  The two fast paths are single
+// basic blocks, which is what lets the compiler interleave the N exp() chains with the matvec.
+template <int V> struct BoolTag2 { static constexpr int value = V; };
+
+// Where the kernels read the model constants from: the kernel parameter itself (uniform datapath) or a copy of it in
+// shared memory (plain LDS into vector registers).  Same member names either way.
+template <int N>
+struct ConstView {
+    const double* A;
+    const double* pi;
+    const double* mu;
+    const double* isg;
+    const double* nrm;
+    const double* nrml;
+};
+template <int N>
+__device__ __forceinline__ ConstView<N> make_const_view(const LaneParams<N>& P, double* smem)
+{
+    // layout of LaneParams is [A | pi | mu | isg | nrm | nrml], all doubles
+    constexpr int TOT = sizeof(LaneParams<N>) / sizeof(double);
+    const double* src = reinterpret_cast<const double*>(&P);
+    for (int k = threadIdx.x; k < TOT; k += blockDim.x) smem[k] = src[k];
+    __syncthreads();
+    ConstView<N> v;
+    v.A = smem; v.pi = smem + N * N; v.mu = v.pi + N; v.isg = v.mu + N; v.nrm = v.isg + N; v.nrml = v.nrm + N;
+    return v;
+}
+enum { PATH_GENERAL = 0, PATH_CHAIN = 1, PATH_WARM = 2 };
+
 template <int N, int EM, bool ROWMAJOR>
 __global__ void __launch_bounds__(LANE_THREADS, LANE_MINB_F)
-k_forward_lane(const __grid_constant__ LaneParams<N> P, const LaneArgs a)
+k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
 {
     constexpr int NP2 = (N + 1) / 2;
     constexpr int PF = 4;
+#if LANE_CONST_SMEM
+    __shared__ double cs[sizeof(LaneParams<N>) / sizeof(double)];
+    const ConstView<N> P = make_const_view<N>(Pk, cs);
+#else
+    const LaneParams<N>& P = Pk;
+#endif
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool have = idx < a.ch.n;
     int c = 0, len = 0, t0 = 0, tstart = 0, mode = 0;        // mode 0: pi, 1: uniform warm-up, 2: exact vector
@@ -202,7 +278,8 @@ k_forward_lane(const __grid_constant__ LaneParams<N> P, const LaneArgs a)
 #pragma unroll
         for (int j = 0; j < N; ++j) al[j] = a.hand_end[(long long)(c - 1) * N + j];
     }
-    LogAcc ll;
+    long long esum = 0;             // sum of the power-of-two shifts applied to the chain's own frames
+    double slow = 0.0, log_start = 0.0, log_end = 0.0;
     double2* il = reinterpret_cast<double2*>(a.alpha_il) + il_base(c, a.Lmax, NP2);
 
     auto fetch = [&](int s) -> double {
@@ -212,8 +289,7 @@ k_forward_lane(const __grid_constant__ LaneParams<N> P, const LaneArgs a)
         if (EM == EM_GAUSS) return __ldg(a.obs + trow + t);
         return __longlong_as_double((long long)__ldg(a.sym + trow + t));
     };
-    // observations are fetched PF frames ahead into a rotating register ring (no unrolling: the loop body stays
-    // small enough for the instruction cache)
+    // observations are fetched PF frames ahead into a rotating register ring
     double ring[PF];
 #pragma unroll
     for (int k = 0; k < PF; ++k) ring[k] = fetch(k);
@@ -221,80 +297,93 @@ k_forward_lane(const __grid_constant__ LaneParams<N> P, const LaneArgs a)
         if (EM == EM_GAUSS) emission_gauss<N>(P, rawv, a.ignore_outliers, pv);
         else emission_disc<N>(a, (int)__double_as_longlong(rawv), pv);
     };
-#if LANE_PIPE_EMIS
-    double pn[N];
-    emission(ring[0], pn);
-#endif
 
-    for (int s = 0; s < total; ++s) {
-        {
-            {
-                const double raw = ring[0];
+    // one frame of the recursion; PATH is a compile-time constant so that the fast paths carry no predicates
+    auto step = [&](auto path_tag, int t, double raw, bool on) {
+        constexpr int PATH = decltype(path_tag)::value;
+        if (!on) return;
+        const bool init = (PATH == PATH_GENERAL) && (t == tstart);
+        double v[N];
+        if (init && mode == 2) {
 #pragma unroll
-                for (int k = 0; k + 1 < PF; ++k) ring[k] = ring[k + 1];
-                ring[PF - 1] = fetch(s + PF);
-                double p[N];
-#if LANE_PIPE_EMIS
+            for (int j = 0; j < N; ++j) v[j] = al[j];
+        } else {
+            double p[N];
+            emission(raw, p);
+            if (init) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) p[j] = pn[j];
-                emission(ring[0], pn);                       // next frame's emission: independent of this step
-#else
-                emission(raw, p);
-#endif
-                (void)raw;
-                const int t = t0 - maxpre + s;
-                const bool on = have && t >= tstart && t < tend;
-                if (on) {
-                    const bool init = (t == tstart);
-                    double v[N];
-                    if (init && mode == 2) {
+                for (int j = 0; j < N; ++j) v[j] = (mode == 0) ? P.pi[j] * p[j] : p[j];
+            } else {
 #pragma unroll
-                        for (int j = 0; j < N; ++j) v[j] = al[j];
-                    } else {
-                        if (init) {
+                for (int j = 0; j < N; ++j) v[j] = al[0] * P.A[j];
 #pragma unroll
-                            for (int j = 0; j < N; ++j) v[j] = (mode == 0) ? P.pi[j] * p[j] : p[j];
-                        } else {
+                for (int i = 1; i < N; ++i) {
 #pragma unroll
-                            for (int j = 0; j < N; ++j) v[j] = al[0] * P.A[j];
-#pragma unroll
-                            for (int i = 1; i < N; ++i) {
-#pragma unroll
-                                for (int j = 0; j < N; ++j) v[j] = fma(al[i], P.A[i * N + j], v[j]);
-                            }
-#pragma unroll
-                            for (int j = 0; j < N; ++j) v[j] *= p[j];
-                        }
-                    }
-                    const double csum = tree_sum<N>(v);
-                    const double rc = (csum != 0.0) ? 1.0 / csum : 1.0;
-#pragma unroll
-                    for (int j = 0; j < N; ++j) al[j] = v[j] * rc;
-                    if (t >= t0) {
-                        ll.add(csum);
-                        if (ROWMAJOR) {
-                            double* dst = a.alpha_rm + (trow + t) * N;
-#pragma unroll
-                            for (int j = 0; j < N; ++j) dst[j] = al[j];
-                        } else {
-                            double2* dst = il + ((long long)(t - t0) * NP2 << 5);
-#pragma unroll
-                            for (int jp = 0; jp < NP2; ++jp)
-                                __stcs(dst + (jp << 5), make_double2(al[2 * jp], (2 * jp + 1 < N) ? al[2 * jp + 1] : 0.0));
-                        }
-                        if (t == tend - 1) {
-#pragma unroll
-                            for (int j = 0; j < N; ++j) a.hand_end[(long long)c * N + j] = al[j];
-                        }
-                    } else if (t == t0 - 1) {
-#pragma unroll
-                        for (int j = 0; j < N; ++j) a.hand_used[(long long)c * N + j] = al[j];
-                    }
+                    for (int j = 0; j < N; ++j) v[j] = fma(al[i], P.A[i * N + j], v[j]);
                 }
+#pragma unroll
+                for (int j = 0; j < N; ++j) v[j] *= p[j];
             }
         }
+        // Renormalise.  Any positive scaling is equivalent for everything downstream (gamma and xi are ratios), so
+        // the fast path scales by an exact power of two and the log-likelihood is kept as
+        //   sum_t log c_t = log sigma_end - log sigma_start + ln2 * sum shift_t (+ slow-path terms),
+        // sigma = sum_j alpha_j at the frame before the chain and at its last frame (telescoping product).
+        const bool inchain = (PATH == PATH_CHAIN) || (PATH == PATH_GENERAL && t >= t0);
+        int shift = 0;
+        if (scale_pow2<N>(v, shift)) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) al[j] = v[j];
+            if (inchain) esum += shift;
+        } else {
+            const double csum = tree_sum<N>(v);
+            const double rc = (csum != 0.0) ? 1.0 / csum : 1.0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) al[j] = v[j] * rc;
+            if (inchain) slow += log(csum);
+        }
+        if (inchain) {
+            if (ROWMAJOR) {
+                double* dst = a.alpha_rm + (trow + t) * N;
+#pragma unroll
+                for (int j = 0; j < N; ++j) dst[j] = al[j];
+            } else {
+                double2* dst = il + ((long long)(t - t0) * NP2 << 5);
+#pragma unroll
+                for (int jp = 0; jp < NP2; ++jp)
+                    __stcs(dst + (jp << 5), make_double2(al[2 * jp], (2 * jp + 1 < N) ? al[2 * jp + 1] : 0.0));
+            }
+        }
+        if (PATH == PATH_GENERAL) {
+            if (t == tend - 1 || t == t0 - 1) {          // hand-over frames: the sum-normalised vector is recorded
+                const double sig = tree_sum<N>(al);
+                const double rs = (sig != 0.0) ? 1.0 / sig : 1.0;
+                double* dst = (t == tend - 1) ? a.hand_end : a.hand_used;
+                if (t == tend - 1) log_end = log(sig);
+                else log_start = (sig != 0.0) ? log(sig) : 0.0;    // an all-zero start keeps the chain's -inf
+#pragma unroll
+                for (int j = 0; j < N; ++j) dst[(long long)c * N + j] = al[j] * rs;
+            }
+        }
+    };
+
+    for (int s = 0; s < total; ++s) {
+        const double raw = ring[0];
+#pragma unroll
+        for (int k = 0; k + 1 < PF; ++k) ring[k] = ring[k + 1];
+        ring[PF - 1] = fetch(s + PF);
+        const int t = t0 - maxpre + s;
+        // lane class: 0 idle, 1 plain frame inside the chain, 2 plain warm-up frame, 3 first / hand-over frame
+        const bool on = have && t >= tstart && t < tend;
+        const int cls = !on ? 0 : ((t == tstart || t == tend - 1 || t == t0 - 1) ? 3 : (t >= t0 ? 1 : 2));
+        const unsigned m1 = __ballot_sync(FULL, cls == 1), m2 = __ballot_sync(FULL, cls == 2),
+                       m3 = __ballot_sync(FULL, cls == 3);
+        if (m3 || (m1 && m2)) step(BoolTag2<PATH_GENERAL>(), t, raw, on);
+        else if (m1) step(BoolTag2<PATH_CHAIN>(), t, raw, on);
+        else if (m2) step(BoolTag2<PATH_WARM>(), t, raw, on);
     }
-    if (have) a.chain_ll[c] = ll.value();
+    // a chain whose last frame was renormalised by the slow path ends with sigma = 1: log_end = 0 is then exact
+    if (have) a.chain_ll[c] = (log_end - log_start) + (double)esum * 0.693147180559945309417 + slow;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,13 +402,19 @@ __device__ __forceinline__ double pick_row(const double (&arr)[N], int qsel, int
 
 template <int N, int EM, int G>
 __global__ void __launch_bounds__(LANE_THREADS, LANE_MINB_B)
-k_backward_stats_lane(const __grid_constant__ LaneParams<N> P, const LaneArgs a)
+k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
 {
     constexpr int NP2 = (N + 1) / 2;
     constexpr int NH = (N + G - 1) / G;
     constexpr int PF = 4;
     constexpr int NSTAT = N * N + 4 * N;
     __shared__ double red[(LANE_THREADS / 32) * NSTAT];
+#if LANE_CONST_SMEM
+    __shared__ double cs[sizeof(LaneParams<N>) / sizeof(double)];
+    const ConstView<N> P = make_const_view<N>(Pk, cs);
+#else
+    const LaneParams<N>& P = Pk;
+#endif
 
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -346,11 +441,11 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> P, const LaneArgs a)
 #pragma unroll
     for (int ii = 0; ii < NH; ++ii) {
         sg[ii] = sgd[ii] = sgdd[ii] = 0.0;
-        muq[ii] = pick_row<N, G, NH>(P.mu, q, ii);
+        muq[ii] = P.mu[min(q * NH + ii, N - 1)];
 #pragma unroll
         for (int j = 0; j < N; ++j) Cq[ii][j] = 0.0;
     }
-    double bt[N];
+    double bt[N];                   // beta of frame f+1 (power-of-two scaled)
 #pragma unroll
     for (int j = 0; j < N; ++j) bt[j] = 0.0;
     const double2* il = reinterpret_cast<const double2*>(a.alpha_il) + il_base(c, a.Lmax, NP2);
@@ -370,181 +465,161 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> P, const LaneArgs a)
         if (EM == EM_GAUSS) emission_gauss<N>(P, rawv, a.ignore_outliers, pv);
         else emission_disc<N>(a, (int)__double_as_longlong(rawv), pv);
     };
-    double pn[N];                   // emission of frame f+1, evaluated during the previous step
-#pragma unroll
-    for (int j = 0; j < N; ++j) pn[j] = 0.0;
-#if !LANE_PIPE_EMIS
     double raw_next = 0.0;          // emission input of frame f+1
-#endif
-#if LANE_ALPHA_MODE == 2
-    double2 aln[NP2];               // forward variables of the next frame to emit, loaded one step ahead
-    {
-        const double2* src0 = il + ((long long)max(len - 1, 0) * NP2 << 5);
-#pragma unroll
-        for (int jp = 0; jp < NP2; ++jp) aln[jp] = have ? __ldcs(src0 + (jp << 5)) : make_double2(0.0, 0.0);
-    }
-#endif
 
-    for (int s = 0; s < total; ++s) {
-        {
-            {
-                const double raw = ring[0];                 // emission input of frame f
+    // statistics of one frame: lane q owns rows q*NH .. q*NH+NH-1 for every chain of its lane group
+    auto accumulate = [&](const double (&w)[N], const double (&u)[N], const double (&gam)[N], double o_f) {
 #pragma unroll
-                for (int k = 0; k + 1 < PF; ++k) ring[k] = ring[k + 1];
-                ring[PF - 1] = fetch(s + PF);
-                const int f = frame_of(s);
-                double p[N];
-#if LANE_PIPE_EMIS
+        for (int d = 0; d < G; ++d) {
+            double ur[NH], gr[NH];
+            double od;
+            if (d == 0) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) p[j] = pn[j];
-                emission(raw, pn);                          // p_f, consumed by the next step (frame f-1)
-#else
-                emission(raw_next, p);
-#endif
-#if LANE_ALPHA_MODE == 2
-                double2 alc[NP2];
-#pragma unroll
-                for (int jp = 0; jp < NP2; ++jp) alc[jp] = aln[jp];
-                if (have && f - 1 >= t0 && f - 1 < e) {
-                    const double2* nxt = il + ((long long)(f - 1 - t0) * NP2 << 5);
-#pragma unroll
-                    for (int jp = 0; jp < NP2; ++jp) aln[jp] = __ldcs(nxt + (jp << 5));
+                for (int ii = 0; ii < NH; ++ii) {
+                    ur[ii] = pick_row<N, G, NH>(u, q, ii);
+                    gr[ii] = pick_row<N, G, NH>(gam, q, ii);
                 }
-#endif
-                const bool on = have && f <= fs && f >= t0;
-                const bool init = on && f == fs;
-                const bool emit = on && f < e;
-                double w[N], u[N], gam[N];
+                od = o_f;
+            } else {
+                // the partner lane^d owns rows (q^d)*NH..: send it those rows of my u and gamma, receive mine
 #pragma unroll
-                for (int j = 0; j < N; ++j) { w[j] = 0.0; u[j] = 0.0; gam[j] = 0.0; }
-                double o_f = 0.0;
-#if LANE_ALPHA_MODE != 2
-                if (have && f - 1 >= t0 && f - 1 < e) {
-                    const double2* nxt = il + ((long long)(f - 1 - t0) * NP2 << 5);
-#pragma unroll
-                    for (int jp = 0; jp < NP2; ++jp) prefetch_l1(nxt + (jp << 5));
+                for (int ii = 0; ii < NH; ++ii) {
+                    ur[ii] = __shfl_xor_sync(FULL, pick_row<N, G, NH>(u, q ^ d, ii), d);
+                    gr[ii] = __shfl_xor_sync(FULL, pick_row<N, G, NH>(gam, q ^ d, ii), d);
                 }
-#endif
-                if (on) {
-                    double b[N];
-                    if (init) {
-                        if (mode == 2) {
+                od = __shfl_xor_sync(FULL, o_f, d);
+            }
 #pragma unroll
-                            for (int j = 0; j < N; ++j) b[j] = a.hand_end[(long long)(c + 1) * N + j];
-                        } else {
+            for (int j = 0; j < N; ++j) {
+                const double wj = (d == 0) ? w[j] : __shfl_xor_sync(FULL, w[j], d);
 #pragma unroll
-                            for (int j = 0; j < N; ++j) b[j] = 1.0;
-                        }
-                    } else {
+                for (int ii = 0; ii < NH; ++ii) Cq[ii][j] = fma(ur[ii], wj, Cq[ii][j]);
+            }
 #pragma unroll
-                        for (int j = 0; j < N; ++j) w[j] = p[j] * bt[j];
-#pragma unroll
-                        for (int i = 0; i < N; ++i) b[i] = P.A[i * N] * w[0];
-#pragma unroll
-                        for (int j = 1; j < N; ++j) {
-#pragma unroll
-                            for (int i = 0; i < N; ++i) b[i] = fma(P.A[i * N + j], w[j], b[i]);
-                        }
-                    }
-                    if (emit) {
-                        // gamma_f = alpha_f o b / S ; xi_f = (alpha_f / S) (x) w   with S = sum_i alpha_f,i b_i
-                        double al[N];
-#if LANE_ALPHA_MODE != 2
-                        const double2* src = il + ((long long)(f - t0) * NP2 << 5);
-#endif
-#pragma unroll
-                        for (int jp = 0; jp < NP2; ++jp) {
-#if LANE_ALPHA_MODE == 2
-                            const double2 v2 = alc[jp];
-#elif LANE_ALPHA_MODE == 1
-                            const double2 v2 = src[jp << 5];
-#else
-                            const double2 v2 = __ldcs(src + (jp << 5));
-#endif
-                            al[2 * jp] = v2.x;
-                            if (2 * jp + 1 < N) al[2 * jp + 1] = v2.y;
-                        }
-                        double gi[N];
-#pragma unroll
-                        for (int i = 0; i < N; ++i) gi[i] = al[i] * b[i];
-                        const double S = tree_sum<N>(gi);
-                        const double rS = 1.0 / S;
-#pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            u[i] = al[i] * rS;
-                            gam[i] = u[i] * b[i];
-                        }
-                        if (EM == EM_GAUSS) o_f = raw;
-                        if (f == 0) {
-#pragma unroll
-                            for (int i = 0; i < N; ++i) a.g0buf[(long long)c * N + i] = gam[i];
-                        }
-                        if (a.gamma) {
-                            double* dst = a.gamma + (trow + f) * N;
-#pragma unroll
-                            for (int i = 0; i < N; ++i) dst[i] = gam[i];
-                        }
-                        if (EM == EM_DISC && a.Bnum) {
-                            const int sy = (int)__double_as_longlong(raw);
-#pragma unroll
-                            for (int i = 0; i < N; ++i) atomicAdd(a.Bnum + (long long)i * a.M + sy, gam[i]);
-                        }
-                    }
-                    const double sb = tree_sum<N>(b);
-                    const double rsb = (sb != 0.0) ? 1.0 / sb : 1.0;
-#pragma unroll
-                    for (int i = 0; i < N; ++i) bt[i] = b[i] * rsb;
-                    if (f == e) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) a.hand_used[(long long)c * N + i] = bt[i];
-                    }
-                    if (f == t0 && t0 > 0) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) a.hand_end[(long long)c * N + i] = bt[i];
-                    }
-#if !LANE_PIPE_EMIS
-                    raw_next = raw;
-#endif
-                }
-                // ---- statistics: lane q owns rows q*NH .. q*NH+NH-1 for every chain of its lane group
-#pragma unroll
-                for (int d = 0; d < G; ++d) {
-                    double ur[NH], gr[NH];
-                    double od;
-                    if (d == 0) {
-#pragma unroll
-                        for (int ii = 0; ii < NH; ++ii) {
-                            ur[ii] = pick_row<N, G, NH>(u, q, ii);
-                            gr[ii] = pick_row<N, G, NH>(gam, q, ii);
-                        }
-                        od = o_f;
-                    } else {
-                        // the partner lane^d owns rows (q^d)*NH..: send it those rows of my u and gamma, receive mine
-#pragma unroll
-                        for (int ii = 0; ii < NH; ++ii) {
-                            ur[ii] = __shfl_xor_sync(FULL, pick_row<N, G, NH>(u, q ^ d, ii), d);
-                            gr[ii] = __shfl_xor_sync(FULL, pick_row<N, G, NH>(gam, q ^ d, ii), d);
-                        }
-                        od = __shfl_xor_sync(FULL, o_f, d);
-                    }
-#pragma unroll
-                    for (int j = 0; j < N; ++j) {
-                        const double wj = (d == 0) ? w[j] : __shfl_xor_sync(FULL, w[j], d);
-#pragma unroll
-                        for (int ii = 0; ii < NH; ++ii) Cq[ii][j] = fma(ur[ii], wj, Cq[ii][j]);
-                    }
-#pragma unroll
-                    for (int ii = 0; ii < NH; ++ii) {
-                        sg[ii] += gr[ii];
-                        if (EM == EM_GAUSS) {
-                            const double dd = od - muq[ii];
-                            sgd[ii] = fma(gr[ii], dd, sgd[ii]);
-                            sgdd[ii] = fma(gr[ii], dd * dd, sgdd[ii]);
-                        }
-                    }
+            for (int ii = 0; ii < NH; ++ii) {
+                sg[ii] += gr[ii];
+                if (EM == EM_GAUSS) {
+                    const double dd = od - muq[ii];
+                    sgd[ii] = fma(gr[ii], dd, sgd[ii]);
+                    sgdd[ii] = fma(gr[ii], dd * dd, sgdd[ii]);
                 }
             }
         }
+    };
+
+    // one frame f: given beta_{f+1} (bt) and the emission input of f+1, form b = A (p_{f+1} o beta_{f+1}), emit the
+    // statistics of frame f when it belongs to the chain, leave beta_f in bt
+    auto step = [&](auto path_tag, int f, double raw, bool on) {
+        constexpr int PATH = decltype(path_tag)::value;
+        const bool init = (PATH == PATH_GENERAL) && on && f == fs;
+        const bool emit = (PATH == PATH_CHAIN && on) || (PATH == PATH_GENERAL && on && f < e);
+        double w[N], u[N], gam[N];
+        double o_f = 0.0;
+        if (PATH == PATH_GENERAL || !on) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) { w[j] = 0.0; u[j] = 0.0; gam[j] = 0.0; }
+        }
+        if (on) {
+            // forward variables of frame f: issued first, consumed after the matvec
+            double2 a2[NP2];
+            if (emit) {
+                const double2* src = il + ((long long)(f - t0) * NP2 << 5);
+#pragma unroll
+                for (int jp = 0; jp < NP2; ++jp) a2[jp] = __ldcs(src + (jp << 5));
+            }
+            double b[N];
+            if (init) {
+                if (mode == 2) {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) b[j] = a.hand_end[(long long)(c + 1) * N + j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) b[j] = 1.0;
+                }
+            } else {
+                double p[N];
+                emission(raw_next, p);
+#pragma unroll
+                for (int j = 0; j < N; ++j) w[j] = p[j] * bt[j];
+#pragma unroll
+                for (int i = 0; i < N; ++i) b[i] = P.A[i * N] * w[0];
+#pragma unroll
+                for (int j = 1; j < N; ++j) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) b[i] = fma(P.A[i * N + j], w[j], b[i]);
+                }
+            }
+            if (emit) {
+                // gamma_f = alpha_f o b / S ; xi_f = (alpha_f / S) (x) w   with S = sum_i alpha_f,i b_i
+                double al[N], gi[N];
+#pragma unroll
+                for (int jp = 0; jp < NP2; ++jp) {
+                    al[2 * jp] = a2[jp].x;
+                    if (2 * jp + 1 < N) al[2 * jp + 1] = a2[jp].y;
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) gi[i] = al[i] * b[i];
+                const double S = tree_sum<N>(gi);
+                const double rS = 1.0 / S;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    u[i] = al[i] * rS;
+                    gam[i] = gi[i] * rS;
+                }
+                if (EM == EM_GAUSS) o_f = raw;
+                if (PATH == PATH_GENERAL && f == 0) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) a.g0buf[(long long)c * N + i] = gam[i];
+                }
+                if (a.gamma) {
+                    double* dst = a.gamma + (trow + f) * N;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) dst[i] = gam[i];
+                }
+                if (EM == EM_DISC && a.Bnum) {
+                    const int sy = (int)__double_as_longlong(raw);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) atomicAdd(a.Bnum + (long long)i * a.M + sy, gam[i]);
+                }
+            }
+            // beta only needs to stay in range: exact power-of-two scaling; the sum-normalised vector of the
+            // reference (_hidden.c:104-107) is formed only where it is handed over
+            int shift = 0;
+            if (scale_pow2<N>(b, shift)) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) bt[i] = b[i];
+            } else {
+                const double sb = tree_sum<N>(b);
+                const double rsb = (sb != 0.0) ? 1.0 / sb : 1.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) bt[i] = b[i] * rsb;
+            }
+            if (PATH == PATH_GENERAL && (f == e || (f == t0 && t0 > 0))) {
+                const double sb = tree_sum<N>(bt);
+                const double rsb = (sb != 0.0) ? 1.0 / sb : 1.0;
+                double* dst = (f == e) ? a.hand_used : a.hand_end;
+#pragma unroll
+                for (int i = 0; i < N; ++i) dst[(long long)c * N + i] = bt[i] * rsb;
+            }
+            raw_next = raw;
+        }
+        if (PATH != PATH_WARM) accumulate(w, u, gam, o_f);
+    };
+
+    for (int s = 0; s < total; ++s) {
+        const double raw = ring[0];                 // emission input of frame f
+#pragma unroll
+        for (int k = 0; k + 1 < PF; ++k) ring[k] = ring[k + 1];
+        ring[PF - 1] = fetch(s + PF);
+        const int f = frame_of(s);
+        // lane class: 0 idle, 1 plain frame inside the chain, 2 plain warm-up frame, 3 first / hand-over / frame 0
+        const bool on = have && f <= fs && f >= t0;
+        const int cls = !on ? 0 : ((f == fs || f == e || f == t0 || f == 0) ? 3 : (f < e ? 1 : 2));
+        const unsigned m1 = __ballot_sync(FULL, cls == 1), m2 = __ballot_sync(FULL, cls == 2),
+                       m3 = __ballot_sync(FULL, cls == 3);
+        if (m3 || (m1 && m2)) step(BoolTag2<PATH_GENERAL>(), f, raw, on);
+        else if (m1) step(BoolTag2<PATH_CHAIN>(), f, raw, on);
+        else if (m2) step(BoolTag2<PATH_WARM>(), f, raw, on);
     }
 
     // ---- reduce over the lanes that own the same rows (lane bits >= log2 G), then over the block's warps
@@ -592,8 +667,9 @@ void fill_params(LaneParams<N>& P, const double* A, const double* pi, const doub
         P.pi[j] = pi ? pi[j] : 0.0;
         P.mu[j] = mu ? mu[j] : 0.0;
         const double s = sigma ? sigma[j] : 1.0;
-        P.isg[j] = 1.0 / s;
-        P.nrm[j] = 1.0 / (sqrt(2.0 * 3.14159265358979323846) * s);   // C of _gaussian.c:18
+        P.isg[j] = 1.0 / (s * sqrt(2.0));                                  // d = (o - mu) * isg, x = -d*d
+        P.nrm[j] = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * s));    // log of C of _gaussian.c:18
+        P.nrml[j] = 1.0 / (sqrt(2.0 * 3.14159265358979323846) * s);
     }
 }
 
