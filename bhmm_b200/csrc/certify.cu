@@ -50,19 +50,27 @@ __global__ void k_certify(Chains ch, int n_total, int N, int dir, const double* 
 
 // stats = [loglik | gamma0 (N) | C (N*N) | sum gamma (N) | sum gamma d (N) | sum gamma d^2 (N)]
 // partial rows are [C' (N*N) | gamma0 | sum gamma | sum gamma d | sum gamma d^2]; C = A o C'.
+// One warp per statistic: lanes stride over the partial rows, fixed shuffle tree => deterministic.  The last block
+// reduces the per-chain log-likelihoods (fixed partition + fixed tree).
 __global__ void k_finalize_stats(const double* __restrict__ partials, int grid, const double* __restrict__ chain_ll,
                                  int n_chains, const double* __restrict__ A, int N, double* __restrict__ stats)
 {
     __shared__ double red[256];
     const int nstat = N * N + 4 * N;
-    for (int k = threadIdx.x; k < nstat; k += blockDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x < gridDim.x - 1) {
+        const int k = blockIdx.x * 8 + warp;
+        if (k >= nstat) return;
         double s = 0.0;
-        for (int b = 0; b < grid; ++b) s += partials[(long long)b * nstat + k];
-        if (k < N * N) stats[1 + N + k] = A[k] * s;
-        else if (k < N * N + N) stats[1 + (k - N * N)] = s;
-        else stats[1 + k] = s;
+        for (int b = lane; b < grid; b += 32) s += partials[(long long)b * nstat + k];
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) {
+            if (k < N * N) stats[1 + N + k] = A[k] * s;
+            else if (k < N * N + N) stats[1 + (k - N * N)] = s;
+            else stats[1 + k] = s;
+        }
+        return;
     }
-    // log-likelihood: fixed partition + fixed tree => deterministic
     const int per = (n_chains + blockDim.x - 1) / blockDim.x;
     double s = 0.0;
     const int lo = threadIdx.x * per, hi = min(n_chains, lo + per);
@@ -90,6 +98,7 @@ int launch_certify(const Chains& ch, int n_total, int N, int dir, const double* 
 int launch_finalize_stats(const double* partials, int grid, const double* chain_ll, int n_chains, const double* A,
                           int N, double* stats, cudaStream_t st)
 {
-    k_finalize_stats<<<1, 256, 0, st>>>(partials, grid, chain_ll, n_chains, A, N, stats);
+    const int nstat = N * N + 4 * N;
+    k_finalize_stats<<<(nstat + 7) / 8 + 1, 256, 0, st>>>(partials, grid, chain_ll, n_chains, A, N, stats);
     return BHMM_OK;
 }

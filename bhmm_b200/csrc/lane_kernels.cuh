@@ -48,8 +48,12 @@ constexpr unsigned FULL = 0xffffffffu;
 #define LANE_FOLD_NRM 1      // Gaussian normalisation constant folded into the exponent's argument (one FMA less per state)
 #endif
 #ifndef LANE_CONST_SMEM
-#define LANE_CONST_SMEM 1    // model constants (A, mu, isg, nrm) are read from shared memory into vector registers (LDS
-#endif                       // broadcast) instead of the uniform datapath (LDCU / R2UR), whose 63 registers thrash at N=10
+#define LANE_CONST_SMEM 1    // 1: all model constants (A, mu, isg, nrm) are read from shared memory into vector registers
+#endif                       //    (LDS broadcast) instead of the uniform datapath (LDCU / R2UR), whose 63 registers thrash
+                             // 2: emission constants from shared memory, transition matrix through the uniform datapath
+#ifndef LANE_KEEP_F
+#define LANE_KEEP_F 40       // forward kernel: this many entries of A stay in registers for the whole kernel (shared-
+#endif                       // memory -> register bandwidth, 8 B per lane and operand, is what bounds the lane kernels)
 #ifndef LANE_G_MID
 #define LANE_G_MID 4         // lanes sharing the xi accumulator rows for 9 <= N <= 12
 #endif
@@ -123,7 +127,9 @@ __device__ __forceinline__ void emission_gauss(const CV& P, double o, int ignore
     for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 1.0);
 #pragma unroll
     for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 1.0);
-    bool tail = false;
+    // tail / outlier tests on the high words with integer instructions (the FP64 pipe is the bottleneck):
+    // x < -708 or NaN  <=>  (hi(x) as unsigned) > hi(-708.0) = 0xC0862000, or exponent field all ones
+    unsigned tailbits = 0u;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const int ni = __double2loint(t[j]);
@@ -131,16 +137,18 @@ __device__ __forceinline__ void emission_gauss(const CV& P, double o, int ignore
 #if !LANE_FOLD_NRM
         p[j] *= P.nrml[j];          // (comparison build only)
 #endif
-        tail |= !(x[j] >= -708.0);
+        const unsigned hx = (unsigned)__double2hiint(x[j]);
+        tailbits |= (hx > 0xC0862000u || (hx & 0x7ff00000u) == 0x7ff00000u) ? (1u << j) : 0u;
     }
-    if (tail) {
+    if (tailbits) {
 #pragma unroll
         for (int j = 0; j < N; ++j)
-            if (!(x[j] >= -708.0)) p[j] = exp(x[j]);
+            if (tailbits & (1u << j)) p[j] = exp(x[j]);
     }
-    bool anynz = false;
+    int nzbits = 0;
 #pragma unroll
-    for (int j = 0; j < N; ++j) anynz |= (p[j] != 0.0);
+    for (int j = 0; j < N; ++j) nzbits |= __double2hiint(p[j]) | __double2loint(p[j]);
+    const bool anynz = (nzbits & 0x7fffffff) != 0 || nzbits != 0;
     if (ignore_outliers && !anynz) {
 #pragma unroll
         for (int j = 0; j < N; ++j) p[j] = 1.0;            // outputmodel.py:126-130
@@ -237,7 +245,12 @@ __device__ __forceinline__ ConstView<N> make_const_view(const LaneParams<N>& P, 
     for (int k = threadIdx.x; k < TOT; k += blockDim.x) smem[k] = src[k];
     __syncthreads();
     ConstView<N> v;
-    v.A = smem; v.pi = smem + N * N; v.mu = v.pi + N; v.isg = v.mu + N; v.nrm = v.isg + N; v.nrml = v.nrm + N;
+#if LANE_CONST_SMEM == 2
+    v.A = P.A;
+#else
+    v.A = smem;
+#endif
+    v.pi = smem + N * N; v.mu = v.pi + N; v.isg = v.mu + N; v.nrm = v.isg + N; v.nrml = v.nrm + N;
     return v;
 }
 enum { PATH_GENERAL = 0, PATH_CHAIN = 1, PATH_WARM = 2 };
@@ -298,6 +311,13 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
         else emission_disc<N>(a, (int)__double_as_longlong(rawv), pv);
     };
 
+    // part of the transition matrix is register resident (the forward kernel has the head-room)
+    constexpr int KEEP = (LANE_KEEP_F < N * N) ? LANE_KEEP_F : N * N;
+    double Areg[KEEP > 0 ? KEEP : 1];
+#pragma unroll
+    for (int k = 0; k < KEEP; ++k) Areg[k] = P.A[k];
+    auto Aat = [&](int k) -> double { return (k < KEEP) ? Areg[k] : P.A[k]; };
+
     // one frame of the recursion; PATH is a compile-time constant so that the fast paths carry no predicates
     auto step = [&](auto path_tag, int t, double raw, bool on) {
         constexpr int PATH = decltype(path_tag)::value;
@@ -315,11 +335,11 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
                 for (int j = 0; j < N; ++j) v[j] = (mode == 0) ? P.pi[j] * p[j] : p[j];
             } else {
 #pragma unroll
-                for (int j = 0; j < N; ++j) v[j] = al[0] * P.A[j];
+                for (int j = 0; j < N; ++j) v[j] = al[0] * Aat(j);
 #pragma unroll
                 for (int i = 1; i < N; ++i) {
 #pragma unroll
-                    for (int j = 0; j < N; ++j) v[j] = fma(al[i], P.A[i * N + j], v[j]);
+                    for (int j = 0; j < N; ++j) v[j] = fma(al[i], Aat(i * N + j), v[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < N; ++j) v[j] *= p[j];

@@ -97,6 +97,8 @@ def estimate_P(C, reversible=True, fixed_statdist=None, maxiter=1000000, maxerr=
     """Full transition matrix for general connectivity (_tmatrix_disconnected.py:68-123)."""
     C = np.array(C, dtype=float)
     n = C.shape[0]
+    if not reversible and fixed_statdist is None and np.all(C > mincount_connectivity):
+        return C / C.sum(axis=1)[:, None]      # one connected set, no empty row: the general code below reduces to this
     P = np.eye(n, dtype=np.float64)
     if fixed_statdist is not None:
         raise NotImplementedError('estimation with a fixed stationary distribution is not part of the hot path')
