@@ -58,8 +58,8 @@ size_t batch_layout(bhmm_b200_batch* b, char* base)
     const size_t o_offs = cv.add<long long>(b->K + 1);
     const size_t o_cw = cv.add<char>(chainwork_bytes(n, N));
     const size_t o_srow = cv.add<long long>(ns), o_slen = cv.add<int>(ns), o_st0 = cv.add<int>(ns), o_sT = cv.add<int>(ns);
-    const size_t o_smap = cv.add<unsigned char>((size_t)ns * N);
-    const size_t o_sent = cv.add<int>(ns);
+    const size_t o_smap = cv.add<unsigned char>((size_t)std::max(ns, n) * N);   // also per-chain maps (lane sampler)
+    const size_t o_sent = cv.add<int>(std::max(ns, n));
     const size_t o_A = cv.add<double>((size_t)N * N), o_pi = cv.add<double>(N), o_mu = cv.add<double>(N),
                  o_sg = cv.add<double>(N);
     b->stats_grid = backward_stats_grid(N, n);
@@ -255,31 +255,49 @@ int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     b->w.ch.warm = b->warm_f;
     if (b->lane) {
+        // lane family: forward on the interleaved layout, then the two-pass hypothesis sampler (lane_kernels.cuh)
         LaneArgs la{};
         LaneHostParams hp{A, pi, mu, sigma};
         la.obs = em.obs; la.sym = em.sym; la.Bt = em.Bt; la.M = em.M; la.ignore_outliers = em.ignore_outliers;
-        la.alpha_rm = b->d_alpha; la.Lmax = b->chunk; la.chain_ll = b->w.chain_ll;
+        la.alpha_il = b->d_alpha; la.Lmax = b->chunk; la.chain_ll = b->w.chain_ll;
         la.hand_used = b->w.hu_f; la.hand_end = b->w.he_f;
         RC_TRY(run_chains_certified(b->w, N, +1, [&](const Chains& ch, cudaStream_t s2) {
             LaneArgs x = la;
             x.ch = ch;
-            return launch_lane(x, hp, N, emkind, LANE_FORWARD_ROWMAJOR, s2);
+            return launch_lane(x, hp, N, emkind, LANE_FORWARD, s2);
         }, b->info, st));
+        if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT);
+        CUDA_TRY(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(long long) * ((size_t)N * N + 2 * N), st));
+        Chains all = b->w.ch;
+        all.list = nullptr; all.n = b->w.n_total; all.exact = 0;
+        la.ch = all;
+        la.u_row = d_u; la.seed = seed; la.sweep = sweep; la.path = d_path;
+        la.smap = b->seg_map; la.enter = b->seg_enter; la.coal = b->w.fail_list;
+        la.counts = d_counts; la.err = b->d_err; la.partials = d_sums ? b->d_partials : nullptr;
+        RC_TRY(launch_lane(la, hp, N, emkind, LANE_SAMPLE_MAP, st));
+        RC_TRY(launch_chase_link(all, N, b->seg_map, b->seg_enter, st));
+        RC_TRY(launch_lane(la, hp, N, emkind, LANE_SAMPLE_FIX, st));
+        LAUNCHED(3);
+        if (d_sums) {
+            RC_TRY(launch_lane_sum_moments(b->d_partials, 2 * lane_blocks(b->w.n_total), N, d_sums, st));
+            LAUNCHED(1);
+        }
     } else {
         RC_TRY(run_forward(b->w, em, emkind, N, b->d_A, b->d_pi, b->d_alpha, b->info, st));
+        if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT);
+        CUDA_TRY(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
+        if (d_u) RC_TRY(launch_sample_table(b->d_alpha, b->d_A, d_u, b->d_offsets, b->K, N, b->rows, b->d_F, b->d_err, st));
+        else RC_TRY(launch_sample_table_philox(b->d_alpha, b->d_A, seed, sweep, b->d_offsets, b->K, N, b->rows, b->d_F, b->d_err, st));
+        RC_TRY(launch_chase(b->d_F, b->seg, N, b->seg_map, b->seg_enter, d_path, st));
+        LAUNCHED(4);
+        CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(long long) * ((size_t)N * N + 2 * N), st));
+        if (d_sums) CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * N, st));
+        RC_TRY(launch_path_stats(d_path, d_sums ? em.obs : nullptr, b->d_offsets, b->K, N, b->rows, d_counts,
+                                 d_counts + (size_t)N * N, d_counts + (size_t)N * N + N, d_sums, d_sums ? d_sums + N : nullptr,
+                                 st));
+        LAUNCHED(1);
     }
-    if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT);
-    CUDA_TRY(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
-    if (d_u) RC_TRY(launch_sample_table(b->d_alpha, b->d_A, d_u, b->d_offsets, b->K, N, b->rows, b->d_F, b->d_err, st));
-    else RC_TRY(launch_sample_table_philox(b->d_alpha, b->d_A, seed, sweep, b->d_offsets, b->K, N, b->rows, b->d_F, b->d_err, st));
-    RC_TRY(launch_chase(b->d_F, b->seg, N, b->seg_map, b->seg_enter, d_path, st));
-    LAUNCHED(4);
-    CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(long long) * ((size_t)N * N + 2 * N), st));
-    if (d_sums) CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * N, st));
-    RC_TRY(launch_path_stats(d_path, d_sums ? em.obs : nullptr, b->d_offsets, b->K, N, b->rows, d_counts,
-                             d_counts + (size_t)N * N, d_counts + (size_t)N * N + N, d_sums, d_sums ? d_sums + N : nullptr,
-                             st));
-    LAUNCHED(1);
     std::vector<double> ll(b->w.n_total);
     int err = 0;
     CUDA_TRY(cudaMemcpyAsync(ll.data(), b->w.chain_ll, sizeof(double) * b->w.n_total, cudaMemcpyDeviceToHost, st));

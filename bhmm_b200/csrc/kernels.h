@@ -77,8 +77,18 @@ struct LaneArgs {
     double* partials;        // (blocks, N*N+4N)
     double* Bnum;
     double* gamma;           // optional (rows,N)
+    // ---- forward-filter / backward-sample (LANE_SAMPLE_MAP / LANE_SAMPLE_FIX)
+    const double* u_row;     // optional (rows) uniforms, one per frame; NULL: Philox4x32-10 keyed by (seed, sweep, row)
+    unsigned long long seed, sweep;
+    int* path;               // (rows) int32 sampled states
+    unsigned char* smap;     // (n_chains, N): state at the chain's first frame for every entering state
+    const int* enter;        // (n_chains): state at the frame after the chain (LANE_SAMPLE_FIX)
+    int* coal;               // (n_chains): frame at which the chain's hypothetical paths coalesced (t0-1: never)
+    long long* counts;       // device int64 [C (N*N) | n0 (N) | frames per state (N)], accumulated with atomics
+    int* err;
 };
-enum { LANE_FORWARD = 0, LANE_FORWARD_ROWMAJOR = 1, LANE_BACKWARD_STATS = 2 };
+enum { LANE_FORWARD = 0, LANE_FORWARD_ROWMAJOR = 1, LANE_BACKWARD_STATS = 2, LANE_SAMPLE_MAP = 3, LANE_SAMPLE_FIX = 4 };
+int launch_lane_sum_moments(const double* partials, int rows, int N, double* sums, cudaStream_t st);
 bool lane_supported(int N, int em);
 int lane_blocks(int n_chains);
 int launch_lane(const LaneArgs& a, const LaneHostParams& hp, int N, int em, int what, cudaStream_t st);
@@ -129,6 +139,8 @@ int launch_sample_table_philox(const double* alpha, const double* A, unsigned lo
 // segment table `seg` has the chain-table layout (row0, len, t0, T), ordered by (trajectory, t0)
 int launch_chase(const unsigned char* F, const Chains& seg, int N, unsigned char* seg_map, int* seg_enter, int* path,
                  cudaStream_t st);
+// link step alone (lane-family sampler): enter[c] = state at the frame after chain c
+int launch_chase_link(const Chains& seg, int N, const unsigned char* seg_map, int* seg_enter, cudaStream_t st);
 int launch_path_stats(const int* path, const double* obs, const long long* offsets, int K, int N, long long rows,
                       long long* Cint, long long* n0, long long* cnt, double* so, double* soo, cudaStream_t st);
 int launch_symbol_histogram(const int* path, const int* sym, long long rows, int N, int M, long long* hist,

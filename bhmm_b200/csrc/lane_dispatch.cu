@@ -30,6 +30,16 @@ __global__ void k_add_gamma0(Chains ch, int n_total, int N, const double* __rest
         __syncthreads();
     }
 }
+
+// sums[k] = sum over the partial rows of column k (fixed order): per-state sum o and sum o^2 of the sampled paths
+__global__ void k_sum_moments(const double* __restrict__ partials, int rows, int n, double* __restrict__ sums)
+{
+    const int k = threadIdx.x;
+    if (k >= n) return;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += partials[(long long)r * n + k];
+    sums[k] = s;
+}
 }  // namespace
 
 int lane_blocks(int n_chains) { return (n_chains + LANE_THREADS - 1) / LANE_THREADS; }
@@ -50,5 +60,11 @@ int launch_lane(const LaneArgs& a, const LaneHostParams& hp, int N, int em, int 
 int launch_add_gamma0(const Chains& ch, int n_total, int N, const double* g0buf, double* stats, cudaStream_t st)
 {
     k_add_gamma0<<<1, 256, 0, st>>>(ch, n_total, N, g0buf, stats);
+    return BHMM_OK;
+}
+
+int launch_lane_sum_moments(const double* partials, int rows, int N, double* sums, cudaStream_t st)
+{
+    k_sum_moments<<<1, 64, 0, st>>>(partials, rows, 2 * N, sums);
     return BHMM_OK;
 }

@@ -679,6 +679,217 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward-filter / backward-sample on the interleaved forward variables
+// ------------------------------------------------------------------------------------------------
+// Given its uniform, the draw at frame t is a function F_t(s_{t+1}) of the next state only (sample_kernels.cu).  A chain
+// does not know the state that enters it from the next chain, so pass 1 (SAMPLE_MAP) walks the chain backwards carrying
+// ALL N hypothetical entering states (4 bits each in one 64-bit word).  The hypotheses coalesce after a few frames
+// (F_t depends only weakly on the next state); from there on a single path is followed, written and counted.  The
+// chains of a trajectory are then linked (k_chase_link), and pass 2 (SAMPLE_FIX) re-walks only the few frames before
+// the coalescence with the now-known entering state.  Same draws as the serial reference for the same uniforms.
+__device__ __forceinline__ void lane_philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                                  uint32_t k1)
+{
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+// identical to philox_uniform() of sample_kernels.cu: uniform in [0,1) keyed by seed, counter (ctr, row)
+__device__ __forceinline__ double lane_philox_uniform(unsigned long long seed, unsigned long long ctr, long long row)
+{
+    uint32_t c0 = (uint32_t)row, c1 = (uint32_t)((unsigned long long)row >> 32);
+    uint32_t c2 = (uint32_t)ctr, c3 = (uint32_t)(ctr >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        lane_philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    const unsigned long long bits = ((unsigned long long)c0 << 32) | c1;
+    return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// state drawn at a frame with forward variables al, uniform r, given next state v (ignored at a trajectory's last frame)
+template <int N, bool EXACT>
+__device__ __forceinline__ int lane_draw(const double (&al)[N], const double* __restrict__ A_s, int v, double r,
+                                         bool last, bool& bad)
+{
+    double pv[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) pv[i] = last ? al[i] : __dmul_rn(al[i], A_s[i * N + v]);
+    if (EXACT) {
+        // the reference's arithmetic: sequential sum, division of every term, running sum (_hidden.c:283-319)
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s = __dadd_rn(s, pv[i]);
+        double acc = 0.0;
+        int pick = -1;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            acc = __dadd_rn(acc, __ddiv_rn(pv[i], s));
+            if (pick < 0 && acc >= r) pick = i;
+        }
+        if (pick < 0) { pick = N - 1; bad = true; }
+        return pick;
+    }
+    // production: first i with sum_{k<=i} pv_k >= r * sum_k pv_k (no divisions)
+    double s = pv[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) s += pv[i];
+    const double thr = r * s;
+    double acc = 0.0;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        acc += pv[i];
+        cnt += (acc < thr) ? 1 : 0;
+    }
+    if (!(s > 0.0)) bad = true;
+    return min(cnt, N - 1);
+}
+
+template <int N, int EM, bool EXACT, bool FIXPASS>
+__global__ void __launch_bounds__(LANE_THREADS)
+k_sample_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
+{
+    constexpr int NP2 = (N + 1) / 2;
+    constexpr int NI = N * N + 2 * N;                 // int counters per thread: C (N*N), n0 (N), frames per state (N)
+    extern __shared__ unsigned char smraw[];
+    double* A_s = reinterpret_cast<double*>(smraw);                       // N*N
+    double* mom = A_s + N * N;                                            // [2N][LANE_THREADS] sum o, sum o^2
+    int* cnts = reinterpret_cast<int*>(mom + 2 * N * LANE_THREADS);       // [NI][LANE_THREADS]
+    for (int k = threadIdx.x; k < N * N; k += blockDim.x) A_s[k] = Pk.A[k];
+    for (int k = threadIdx.x; k < 2 * N * LANE_THREADS; k += blockDim.x) mom[k] = 0.0;
+    for (int k = threadIdx.x; k < NI * LANE_THREADS; k += blockDim.x) cnts[k] = 0;
+    __syncthreads();
+
+    const int tid = threadIdx.x;
+    const int idx = blockIdx.x * blockDim.x + tid;
+    const bool have = idx < a.ch.n;
+    int c = 0, len = 0, t0 = 0, T = 0, e = 0;
+    long long trow = 0;
+    if (have) {
+        c = idx;
+        len = a.ch.len[c];
+        t0 = a.ch.t0[c];
+        T = a.ch.T[c];
+        trow = a.ch.row0[c] - t0;
+        e = t0 + len;
+    }
+    const double2* il = reinterpret_cast<const double2*>(a.alpha_il) + il_base(c, a.Lmax, NP2);
+    bool bad = false;
+
+    auto load_alpha = [&](int f, double (&al)[N]) {
+        const double2* src = il + ((long long)(f - t0) * NP2 << 5);
+#pragma unroll
+        for (int jp = 0; jp < NP2; ++jp) {
+            const double2 v2 = __ldcs(src + (jp << 5));
+            al[2 * jp] = v2.x;
+            if (2 * jp + 1 < N) al[2 * jp + 1] = v2.y;
+        }
+    };
+    auto uniform = [&](int f) -> double {
+        return a.u_row ? __ldg(a.u_row + trow + f) : lane_philox_uniform(a.seed, a.sweep, trow + f);
+    };
+    auto count_frame = [&](int f, int st) {           // per-state frame count and observation moments
+        cnts[(N * N + N + st) * LANE_THREADS + tid] += 1;
+        if (f == 0) cnts[(N * N + st) * LANE_THREADS + tid] += 1;
+        if (EM == EM_GAUSS) {
+            const double o = __ldg(a.obs + trow + f);
+            mom[st * LANE_THREADS + tid] += o;
+            mom[(N + st) * LANE_THREADS + tid] += o * o;
+        }
+        if (a.path) a.path[trow + f] = st;
+    };
+    auto count_transition = [&](int st, int nxt) { cnts[(st * N + nxt) * LANE_THREADS + tid] += 1; };
+
+    // uniform trip count per warp keeps the interleaved loads coalesced
+    const int maxlen = __reduce_max_sync(FULL, len);
+    if (!FIXPASS) {
+        unsigned long long hyp = 0ULL;                // nibble s' = current state given entering state s'
+#pragma unroll
+        for (int sp = 0; sp < N; ++sp) hyp |= (unsigned long long)sp << (4 * sp);
+        const unsigned long long ones = 0x1111111111111111ULL & ((N == 16) ? ~0ULL : ((1ULL << (4 * N)) - 1ULL));
+        bool coalesced = false;
+        int coal = t0 - 1, prev = 0;
+        for (int k = 0; k < maxlen; ++k) {
+            const int f = e - 1 - k;
+            if (!have || f < t0) continue;
+            double al[N];
+            load_alpha(f, al);
+            const double r = uniform(f);
+            const bool last = (f == T - 1);
+            if (!coalesced) {
+                unsigned long long nsp = 0ULL;        // nibble v = state drawn when the next state is v
+#pragma unroll
+                for (int v = 0; v < N; ++v) nsp |= (unsigned long long)lane_draw<N, EXACT>(al, A_s, v, r, last, bad) << (4 * v);
+                unsigned long long nh = 0ULL;
+#pragma unroll
+                for (int sp = 0; sp < N; ++sp) {
+                    const int cur = (int)((hyp >> (4 * sp)) & 15ULL);
+                    nh |= ((nsp >> (4 * cur)) & 15ULL) << (4 * sp);
+                }
+                hyp = nh;
+                if (hyp == (hyp & 15ULL) * ones) {
+                    coalesced = true;
+                    coal = f;
+                    prev = (int)(hyp & 15ULL);
+                    count_frame(f, prev);
+                }
+            } else {
+                const int st = lane_draw<N, EXACT>(al, A_s, prev, r, last, bad);
+                count_frame(f, st);
+                count_transition(st, prev);
+                prev = st;
+            }
+        }
+        if (have) {
+#pragma unroll
+            for (int sp = 0; sp < N; ++sp)
+                a.smap[(long long)c * N + sp] = (unsigned char)(coalesced ? prev : (int)((hyp >> (4 * sp)) & 15ULL));
+            a.coal[c] = coal;
+        }
+    } else {
+        // frames after the coalescence point: re-walk with the known entering state
+        const int coal = have ? a.coal[c] : 0;
+        int prev = (have && e < T) ? a.enter[c] : 0;
+        for (int k = 0; k < maxlen; ++k) {
+            const int f = e - 1 - k;
+            if (!have || f < t0 || f < coal) continue;
+            double al[N];
+            load_alpha(f, al);
+            const double r = uniform(f);
+            const bool last = (f == T - 1);
+            const int st = lane_draw<N, EXACT>(al, A_s, prev, r, last, bad);
+            if (f > coal) count_frame(f, st);
+            if (!last) count_transition(st, prev);
+            prev = st;
+        }
+    }
+    if (bad) atomicExch(a.err, BHMM_ERR_SAMPLE);
+
+    // ---- block reduction of the private counters (fixed order), then one atomic per counter and block
+    __syncthreads();
+    unsigned long long* gcnt = reinterpret_cast<unsigned long long*>(a.counts);
+    for (int k = tid; k < NI; k += blockDim.x) {
+        long long s = 0;
+        for (int t = 0; t < LANE_THREADS; ++t) s += cnts[k * LANE_THREADS + t];
+        if (s) atomicAdd(gcnt + k, (unsigned long long)s);
+    }
+    if (EM == EM_GAUSS && a.partials) {
+        double* out = a.partials + ((long long)(FIXPASS ? gridDim.x : 0) + blockIdx.x) * 2 * N;
+        for (int k = tid; k < 2 * N; k += blockDim.x) {
+            double s = 0.0;
+            for (int t = 0; t < LANE_THREADS; ++t) s += mom[k * LANE_THREADS + t];
+            out[k] = s;
+        }
+    }
+}
+
 template <int N>
 void fill_params(LaneParams<N>& P, const double* A, const double* pi, const double* mu, const double* sigma)
 {
@@ -713,9 +924,29 @@ int launch_lane_n(const LaneArgs& a, const LaneHostParams& hp, int em, int what,
     } else if (what == LANE_FORWARD_ROWMAJOR) {
         if (em == EM_GAUSS) k_forward_lane<N, EM_GAUSS, true><<<blocks, LANE_THREADS, 0, st>>>(P, a);
         else k_forward_lane<N, EM_DISC, true><<<blocks, LANE_THREADS, 0, st>>>(P, a);
-    } else {
+    } else if (what == LANE_BACKWARD_STATS) {
         if (em == EM_GAUSS) k_backward_stats_lane<N, EM_GAUSS, G><<<blocks, LANE_THREADS, 0, st>>>(P, a);
         else k_backward_stats_lane<N, EM_DISC, G><<<blocks, LANE_THREADS, 0, st>>>(P, a);
+    } else {
+        const size_t smem = sizeof(double) * ((size_t)N * N + 2 * N * LANE_THREADS) + sizeof(int) * (size_t)(N * N + 2 * N) * LANE_THREADS;
+        const bool exact = a.u_row != nullptr;
+        const bool fix = (what == LANE_SAMPLE_FIX);
+#define LAUNCH_SAMPLE(EMK, EX, FX)                                                                              \
+    do {                                                                                                      \
+        if (smem > 48 * 1024 &&                                                                               \
+            cudaFuncSetAttribute(k_sample_lane<N, EMK, EX, FX>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                 (int)smem) != cudaSuccess)                                                   \
+            return BHMM_ERR_CUDA;                                                                             \
+        k_sample_lane<N, EMK, EX, FX><<<blocks, LANE_THREADS, smem, st>>>(P, a);                              \
+    } while (0)
+        if (em == EM_GAUSS) {
+            if (exact) { if (fix) LAUNCH_SAMPLE(EM_GAUSS, true, true); else LAUNCH_SAMPLE(EM_GAUSS, true, false); }
+            else { if (fix) LAUNCH_SAMPLE(EM_GAUSS, false, true); else LAUNCH_SAMPLE(EM_GAUSS, false, false); }
+        } else {
+            if (exact) { if (fix) LAUNCH_SAMPLE(EM_DISC, true, true); else LAUNCH_SAMPLE(EM_DISC, true, false); }
+            else { if (fix) LAUNCH_SAMPLE(EM_DISC, false, true); else LAUNCH_SAMPLE(EM_DISC, false, false); }
+        }
+#undef LAUNCH_SAMPLE
     }
     return BHMM_OK;
 }

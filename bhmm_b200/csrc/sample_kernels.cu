@@ -215,6 +215,13 @@ int launch_chase(const unsigned char* F, const Chains& seg, int N, unsigned char
     return BHMM_OK;
 }
 
+int launch_chase_link(const Chains& seg, int N, const unsigned char* seg_map, int* seg_enter, cudaStream_t st)
+{
+    if (seg.n <= 0) return BHMM_OK;
+    k_chase_link<<<nblk(seg.n, 128), 128, 0, st>>>(seg, N, seg_map, seg_enter);
+    return BHMM_OK;
+}
+
 int launch_path_stats(const int* path, const double* obs, const long long* offsets, int K, int N, long long rows,
                       long long* Cint, long long* n0, long long* cnt, double* so, double* soo, cudaStream_t st)
 {
