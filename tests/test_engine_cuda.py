@@ -229,3 +229,73 @@ def test_gibbs_philox_is_distributionally_correct(eng, oracle_port):
     p3, _, _, _ = batch.gibbs_gaussian(A, pi, means, sigmas, seed=1234, sweep=7)
     assert np.array_equal(p2, p3.cpu().numpy())    # same (seed, sweep) -> same paths
     batch.close()
+
+
+def test_edge_cases_short_ragged_outliers(eng, oracle_port):
+    """Trajectories of 1 and 2 frames next to long ones, an observation whose density underflows for every state
+    (outlier rule, outputmodel.py:119-131) and a NaN-free far tail (denormal densities): E-step statistics, Viterbi and
+    the Gibbs log-likelihood agree with the oracle."""
+    rng = np.random.default_rng(99)
+    N = 5
+    X = rng.random((N, N)) + 0.05
+    A = X / X.sum(axis=1)[:, None]
+    pi = rng.random(N) + 0.1
+    pi /= pi.sum()
+    means, sigmas = np.linspace(-4, 4, N), np.linspace(0.3, 1.2, N)
+    lengths = [1, 2, 700, 3, 1500, 64, 65]
+    obs = []
+    for T in lengths:
+        s = rng.integers(0, N, size=T)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    obs[2][100] = 400.0          # all densities underflow to 0 -> row of ones
+    obs[4][700] = -17.0          # far tail: densities of ~1e-300 and denormals
+    obs[4][701] = 15.5
+    batch = eng.TrajectoryBatch(obs, N, chunk=64, warm=16)
+    st = eng.unpack_stats(batch.estep_gaussian(A, pi, means, sigmas).cpu().numpy(), N)
+    ref, wd, wdd = oracle_stats_gaussian(oracle_port, obs, A, pi, means, sigmas)
+    assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])
+    np.testing.assert_allclose(st['gamma0'], ref['gamma0'], rtol=RTOL)
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(st['wsum'], ref['wsum'], rtol=RTOL)
+    np.testing.assert_allclose(st['wdd'], wdd, rtol=1e-9)
+    assert abs(st['C'].sum() - sum(T - 1 for T in lengths)) < 1e-8
+    paths = batch.split(batch.viterbi_gaussian(A, pi, means, sigmas).cpu().numpy())
+    for o, p in zip(obs, paths):
+        assert np.array_equal(p, oracle_port.viterbi(A, oracle_port.gaussian_p_obs(o, means, sigmas), pi))
+    path, counts, sums, ll = batch.gibbs_gaussian(A, pi, means, sigmas, seed=3, sweep=0)
+    assert abs(ll - ref['loglik']) <= RTOL * abs(ref['loglik'])
+    c = batch.unpack_counts(counts)
+    assert c['count'].sum() == sum(lengths) and c['n0'].sum() == len(lengths)
+    assert c['C'].sum() == sum(T - 1 for T in lengths)
+    # the counts are those of the returned paths
+    ref_stats = oracle_port.path_stats(batch.split(path.cpu().numpy()), obs, N)
+    assert np.array_equal(c['C'], ref_stats['C']) and np.array_equal(c['n0'], ref_stats['n0'])
+    assert np.array_equal(c['count'], ref_stats['count'])
+    np.testing.assert_allclose(sums.cpu().numpy()[:N], ref_stats['so'], rtol=1e-12)
+    np.testing.assert_allclose(sums.cpu().numpy()[N:], ref_stats['soo'], rtol=1e-12)
+    # ignore_outliers=False: the impossible frame makes the likelihood -inf in the reference too
+    st2 = eng.unpack_stats(batch.estep_gaussian(A, pi, means, sigmas, ignore_outliers=False).cpu().numpy(), N)
+    ref2 = oracle_port.estep_gaussian(obs, A, pi, means, sigmas, ignore_outliers=False)
+    assert st2['loglik'] == -np.inf and ref2['loglik'] == -np.inf
+    batch.close()
+
+
+@pytest.mark.parametrize('N', [1, 16])
+def test_lane_family_extremes(eng, oracle_port, N):
+    rng = np.random.default_rng(N)
+    X = rng.random((N, N)) + 0.02
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    means, sigmas = np.linspace(-3, 3, N) if N > 1 else np.zeros(1), np.linspace(0.5, 1.0, N)
+    obs = [rng.normal(size=T) * 2.0 for T in (900, 333)]
+    batch = eng.TrajectoryBatch(obs, N, chunk=200, warm=0)
+    st = eng.unpack_stats(batch.estep_gaussian(A, pi, means, sigmas).cpu().numpy(), N)
+    ref, wd, wdd = oracle_stats_gaussian(oracle_port, obs, A, pi, means, sigmas)
+    assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9, atol=1e-12 * ref['C'].max())
+    np.testing.assert_allclose(st['wsum'], ref['wsum'], rtol=RTOL)
+    np.testing.assert_allclose(st['wdd'], wdd, rtol=1e-9)
+    path, counts, sums, ll = batch.gibbs_gaussian(A, pi, means, sigmas, seed=5, sweep=1)
+    ref_stats = oracle_port.path_stats(batch.split(path.cpu().numpy()), obs, N)
+    assert np.array_equal(batch.unpack_counts(counts)['C'], ref_stats['C'])
+    batch.close()
