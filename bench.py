@@ -297,8 +297,36 @@ def run_ours(args):
     value = world * rows * args.steps / (ms * 1e-3)
     info = batch.info()
 
-    # ---- end-to-end: observations start in pinned host memory every step
+    # ---- end-to-end: observations start in pinned host memory every step.  Every step's inputs are copied host ->
+    # device inside the timed region and its statistics are read back; the copy of step k+1 runs on a second stream
+    # while step k computes (double-buffered device input), as a serving loop would do it.
     e2e_steps = max(1, min(args.steps, 5))
+    obs_a = batch.obs
+    obs_b = torch.empty_like(obs_a)
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    bufs = [obs_a, obs_b]
+    barrier()
+    e0.record()
+    with torch.cuda.stream(copy_stream):
+        bufs[0].copy_(host_obs, non_blocking=True)
+        ready[0].record(copy_stream)
+    for k in range(e2e_steps):
+        if k + 1 < e2e_steps:
+            with torch.cuda.stream(copy_stream):
+                bufs[(k + 1) & 1].copy_(host_obs, non_blocking=True)
+                ready[(k + 1) & 1].record(copy_stream)
+        torch.cuda.current_stream(dev).wait_event(ready[k & 1])
+        batch.obs = bufs[k & 1]
+        model, ll = em_step(batch, model, dist, N)
+    e1.record()
+    barrier()
+    batch.obs = obs_a
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    e2e_value = world * rows * e2e_steps / (float(t.item()) * 1e-3)
+    # the same without overlap (copy, then compute), for reference
     barrier()
     e0.record()
     for _ in range(e2e_steps):
@@ -309,7 +337,7 @@ def run_ours(args):
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
-    e2e_value = world * rows * e2e_steps / (float(t.item()) * 1e-3)
+    e2e_serial = world * rows * e2e_steps / (float(t.item()) * 1e-3)
     stats_bytes = 8 * (1 + N + N * N + 3 * N)
 
     # ---- Gibbs sweep (second half of the metric), device resident
@@ -378,7 +406,9 @@ def run_ours(args):
             'cpu_baseline': cpu_baseline,
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'frames*iters/s', 'h2d_bytes_per_step': rows * 8,
-                    'd2h_bytes_per_step': stats_bytes, 'steps': e2e_steps},
+                    'd2h_bytes_per_step': stats_bytes, 'steps': e2e_steps,
+                    'note': 'input copy of step k+1 overlaps the compute of step k (double-buffered device input)',
+                    'value_without_overlap': e2e_serial},
             'gpu_launches': int(launches),
             'gibbs': {'value': gibbs_value, 'unit': 'frames*sweeps/s', 'steps': gsteps,
                       'note': 'forward + time-parallel backward sampling + path statistics, Philox uniforms'},

@@ -62,6 +62,14 @@ __device__ __forceinline__ int block_max(int v)
     return v;   // multi-warp blocks carry a single team: the value is already uniform
 }
 
+// xor-butterfly sum over the 32 lanes: every lane ends with the bitwise identical total
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
 // Raw emission input of (row, state j): the table entry, the observation, or the symbol's B entry.
 template <int EM>
 __device__ __forceinline__ double em_load(const Emission& em, long long row, int j, int N)
@@ -81,7 +89,9 @@ __device__ __forceinline__ double em_value(double raw, double mu, double sigma)
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int EM>
+// WARP1: the block is one warp carrying one team (17 <= N <= 32): the thread's column of A lives in registers and the
+// row sums are warp shuffles, which halves the shared-memory traffic that bounds the general code.
+template <int EM, bool WARP1>
 __global__ void k_forward_team(const FwdArgs a)
 {
     extern __shared__ double sm[];
@@ -93,6 +103,11 @@ __global__ void k_forward_team(const FwdArgs a)
     const bool jv = g.owns && j < N;
 
     for (int k = threadIdx.x; k < N * N; k += blockDim.x) A_s[k] = a.A[k];
+    double Acol[WARP1 ? 32 : 1];
+    if (WARP1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) Acol[WARP1 ? i : 0] = (i < N && jv) ? a.A[i * N + j] : 0.0;
+    }
     const double pi_j = jv ? a.pi[j] : 0.0;
     double mu = 0.0, sigma = 1.0;
     if (EM == EM_GAUSS && jv) { mu = a.em.mu[j]; sigma = a.em.sigma[j]; }
@@ -150,7 +165,13 @@ __global__ void k_forward_team(const FwdArgs a)
                     av = (mode == 0) ? pi_j * p : ((mode == 1) ? p : vec_j);
                 } else {
                     double m = 0.0;
-                    for (int i = 0; i < N; ++i) m = fma(xprev[i], A_s[i * N + j], m);
+                    if (WARP1) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < N) m = fma(xprev[i], Acol[WARP1 ? i : 0], m);
+                    } else {
+                        for (int i = 0; i < N; ++i) m = fma(xprev[i], A_s[i * N + j], m);
+                    }
                     if (cprev != 0.0) m /= cprev;
                     av = m * p;
                 }
@@ -158,7 +179,8 @@ __global__ void k_forward_team(const FwdArgs a)
             if (g.owns && j < N) xcur[j] = av;
             __syncthreads();
             double csum = 0.0;
-            if (g.owns) for (int i = 0; i < N; ++i) csum += xcur[i];
+            if (WARP1) csum = warp_sum(av);
+            else if (g.owns) for (int i = 0; i < N; ++i) csum += xcur[i];
             if (on && jv) {
                 const double outv = (csum != 0.0) ? av / csum : av;
                 if (t >= t0) {
@@ -185,7 +207,7 @@ __global__ void k_forward_team(const FwdArgs a)
 // STATS: exchange 2 publishes (g_i, alpha_{f-1,i}, b(f-1)_i) with g_i = alpha_{f-1,i} b(f-1)_i, whose sum
 // S normalises both gamma_{f-1} = g/S and xi_{f-1} = alpha_{f-1,i} A_ij w_j / (sb S)  (_hidden.c:168-180),
 // so gamma and xi are reduced on chip and never written unless a.gamma is given.
-template <int EM, bool STATS>
+template <int EM, bool STATS, bool WARP1>
 __global__ void k_backward_team(const BwdArgs a)
 {
     extern __shared__ double sm[];
@@ -204,6 +226,15 @@ __global__ void k_backward_team(const BwdArgs a)
         At_s[jj * N + i] = a.A[k];
     }
     if (STATS) for (int k = threadIdx.x; k < cpb * N * N; k += blockDim.x) Cacc[k] = 0.0;
+    double Arow[WARP1 ? 32 : 1];             // WARP1: A[j][i'] and the thread's column of the xi accumulator in registers
+    double Ccol[(WARP1 && STATS) ? 32 : 1];
+    if (WARP1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            Arow[WARP1 ? i : 0] = (i < N && jv) ? a.A[j * N + i] : 0.0;
+            if (STATS) Ccol[(WARP1 && STATS) ? i : 0] = 0.0;
+        }
+    }
     double mu = 0.0, sigma = 1.0;
     if (EM == EM_GAUSS && jv) { mu = a.em.mu[j]; sigma = a.em.sigma[j]; }
     double st_g0 = 0.0, st_g = 0.0, st_gd = 0.0, st_gdd = 0.0;
@@ -265,12 +296,20 @@ __global__ void k_backward_team(const BwdArgs a)
                 if (!anynz) p = 1.0;
             }
             // ---- exchange 1: (w_j, b_j) of frame f
-            double* x1 = xb + (STATS ? 0 : (s & 1)) * cpb * 3 * N + g.team * 3 * N;
+            const int tm = WARP1 ? 0 : g.team;       // WARP1: the idle lanes (j >= N) read team 0's slab too
+            double* x1 = xb + (STATS ? 0 : (s & 1)) * cpb * 3 * N + tm * 3 * N;
             const double w_own = p * b_own;
             if (jv) { x1[2 * j] = (on && !isvirt) ? w_own : 0.0; x1[2 * j + 1] = (on && !isvirt) ? b_own : 0.0; }
             __syncthreads();
             double sb = 0.0, bnew = 0.0;
-            if (g.owns) {
+            if (WARP1) {
+                sb = warp_sum((jv && on && !isvirt) ? b_own : 0.0);
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < N) bnew = fma(Arow[WARP1 ? i : 0], x1[2 * i], bnew);
+                if (sb != 0.0) bnew /= sb;
+                if (!jv) bnew = 0.0;
+            } else if (g.owns) {
                 for (int i = 0; i < N; ++i) sb += x1[2 * i + 1];
                 if (jv) {
                     for (int i = 0; i < N; ++i) bnew = fma(At_s[i * N + j], x1[2 * i], bnew);   // sum_i' A[j][i'] w_i'
@@ -289,13 +328,19 @@ __global__ void k_backward_team(const BwdArgs a)
             if (STATS) {
                 // ---- exchange 2: (g_i, alpha_{f-1,i}, b(f-1)_i); emits frame f-1 when it lies in the chain
                 const bool emit = on && (f - 1) < e;           // f-1 >= t0 holds because f >= flast = t0+1
-                double* x2 = xb + cpb * 3 * N + g.team * 3 * N;
+                double* x2 = xb + cpb * 3 * N + tm * 3 * N;
                 const double g_own = emit ? al * bnew : 0.0;
                 if (jv) { x2[3 * j] = g_own; x2[3 * j + 1] = emit ? al : 0.0; x2[3 * j + 2] = emit ? bnew : 0.0; }
                 __syncthreads();
+                double S = 0.0, sbn = 0.0;
+                if (WARP1) {                                 // every lane of the warp takes part in the shuffles
+                    S = warp_sum(jv ? g_own : 0.0);
+                    sbn = warp_sum((jv && emit) ? bnew : 0.0);
+                }
                 if (g.owns) {
-                    double S = 0.0, sbn = 0.0;
-                    for (int i = 0; i < N; ++i) { S += x2[3 * i]; sbn += x2[3 * i + 2]; }
+                    if (!WARP1) {
+                        for (int i = 0; i < N; ++i) { S += x2[3 * i]; sbn += x2[3 * i + 2]; }
+                    }
                     if (emit && jv) {
                         const long long row = trow + (f - 1);
                         // transition f-1 -> f : C'[i][j] += alpha_{f-1,i} * w_j / (sb * S)
@@ -303,8 +348,14 @@ __global__ void k_backward_team(const BwdArgs a)
                             double wn = w_own;
                             if (sb != 0.0) wn /= sb;
                             wn /= S;
-                            double* Cc = Cacc + g.team * N * N;
-                            for (int i = 0; i < N; ++i) Cc[i * N + j] = fma(x2[3 * i + 1], wn, Cc[i * N + j]);
+                            if (WARP1) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (i < N) Ccol[(WARP1 && STATS) ? i : 0] = fma(x2[3 * i + 1], wn, Ccol[(WARP1 && STATS) ? i : 0]);
+                            } else {
+                                double* Cc = Cacc + g.team * N * N;
+                                for (int i = 0; i < N; ++i) Cc[i * N + j] = fma(x2[3 * i + 1], wn, Cc[i * N + j]);
+                            }
                         }
                         const double gam = g_own / S;
                         st_g += gam;
@@ -329,6 +380,11 @@ __global__ void k_backward_team(const BwdArgs a)
         // per-block partial statistics: [C' (N*N) | gamma0 (N) | sum gamma (N) | sum gamma d (N) | sum gamma d^2 (N)]
         const int nstat = N * N + 4 * N;
         double* out = a.partials + (long long)blockIdx.x * nstat;
+        if (WARP1 && jv) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < N) Cacc[i * N + j] = Ccol[(WARP1 && STATS) ? i : 0];
+        }
         __syncthreads();
         for (int k = threadIdx.x; k < N * N; k += blockDim.x) {
             double v = 0.0;
@@ -484,11 +540,12 @@ static int launch_forward_em(const FwdArgs& a, cudaStream_t st)
     FwdArgs b = a;
     b.cpb = cpb;
     const size_t smem = sizeof(double) * ((size_t)a.N * a.N + 2 * (size_t)cpb * a.N);
-    int rc = set_smem(k_forward_team<EM>, smem);
+    int rc = set_smem(k_forward_team<EM, false>, smem);
     if (rc) return rc;
     const int groups = (a.ch.n + cpb - 1) / cpb;
     if (groups <= 0) return BHMM_OK;
-    k_forward_team<EM><<<persistent_grid(groups, threads, smem), threads, smem, st>>>(b);
+    if (threads == 32 && cpb == 1) k_forward_team<EM, true><<<persistent_grid(groups, threads, smem), threads, smem, st>>>(b);
+    else k_forward_team<EM, false><<<persistent_grid(groups, threads, smem), threads, smem, st>>>(b);
     return BHMM_OK;
 }
 
@@ -520,12 +577,16 @@ static int launch_backward_em(const BwdArgs& a, cudaStream_t st)
     b.cpb = cpb;
     size_t smem = sizeof(double) * ((size_t)a.N * a.N + 6 * (size_t)cpb * a.N);
     if (STATS) smem += sizeof(double) * (size_t)cpb * a.N * a.N;
-    int rc = set_smem(k_backward_team<EM, STATS>, smem);
+    int rc = set_smem(k_backward_team<EM, STATS, false>, smem);
     if (rc) return rc;
     const int groups = (a.ch.n + cpb - 1) / cpb;
     if (groups <= 0) return BHMM_OK;
     const int grid = STATS ? a.grid : persistent_grid(groups, threads, smem);
-    k_backward_team<EM, STATS><<<grid, threads, smem, st>>>(b);
+#ifndef TEAM_WARP1_STATS
+#define TEAM_WARP1_STATS 0   // measured slower for the fused statistics kernel at N=32 (33 vs 25 ms); kept for forward and literal backward
+#endif
+    if (threads == 32 && cpb == 1 && (!STATS || TEAM_WARP1_STATS)) k_backward_team<EM, STATS, true><<<grid, threads, smem, st>>>(b);
+    else k_backward_team<EM, STATS, false><<<grid, threads, smem, st>>>(b);
     return BHMM_OK;
 }
 
