@@ -106,12 +106,12 @@ int auto_warm_lane(int N)
 
 int auto_chunk_lane(long long rows, int N, int warm)
 {
-    // one thread per chain; ~8 resident warps per SM (register-limited) fill the machine once
+    // one thread per chain
     if (g_chunk_override > 0) return g_chunk_override;
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    (void)N;
-    const long long target = (long long)sms * 8 * 32;
+    // exactly one wave of resident blocks (occupancy of the register-hungriest lane kernel for this N)
+    const long long target = (long long)sms * lane_blocks_per_sm(N, EM_GAUSS) * lane_threads();
     long long c = (rows + target - 1) / target;
     c = std::max<long long>(c, 2LL * warm);
     c = std::max<long long>(c, 64);

@@ -119,6 +119,19 @@ void batch_plan(bhmm_b200_batch* b, int chunk, int warm)
 {
     const int w = warm > 0 ? warm : (b->lane ? auto_warm_lane(b->N) : auto_warm(b->N));
     b->chunk = chunk > 0 ? chunk : (b->lane ? auto_chunk_lane(b->rows, b->N, w) : auto_chunk(b->rows, b->N, w));
+    if (chunk <= 0 && b->lane) {
+        // the lane kernels run all chains in ONE wave of resident blocks: a few chains too many (every trajectory rounds
+        // its chain count up) would double the kernel time, so lengthen the chunk until the count fits
+        int sms = 148, dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long cap = (long long)sms * lane_blocks_per_sm(b->N, EM_GAUSS) * lane_threads();
+        for (int it = 0; it < 200; ++it) {
+            long long n = 0;
+            for (int k = 0; k < b->K; ++k) n += (b->offsets[k + 1] - b->offsets[k] + b->chunk - 1) / b->chunk;
+            if (n <= cap || b->chunk >= (1 << 30)) break;
+            b->chunk = (int)std::min<long long>((long long)b->chunk + std::max(1, b->chunk / 100), 1 << 30);
+        }
+    }
     b->warm_f = b->warm_b = w;
     b->warm_min = warm > 0 ? warm : 32;       // an explicit warm-up length is a floor for the adaptation
     build_plan(b->offsets.data(), b->K, b->chunk, b->plan);

@@ -87,7 +87,11 @@ struct LaneArgs {
     long long* counts;       // device int64 [C (N*N) | n0 (N) | frames per state (N)], accumulated with atomics
     int* err;
 };
-enum { LANE_FORWARD = 0, LANE_FORWARD_ROWMAJOR = 1, LANE_BACKWARD_STATS = 2, LANE_SAMPLE_MAP = 3, LANE_SAMPLE_FIX = 4 };
+enum { LANE_FORWARD = 0, LANE_FORWARD_ROWMAJOR = 1, LANE_BACKWARD_STATS = 2, LANE_SAMPLE_MAP = 3, LANE_SAMPLE_FIX = 4,
+       LANE_QUERY_BLOCKS = 5 };
+// resident blocks per SM of the most register-hungry lane kernel for this N (occupancy API); sizes the chain count
+int lane_blocks_per_sm(int N, int em);
+int lane_threads();
 int launch_lane_sum_moments(const double* partials, int rows, int N, double* sums, cudaStream_t st);
 bool lane_supported(int N, int em);
 int lane_blocks(int n_chains);

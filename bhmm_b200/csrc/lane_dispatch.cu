@@ -68,3 +68,18 @@ int launch_lane_sum_moments(const double* partials, int rows, int N, double* sum
     k_sum_moments<<<1, 64, 0, st>>>(partials, rows, 2 * N, sums);
     return BHMM_OK;
 }
+
+int lane_threads() { return LANE_THREADS; }
+
+int lane_blocks_per_sm(int N, int em)
+{
+    static int cache[LANE_MAX_N + 1][3] = {};
+    if (N < 1 || N > LANE_MAX_N || em < 0 || em > 2) return 4;
+    if (cache[N][em] == 0) {
+        LaneArgs a{};
+        LaneHostParams hp{nullptr, nullptr, nullptr, nullptr};
+        const int r = launch_lane(a, hp, N, em, LANE_QUERY_BLOCKS, nullptr);
+        cache[N][em] = (r < 0) ? -r : 4;
+    }
+    return cache[N][em];
+}

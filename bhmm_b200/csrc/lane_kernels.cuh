@@ -893,7 +893,7 @@ k_sample_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
 template <int N>
 void fill_params(LaneParams<N>& P, const double* A, const double* pi, const double* mu, const double* sigma)
 {
-    for (int k = 0; k < N * N; ++k) P.A[k] = A[k];
+    for (int k = 0; k < N * N; ++k) P.A[k] = A ? A[k] : 0.0;
     for (int j = 0; j < N; ++j) {
         P.pi[j] = pi ? pi[j] : 0.0;
         P.mu[j] = mu ? mu[j] : 0.0;
@@ -916,8 +916,20 @@ int launch_lane_n(const LaneArgs& a, const LaneHostParams& hp, int em, int what,
     LaneParams<N> P;
     fill_params<N>(P, hp.A, hp.pi, hp.mu, hp.sigma);
     const int blocks = (a.ch.n + LANE_THREADS - 1) / LANE_THREADS;
-    if (blocks <= 0) return BHMM_OK;
+    if (blocks <= 0 && what != LANE_QUERY_BLOCKS) return BHMM_OK;
     constexpr int G = group_of<N>();
+    if (what == LANE_QUERY_BLOCKS) {
+        // (returned through the int result: resident blocks per SM, limited by the backward + statistics kernel)
+        int nf = 0, nb = 0;
+        if (em == EM_GAUSS) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nf, k_forward_lane<N, EM_GAUSS, false>, LANE_THREADS, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_backward_stats_lane<N, EM_GAUSS, G>, LANE_THREADS, 0);
+        } else {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nf, k_forward_lane<N, EM_DISC, false>, LANE_THREADS, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_backward_stats_lane<N, EM_DISC, G>, LANE_THREADS, 0);
+        }
+        return -max(1, min(nf, nb));     // negative: not an error code
+    }
     if (what == LANE_FORWARD) {
         if (em == EM_GAUSS) k_forward_lane<N, EM_GAUSS, false><<<blocks, LANE_THREADS, 0, st>>>(P, a);
         else k_forward_lane<N, EM_DISC, false><<<blocks, LANE_THREADS, 0, st>>>(P, a);
