@@ -80,7 +80,7 @@ def synth_gaussian_gpu(N, K, T, seed, device):
 
 # ------------------------------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md clocks line)."""
+    """nvidia-smi sampled every 100 ms while the timed region runs (B200_PROFILING.md clocks line)."""
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
@@ -96,7 +96,7 @@ class ClockSampler(object):
             os.close(fd)
             self.fh = open(self.path, 'w')
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
-                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=self.fh,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -270,7 +270,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident measurement (the clock sampler starts before the warm-up so that nvidia-smi is up and
-    # sampling every 200 ms by the time the timed region runs; only samples under load are summarised)
+    # sampling every 100 ms by the time the timed region runs; only samples under load are summarised)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -431,8 +431,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--trajectories', type=int, default=0, help='override trajectories per GPU')
