@@ -318,6 +318,9 @@ extern "C" void bhmm_b200_glibc_uniforms(int seed, long n, double* u)
     for (long k = 0; k < n; ++k) u[k] = r.uniform();
 }
 
+static size_t chase_scratch_bytes(int N, int T);
+static int chase_single(const unsigned char* F, int N, int T, char* scratch, int* d_path, cudaStream_t st);
+
 static int require_device()
 {
     int n = 0;
@@ -467,6 +470,7 @@ extern "C" int bhmm_b200_viterbi_dev(int* d_path, const double* d_A, const doubl
     Carver cv;
     const size_t o_off = cv.add<long long>(2);
     const size_t o_bp = cv.add<unsigned short>((size_t)T * N);
+    const size_t o_chase = cv.add<char>(chase_scratch_bytes(N, T));
     RC_TRY(g_lit_arena.ensure(cv.off + 256));
     long long* d_offs = (long long*)(g_lit_arena.base + o_off);
     const long long offs[2] = {0, T};
@@ -478,32 +482,34 @@ extern "C" int bhmm_b200_viterbi_dev(int* d_path, const double* d_A, const doubl
     a.backptr = g_lit_arena.base + o_bp; a.path = d_path;
     RC_TRY(launch_viterbi_team(a, EM_POBS, st));
     LAUNCHED(1);
+    if (N <= 256)       // uint8 maps: the path is resolved in parallel; wider back-pointers were backtraced in the kernel
+        RC_TRY(chase_single((const unsigned char*)a.backptr, N, T, g_lit_arena.base + o_chase, d_path, st));
     return finish(st);
 }
 
-// path from a (T,N) alpha and per-ROW uniforms (u_row[t] is the draw of frame t)
-static int sample_rows_locked(int* d_path, const double* d_alpha, const double* d_A, const double* d_urow, int N,
-                              int T, char* scratch, cudaStream_t st)
+// Resolve the path of ONE trajectory from its map table F (T,N): F[t][s'] = state at t given state s' at t+1 (the last
+// row ignores s').  Segment-wise map composition (k_chase_*); `scratch` holds chase_scratch_bytes(N, T) bytes.
+static size_t chase_scratch_bytes(int N, int T)
+{
+    const size_t nseg = (size_t)(T + 255) / 256 + 1;
+    return nseg * (8 + 12 + N + 4) + 16 + 4096;
+}
+
+static int chase_single(const unsigned char* F, int N, int T, char* scratch, int* d_path, cudaStream_t st)
 {
     const int seg = 256;
     HostPlan sp;
     const long long offs[2] = {0, T};
     build_plan(offs, 1, seg, sp);
     Carver cv;
-    const size_t o_off = cv.add<long long>(2);
-    const size_t o_F = cv.add<unsigned char>((size_t)T * N);
     const size_t o_row0 = cv.add<long long>(sp.n);
     const size_t o_len = cv.add<int>(sp.n), o_t0 = cv.add<int>(sp.n), o_T = cv.add<int>(sp.n);
     const size_t o_map = cv.add<unsigned char>((size_t)sp.n * N);
     const size_t o_enter = cv.add<int>(sp.n);
-    const size_t o_err = cv.add<int>(1);
-    long long* d_offs = (long long*)(scratch + o_off);
-    CUDA_TRY(cudaMemcpyAsync(d_offs, offs, sizeof(offs), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(scratch + o_row0, sp.row0.data(), sizeof(long long) * sp.n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(scratch + o_len, sp.len.data(), sizeof(int) * sp.n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(scratch + o_t0, sp.t0.data(), sizeof(int) * sp.n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(scratch + o_T, sp.T.data(), sizeof(int) * sp.n, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(scratch + o_err, 0, sizeof(int), st));
     CUDA_TRY(cudaStreamSynchronize(st));
     Chains sg{};
     sg.row0 = (const long long*)(scratch + o_row0);
@@ -511,10 +517,29 @@ static int sample_rows_locked(int* d_path, const double* d_alpha, const double* 
     sg.t0 = (const int*)(scratch + o_t0);
     sg.T = (const int*)(scratch + o_T);
     sg.n = sp.n;
+    RC_TRY(launch_chase(F, sg, N, (unsigned char*)(scratch + o_map), (int*)(scratch + o_enter), d_path, st));
+    LAUNCHED(3);
+    return BHMM_OK;
+}
+
+// path from a (T,N) alpha and per-ROW uniforms (u_row[t] is the draw of frame t)
+static int sample_rows_locked(int* d_path, const double* d_alpha, const double* d_A, const double* d_urow, int N,
+                              int T, char* scratch, cudaStream_t st)
+{
+    Carver cv;
+    const size_t o_off = cv.add<long long>(2);
+    const size_t o_F = cv.add<unsigned char>((size_t)T * N);
+    const size_t o_err = cv.add<int>(1);
+    const size_t o_chase = cv.add<char>(chase_scratch_bytes(N, T));
+    long long* d_offs = (long long*)(scratch + o_off);
+    const long long offs[2] = {0, T};
+    CUDA_TRY(cudaMemcpyAsync(d_offs, offs, sizeof(offs), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(scratch + o_err, 0, sizeof(int), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     unsigned char* F = (unsigned char*)(scratch + o_F);
     RC_TRY(launch_sample_table(d_alpha, d_A, d_urow, d_offs, 1, N, T, F, (int*)(scratch + o_err), st));
-    RC_TRY(launch_chase(F, sg, N, (unsigned char*)(scratch + o_map), (int*)(scratch + o_enter), d_path, st));
-    LAUNCHED(4);
+    LAUNCHED(1);
+    RC_TRY(chase_single(F, N, T, scratch + o_chase, d_path, st));
     int err = 0;
     CUDA_TRY(cudaMemcpyAsync(&err, scratch + o_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -524,8 +549,7 @@ static int sample_rows_locked(int* d_path, const double* d_alpha, const double* 
 
 static size_t sample_scratch_bytes(int N, int T)
 {
-    const size_t nseg = (size_t)(T + 255) / 256 + 1;
-    return (size_t)T * N + nseg * (8 + 12 + N + 4) + 4096;
+    return (size_t)T * N + chase_scratch_bytes(N, T) + 4096;
 }
 
 extern "C" int bhmm_b200_sample_path_dev(int* d_path, const double* d_alpha, const double* d_A, const double* d_u,

@@ -459,6 +459,10 @@ static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const do
     a.backptr = b->d_F; a.path = d_path;
     RC_TRY(launch_viterbi_team(a, emkind, st));
     LAUNCHED(1);
+    if (N <= 256) {     // uint8 maps written by the kernel: resolve the paths by segment-wise map composition
+        RC_TRY(launch_chase(b->d_F, b->seg, N, b->seg_map, b->seg_enter, d_path, st));
+        LAUNCHED(3);
+    }
     return finish_stream(st);
 }
 

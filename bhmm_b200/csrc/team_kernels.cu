@@ -79,6 +79,18 @@ __device__ __forceinline__ double em_load(const Emission& em, long long row, int
     return em.Bt[(long long)em.sym[row] * N + j];
 }
 
+// L1 prefetch of the emission input `ahead` frames further along the trajectory (sequential walks with few warps per SM
+// cannot hide the DRAM latency of a load issued one step ahead)
+template <int EM>
+__device__ __forceinline__ void em_prefetch(const Emission& em, long long row, int j, int N)
+{
+    const void* p;
+    if (EM == EM_POBS) p = em.pobs + row * N + j;
+    else if (EM == EM_GAUSS) p = em.obs + row;
+    else p = em.sym + row;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 template <int EM>
 __device__ __forceinline__ double em_value(double raw, double mu, double sigma)
 {
@@ -415,10 +427,15 @@ __global__ void k_backward_team(const BwdArgs a)
 template <int EM, typename PtrT>
 __global__ void k_viterbi_team(const VitArgs a)
 {
+    // CHASE (N <= 256): the kernel writes the map F[t][s'] = state at t given state s' at t+1 (i.e. the back-pointers
+    // shifted by one frame, and the final argmax in the last row); the path is then resolved in parallel by the
+    // segment-wise map composition of sample_kernels.cu (k_chase_*).  Otherwise thread 0 backtraces in place.
+    constexpr bool CHASE = (sizeof(PtrT) == 1);
     extern __shared__ double sm[];
     const int N = a.N, cpb = a.cpb;
     double* A_s = sm;                         // N*N
-    double* vb = A_s + N * N;                 // 2 * cpb * N
+    double* ub = A_s + N * N;                 // cpb * N  unnormalised row
+    double* vb = ub + cpb * N;                // cpb * N  normalised row
     const TeamGeom g = team_geometry(N, cpb);
     const int j = g.j;
     const bool jv = g.owns && j < N;
@@ -428,6 +445,8 @@ __global__ void k_viterbi_team(const VitArgs a)
     const double pi_j = jv ? a.pi[j] : 0.0;
     PtrT* bp = reinterpret_cast<PtrT*>(a.backptr);
     __syncthreads();
+    const bool onewarp = (blockDim.x == 32);
+    auto team_sync = [&]() { if (onewarp) __syncwarp(); else __syncthreads(); };
 
     for (int base = blockIdx.x * cpb; base < a.K; base += gridDim.x * cpb) {
         const int k = base + g.team;
@@ -436,56 +455,61 @@ __global__ void k_viterbi_team(const VitArgs a)
         int T = 0;
         if (have) { row0 = a.offsets[k]; T = (int)(a.offsets[k + 1] - row0); }
         const int Tmax = block_max(T);
+        double* urow = ub + (g.owns ? g.team : 0) * N;
+        double* vrow = vb + (g.owns ? g.team : 0) * N;
         double raw_next = (have && jv && T > 0) ? em_load<EM>(a.em, row0, j, N) : 0.0;
         for (int t = 0; t < Tmax; ++t) {
             const bool on = have && t < T;
             const double raw = raw_next;
             if (have && jv && t + 1 < T) raw_next = em_load<EM>(a.em, row0 + t + 1, j, N);
+            if (have && jv && t + 64 < T && (EM == EM_POBS || (t & 3) == 0)) em_prefetch<EM>(a.em, row0 + t + 64, j, N);
             double p = 0.0;
             if (on && jv) p = em_value<EM>(raw, mu, sigma);
             if (EM != EM_POBS && a.em.ignore_outliers) {
                 const bool anynz = team_any(p != 0.0, g);
                 if (!anynz) p = 1.0;
             }
-            const double* vprev = vb + ((t + 1) & 1) * cpb * N + g.team * N;
-            double* vcur = vb + (t & 1) * cpb * N + g.team * N;
             double vn = 0.0;
             if (on && jv) {
                 if (t == 0) {
                     vn = __dmul_rn(p, pi_j);
                 } else {
                     int best = 0;
-                    double m = __dmul_rn(vprev[0], A_s[j]);
+                    double m = __dmul_rn(vrow[0], A_s[j]);
                     for (int i = 1; i < N; ++i) {
-                        const double h = __dmul_rn(vprev[i], A_s[i * N + j]);
+                        const double h = __dmul_rn(vrow[i], A_s[i * N + j]);
                         if (h > m) { m = h; best = i; }
                     }
-                    bp[(row0 + t) * N + j] = (PtrT)best;
-                    vn = __dmul_rn(__dmul_rn(p, vprev[best]), A_s[best * N + j]);
+                    if (CHASE) bp[(row0 + t - 1) * N + j] = (PtrT)best;
+                    else bp[(row0 + t) * N + j] = (PtrT)best;
+                    vn = __dmul_rn(__dmul_rn(p, vrow[best]), A_s[best * N + j]);
                 }
+                urow[j] = vn;
             }
-            if (jv && on) vcur[j] = vn;
-            __syncthreads();
-            double ssum = 0.0;
-            if (on) for (int i = 0; i < N; ++i) ssum = __dadd_rn(ssum, vcur[i]);
-            __syncthreads();
-            if (jv && on) vcur[j] = __ddiv_rn(vn, ssum);   // finished teams keep their last row for the backtrace
-            __syncthreads();
+            team_sync();
+            if (on && jv) {
+                double ssum = 0.0;
+                for (int i = 0; i < N; ++i) ssum = __dadd_rn(ssum, urow[i]);
+                vrow[j] = __ddiv_rn(vn, ssum);      // finished teams keep their last row
+            }
+            team_sync();
         }
-        // backtrace by the team's thread 0 (path[T-1] = first max of v, then follow the back-pointers);
-        // the back-pointer rows were written by this block, so a block-level fence suffices.
-        __threadfence_block();
-        __syncthreads();
-        if (have && j == 0 && T > 0) {
-            const double* vlast = vb + ((T - 1) & 1) * cpb * N + g.team * N;
+        // path[T-1] = first maximum of the last row (_hidden.c:268)
+        if (have && jv && T > 0) {
             int best = 0;
-            double m = vlast[0];
-            for (int i = 1; i < N; ++i) if (vlast[i] > m) { m = vlast[i]; best = i; }
-            int* path = a.path + row0;
-            path[T - 1] = best;
-            for (int t = T - 2; t >= 0; --t) {
-                best = (int)bp[(row0 + t + 1) * N + best];
-                path[t] = best;
+            double m = vrow[0];
+            for (int i = 1; i < N; ++i) if (vrow[i] > m) { m = vrow[i]; best = i; }
+            if (CHASE) {
+                bp[(row0 + T - 1) * N + j] = (PtrT)best;
+            } else if (j == 0) {
+                // the back-pointer rows were written by this block: a block-level fence suffices
+                __threadfence_block();
+                int* path = a.path + row0;
+                path[T - 1] = best;
+                for (int t = T - 2; t >= 0; --t) {
+                    best = (int)bp[(row0 + t + 1) * N + best];
+                    path[t] = best;
+                }
             }
         }
         __syncthreads();
