@@ -48,6 +48,16 @@ bool lane_supported(int N, int em) { return N >= 1 && N <= LANE_MAX_N && (em == 
 
 int launch_lane(const LaneArgs& a, const LaneHostParams& hp, int N, int em, int what, cudaStream_t st)
 {
+    if (em == EM_GAUSS && hp.sigma) {
+        // the lazily rescaled recursion leaves 2^(1024 - LANE_LAZY) of head-room for one step's growth, which is at most
+        // N times the largest emission density 1 / (sigma sqrt(2 pi))
+        for (int j = 0; j < N; ++j) {
+            if (!(hp.sigma[j] >= 1e-100)) {
+                bhmm_set_error(BHMM_ERR_UNSUPPORTED, "Gaussian output model: every sigma must be >= 1e-100 (and not NaN)");
+                return BHMM_ERR_UNSUPPORTED;
+            }
+        }
+    }
     switch (N) {
 #define CASE(NN) case NN: return launch_lane_##NN(a, hp, em, what, st);
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)

@@ -54,6 +54,10 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef LANE_KEEP_F
 #define LANE_KEEP_F 40       // forward kernel: this many entries of A stay in registers for the whole kernel (shared-
 #endif                       // memory -> register bandwidth, 8 B per lane and operand, is what bounds the lane kernels)
+#ifndef LANE_EXP_TABLE
+#define LANE_EXP_TABLE 1     // exp() of the Gaussian emission: 0 = degree-11 polynomial on |r| <= ln2/2; 1 = 32-entry table of
+#endif                       // 2^(j/32) in shared memory + degree-5 polynomial on |r| <= ln2/64 (6 FP64 instructions less
+                             // per state; fetching the entry with warp shuffles instead was measured slower)
 #ifndef LANE_G_MID
 #define LANE_G_MID 4         // lanes sharing the xi accumulator rows for 9 <= N <= 12
 #endif
@@ -87,12 +91,29 @@ __constant__ double EXPK[13] = {
     0x1.555555555555ap-3,  0x1.0000000000011p-1,
     1.4426950408889634074, 6.93147180369123816490e-01, 1.90821492927058770002e-10};
 
+// Table variant: exp(x) = 2^k 2^(j/32) exp(r), 32 k + j = rint(32 x / ln 2), |r| <= ln2/64.  EXPK2 = c5..c2 of the
+// degree-5 Chebyshev-node interpolant of exp on that interval (relative error 1.4e-16), 32/ln2, ln2/32.  The reduction
+// is a single FMA: the rounding of ln2/32 costs |x| 8e-17 relative, below the rounding of x itself.
+__constant__ double EXPK2[6] = {0x1.11115c0cff61ap-7, 0x1.5555d88e3ae37p-5, 0x1.5555555547d22p-3, 0x1.ffffffffd0b4bp-2,
+                                0x1.71547652b82fep+5, 0x1.62e42fefa39efp-6};
+__constant__ double EXPT[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+
+__device__ __noinline__ double slow_exp(double x) { return exp(x); }
+
 // Gaussian emission of one frame for all N states, evaluated "vertically": every stage of the exp() (range
 // reduction by ln 2, Horner steps, exponent insertion) is issued for all states before the next stage, so the N
 // dependent chains interleave and hide the FP64 latency.  exp(x) = 2^n exp(r), n = rint(x/ln2), |r| <= ln2/2,
 // degree-11 near-minimax polynomial (< 1 ulp).  The main path is branch free; states whose argument lies below
 // -708 (result denormal or zero) or is NaN are redone with the library exp() in a rarely taken tail.
-template <int N, typename CV>
+template <int N, int TB, typename CV>
 __device__ __forceinline__ void emission_gauss(const CV& P, double o, int ignore_outliers, double (&p)[N])
 {
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
@@ -108,42 +129,94 @@ __device__ __forceinline__ void emission_gauss(const CV& P, double o, int ignore
         x[j] = -(d * d);
 #endif
     }
+    if constexpr (TB == 0) {
 #pragma unroll
-    for (int j = 0; j < N; ++j) t[j] = fma(x[j], EXPK[10], MAGIC);
+        for (int j = 0; j < N; ++j) t[j] = fma(x[j], EXPK[10], MAGIC);
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-        const double n = t[j] - MAGIC;
-        r[j] = fma(n, -EXPK[11], x[j]);
-        r[j] = fma(n, -EXPK[12], r[j]);
-    }
+        for (int j = 0; j < N; ++j) {
+            const double n = t[j] - MAGIC;
+            r[j] = fma(n, -EXPK[11], x[j]);
+            r[j] = fma(n, -EXPK[12], r[j]);
+        }
 #pragma unroll
-    for (int j = 0; j < N; ++j) p[j] = fma(EXPK[0], r[j], EXPK[1]);
+        for (int j = 0; j < N; ++j) p[j] = fma(EXPK[0], r[j], EXPK[1]);
 #pragma unroll
-    for (int k = 2; k < 10; ++k) {
+        for (int k = 2; k < 10; ++k) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], EXPK[k]);
-    }
+            for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], EXPK[k]);
+        }
 #pragma unroll
-    for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 1.0);
+        for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 1.0);
 #pragma unroll
-    for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 1.0);
-    // tail / outlier tests on the high words with integer instructions (the FP64 pipe is the bottleneck):
-    // x < -708 or NaN  <=>  (hi(x) as unsigned) > hi(-708.0) = 0xC0862000, or exponent field all ones
-    unsigned tailbits = 0u;
+        for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 1.0);
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-        const int ni = __double2loint(t[j]);
-        p[j] = __longlong_as_double(__double_as_longlong(p[j]) + ((long long)ni << 52));
+        for (int j = 0; j < N; ++j) {
+            const int ni = __double2loint(t[j]);
+            p[j] = __longlong_as_double(__double_as_longlong(p[j]) + ((long long)ni << 52));
 #if !LANE_FOLD_NRM
-        p[j] *= P.nrml[j];          // (comparison build only)
+            p[j] *= P.nrml[j];          // (comparison build only)
 #endif
-        const unsigned hx = (unsigned)__double2hiint(x[j]);
-        tailbits |= (hx > 0xC0862000u || (hx & 0x7ff00000u) == 0x7ff00000u) ? (1u << j) : 0u;
-    }
-    if (tailbits) {
+        }
+    } else {
 #pragma unroll
-        for (int j = 0; j < N; ++j)
-            if (tailbits & (1u << j)) p[j] = exp(x[j]);
+        for (int j = 0; j < N; ++j) t[j] = fma(x[j], EXPK2[4], MAGIC);
+#pragma unroll
+        for (int j = 0; j < N; ++j) r[j] = fma(t[j] - MAGIC, -EXPK2[5], x[j]);
+        // 2^k 2^(j/32) as one double: the table's high words are stored minus (j << 15), so adding kk << 15
+        // (kk = 32 k + j) leaves hi(2^(j/32)) + (k << 20)
+        double tb[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const int kk = __double2loint(t[j]);
+            const double e = P.tab[kk & 31];
+            tb[j] = __hiloint2double(__double2hiint(e) + (kk << 15), __double2loint(e));
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) p[j] = fma(EXPK2[0], r[j], EXPK2[1]);
+#pragma unroll
+        for (int k = 2; k < 4; ++k) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], EXPK2[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 1.0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 1.0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            p[j] *= tb[j];
+#if !LANE_FOLD_NRM
+            p[j] *= P.nrml[j];          // (comparison build only)
+#endif
+        }
+    }
+    // tail test on the high words with integer instructions: x < -708 (result denormal or zero), x > 708 or x not
+    // finite  <=>  max_j (unsigned) hi(x_j) > hi(-708.0)  or  max_j (signed) hi(x_j) > hi(708.0)
+    {
+        unsigned umax = (unsigned)__double2hiint(x[0]);
+        int smax = __double2hiint(x[0]);
+#pragma unroll
+        for (int j = 1; j < N; ++j) {
+            umax = max(umax, (unsigned)__double2hiint(x[j]));
+            smax = max(smax, __double2hiint(x[j]));
+        }
+        if (umax > 0xC0862000u || smax > 0x40862000) {
+            // Far states are common (any state more than 37.6 sigma away from the observation lands here), so the
+            // usual case is cheap: x <= -746 underflows to exactly zero.  Only the thin band whose result is
+            // denormal, overflow and non-finite arguments go through the library exp(), out of line.
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const unsigned hx = (unsigned)__double2hiint(x[j]);
+                if (hx >= 0xC0875000u && hx <= 0xFFF00000u) {
+                    p[j] = 0.0;
+                } else if ((hx & 0x7fffffffu) > 0x40862000u) {
+                    p[j] = slow_exp(x[j]);
+#if !LANE_FOLD_NRM
+                    p[j] *= P.nrml[j];
+#endif
+                }
+            }
+        }
     }
     int nzbits = 0;
 #pragma unroll
@@ -186,27 +259,46 @@ struct LogAcc {
     __device__ __forceinline__ double value() const { return (double)esum * 0.693147180559945309417 + log(prod) + slow; }
 };
 
-// Power-of-two renormalisation: v *= 2^-shift with shift = (biased exponent of the largest component) - 1023, done
-// on the high words with integer instructions (exact, and off the FP64 pipe).  Components more than 2^-1022 below
-// the largest one (or denormal) are flushed to zero.  Returns false when the largest component is tiny (< 2^-959),
-// zero, negative or not finite: the caller then normalises by the sum like the reference does.
+// Power-of-two renormalisation.  alpha and beta only have to stay inside the double range (gamma and xi are ratios), so
+// they are rescaled by an exact power of two, and only when the largest component has drifted out of the band
+// [1, 2^LANE_LAZY] (then it is put back to the middle; about one step in four has a lane that needs it).  The band
+// lies ABOVE one: a lazily scaled vector is never smaller than the reference's sum-normalised one, so nothing underflows
+// here that does not underflow there, and with LANE_LAZY = 480 the products alpha_i b_i of two such vectors and one
+// step's growth (at most N x the largest emission density) stay far below 2^1024.  top_exponent() is the biased
+// exponent of the largest component (integer max over the high words: off the FP64 pipe); when it is not a normal,
+// comfortably large number (tiny, zero, negative, not finite) the caller normalises by the sum like the reference
+// does (_hidden.c:57-63).
+#ifndef LANE_LAZY
+#define LANE_LAZY 480
+#endif
 template <int N>
-__device__ __forceinline__ bool scale_pow2(double (&v)[N], int& shift)
+__device__ __forceinline__ int top_exponent(const double (&v)[N])
 {
-    int hmax = __double2hiint(v[0]);
+    // ternary tree (the integer max takes three operands): depth 3 for N = 10 instead of a chain of 5
+    int h[N];
 #pragma unroll
-    for (int j = 1; j < N; ++j) hmax = max(hmax, __double2hiint(v[j]));
-    const int e = hmax >> 20;
-    if (e < 64 || e >= 0x7ff) return false;
-    shift = e - 1023;
-    const int dh = shift << 20;
-    const int floor_e = max(shift, 0);
+    for (int j = 0; j < N; ++j) h[j] = __double2hiint(v[j]);
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-        const int h = __double2hiint(v[j]);
-        v[j] = ((h >> 20) > floor_e) ? __hiloint2double(h - dh, __double2loint(v[j])) : 0.0;
+    for (int w = 1; w < N; w *= 3) {
+#pragma unroll
+        for (int j = 0; j < N; j += 3 * w) {
+            if (j + w < N) h[j] = max(h[j], h[j + w]);
+            if (j + 2 * w < N) h[j] = max(h[j], h[j + 2 * w]);
+        }
     }
-    return true;
+    return h[0] >> 20;
+}
+__device__ __forceinline__ bool regular_exponent(int e) { return e >= 64 && e < 2040; }
+// v *= 2^-shift unless e lies in the band; returns the shift applied
+template <int N>
+__device__ __forceinline__ int rescale_pow2(double (&v)[N], int e)
+{
+    if ((unsigned)(e - 1023) <= (unsigned)LANE_LAZY) return 0;
+    const int shift = max(e - (1023 + LANE_LAZY / 2), -1022);
+    const double f = __hiloint2double((1023 - shift) << 20, 0);
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] *= f;
+    return shift;
 }
 
 __device__ __forceinline__ long long il_base(int c, int Lmax, int NP2)
@@ -235,7 +327,10 @@ struct ConstView {
     const double* isg;
     const double* nrm;
     const double* nrml;
+    const double* tab;      // 2^(j/32), j = 0..31, in shared memory (high words pre-shifted, see emission_gauss)
 };
+template <int N>
+constexpr int lane_const_doubles() { return (int)(sizeof(LaneParams<N>) / sizeof(double)) + 32; }
 template <int N>
 __device__ __forceinline__ ConstView<N> make_const_view(const LaneParams<N>& P, double* smem)
 {
@@ -243,8 +338,14 @@ __device__ __forceinline__ ConstView<N> make_const_view(const LaneParams<N>& P, 
     constexpr int TOT = sizeof(LaneParams<N>) / sizeof(double);
     const double* src = reinterpret_cast<const double*>(&P);
     for (int k = threadIdx.x; k < TOT; k += blockDim.x) smem[k] = src[k];
+    if (threadIdx.x < 32) {
+        const double e = EXPT[threadIdx.x];
+        smem[TOT + threadIdx.x] = __hiloint2double(__double2hiint(e) - (threadIdx.x << 15), __double2loint(e));
+    }
     __syncthreads();
     ConstView<N> v;
+    v.tab = smem + TOT;
+
 #if LANE_CONST_SMEM == 2
     v.A = P.A;
 #else
@@ -262,7 +363,7 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
     constexpr int NP2 = (N + 1) / 2;
     constexpr int PF = 4;
 #if LANE_CONST_SMEM
-    __shared__ double cs[sizeof(LaneParams<N>) / sizeof(double)];
+    __shared__ double cs[lane_const_doubles<N>()];
     const ConstView<N> P = make_const_view<N>(Pk, cs);
 #else
     const LaneParams<N>& P = Pk;
@@ -307,7 +408,7 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
 #pragma unroll
     for (int k = 0; k < PF; ++k) ring[k] = fetch(k);
     auto emission = [&](double rawv, double (&pv)[N]) {
-        if (EM == EM_GAUSS) emission_gauss<N>(P, rawv, a.ignore_outliers, pv);
+        if (EM == EM_GAUSS) emission_gauss<N, LANE_EXP_TABLE>(P, rawv, a.ignore_outliers, pv);
         else emission_disc<N>(a, (int)__double_as_longlong(rawv), pv);
     };
 
@@ -318,31 +419,36 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
     for (int k = 0; k < KEEP; ++k) Areg[k] = P.A[k];
     auto Aat = [&](int k) -> double { return (k < KEEP) ? Areg[k] : P.A[k]; };
 
+    // v = (al A) o p
+    auto propagate = [&](double (&v)[N], const double (&p)[N]) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = al[0] * Aat(j);
+#pragma unroll
+        for (int i = 1; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) v[j] = fma(al[i], Aat(i * N + j), v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] *= p[j];
+    };
+
     // one frame of the recursion; PATH is a compile-time constant so that the fast paths carry no predicates
     auto step = [&](auto path_tag, int t, double raw, bool on) {
         constexpr int PATH = decltype(path_tag)::value;
         if (!on) return;
+        double p[N];
         const bool init = (PATH == PATH_GENERAL) && (t == tstart);
         double v[N];
         if (init && mode == 2) {
 #pragma unroll
             for (int j = 0; j < N; ++j) v[j] = al[j];
         } else {
-            double p[N];
             emission(raw, p);
             if (init) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) v[j] = (mode == 0) ? P.pi[j] * p[j] : p[j];
             } else {
-#pragma unroll
-                for (int j = 0; j < N; ++j) v[j] = al[0] * Aat(j);
-#pragma unroll
-                for (int i = 1; i < N; ++i) {
-#pragma unroll
-                    for (int j = 0; j < N; ++j) v[j] = fma(al[i], Aat(i * N + j), v[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < N; ++j) v[j] *= p[j];
+                propagate(v, p);
             }
         }
         // Renormalise.  Any positive scaling is equivalent for everything downstream (gamma and xi are ratios), so
@@ -350,8 +456,9 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
         //   sum_t log c_t = log sigma_end - log sigma_start + ln2 * sum shift_t (+ slow-path terms),
         // sigma = sum_j alpha_j at the frame before the chain and at its last frame (telescoping product).
         const bool inchain = (PATH == PATH_CHAIN) || (PATH == PATH_GENERAL && t >= t0);
-        int shift = 0;
-        if (scale_pow2<N>(v, shift)) {
+        const int e = top_exponent<N>(v);
+        if (regular_exponent(e)) {
+            const int shift = rescale_pow2<N>(v, e);
 #pragma unroll
             for (int j = 0; j < N; ++j) al[j] = v[j];
             if (inchain) esum += shift;
@@ -387,20 +494,37 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
         }
     };
 
-    for (int s = 0; s < total; ++s) {
+    // The steps of a warp come in runs: between two special frames of any of its lanes (first frame, hand-over
+    // frames, last frame) every lane keeps its class, so the class vote is taken once per run and the run itself is
+    // a tight loop over one of the fast paths.
+    auto next_raw = [&](int s) -> double {
         const double raw = ring[0];
 #pragma unroll
         for (int k = 0; k + 1 < PF; ++k) ring[k] = ring[k + 1];
         ring[PF - 1] = fetch(s + PF);
+        return raw;
+    };
+    int s = 0;
+    while (s < total) {
         const int t = t0 - maxpre + s;
         // lane class: 0 idle, 1 plain frame inside the chain, 2 plain warm-up frame, 3 first / hand-over frame
         const bool on = have && t >= tstart && t < tend;
         const int cls = !on ? 0 : ((t == tstart || t == tend - 1 || t == t0 - 1) ? 3 : (t >= t0 ? 1 : 2));
         const unsigned m1 = __ballot_sync(FULL, cls == 1), m2 = __ballot_sync(FULL, cls == 2),
                        m3 = __ballot_sync(FULL, cls == 3);
-        if (m3 || (m1 && m2)) step(BoolTag2<PATH_GENERAL>(), t, raw, on);
-        else if (m1) step(BoolTag2<PATH_CHAIN>(), t, raw, on);
-        else if (m2) step(BoolTag2<PATH_WARM>(), t, raw, on);
+        if (m3 || (m1 && m2) || !(m1 | m2)) {
+            step(BoolTag2<PATH_GENERAL>(), t, next_raw(s), on);
+            ++s;
+            continue;
+        }
+        // plain steps this lane has left before its next special frame (idle lanes: before they start)
+        const int rem = (cls == 1) ? tend - 2 - t : (cls == 2) ? t0 - 2 - t : (have && t < tstart) ? tstart - 1 - t : 0x7fffffff;
+        const int run = 1 + __reduce_min_sync(FULL, rem);
+        if (m1) {
+            for (int k = 0; k < run; ++k, ++s) step(BoolTag2<PATH_CHAIN>(), t0 - maxpre + s, next_raw(s), on);
+        } else {
+            for (int k = 0; k < run; ++k, ++s) step(BoolTag2<PATH_WARM>(), t0 - maxpre + s, next_raw(s), on);
+        }
     }
     // a chain whose last frame was renormalised by the slow path ends with sigma = 1: log_end = 0 is then exact
     if (have) a.chain_ll[c] = (log_end - log_start) + (double)esum * 0.693147180559945309417 + slow;
@@ -430,7 +554,7 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
     constexpr int NSTAT = N * N + 4 * N;
     __shared__ double red[(LANE_THREADS / 32) * NSTAT];
 #if LANE_CONST_SMEM
-    __shared__ double cs[sizeof(LaneParams<N>) / sizeof(double)];
+    __shared__ double cs[lane_const_doubles<N>()];
     const ConstView<N> P = make_const_view<N>(Pk, cs);
 #else
     const LaneParams<N>& P = Pk;
@@ -482,7 +606,7 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
 #pragma unroll
     for (int k = 0; k < PF; ++k) ring[k] = fetch(k);
     auto emission = [&](double rawv, double (&pv)[N]) {
-        if (EM == EM_GAUSS) emission_gauss<N>(P, rawv, a.ignore_outliers, pv);
+        if (EM == EM_GAUSS) emission_gauss<N, LANE_EXP_TABLE>(P, rawv, a.ignore_outliers, pv);
         else emission_disc<N>(a, (int)__double_as_longlong(rawv), pv);
     };
     double raw_next = 0.0;          // emission input of frame f+1
@@ -527,23 +651,41 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
         }
     };
 
+    // w = p o bt, b = A w
+    auto back_propagate = [&](double (&b)[N], double (&w)[N], const double (&p)[N]) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) w[j] = p[j] * bt[j];
+#pragma unroll
+        for (int i = 0; i < N; ++i) b[i] = P.A[i * N] * w[0];
+#pragma unroll
+        for (int j = 1; j < N; ++j) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) b[i] = fma(P.A[i * N + j], w[j], b[i]);
+        }
+    };
+
     // one frame f: given beta_{f+1} (bt) and the emission input of f+1, form b = A (p_{f+1} o beta_{f+1}), emit the
     // statistics of frame f when it belongs to the chain, leave beta_f in bt
     auto step = [&](auto path_tag, int f, double raw, bool on) {
         constexpr int PATH = decltype(path_tag)::value;
+        // CHAIN: straight-line code for all 32 lanes.  A lane whose chain has already ended (shorter chains of the
+        // same warp) keeps computing on the clamped inputs and is masked where its contribution is formed (rS = 0),
+        // which is cheaper than predicating the step and zeroing its w, u, gamma for the exchange.
+        const bool act = (PATH == PATH_CHAIN) || on;
         const bool init = (PATH == PATH_GENERAL) && on && f == fs;
-        const bool emit = (PATH == PATH_CHAIN && on) || (PATH == PATH_GENERAL && on && f < e);
+        const bool emit = (PATH == PATH_CHAIN) || (PATH == PATH_GENERAL && on && f < e);
         double w[N], u[N], gam[N];
         double o_f = 0.0;
-        if (PATH == PATH_GENERAL || !on) {
+        double p[N];
+        if (PATH == PATH_GENERAL) {
 #pragma unroll
             for (int j = 0; j < N; ++j) { w[j] = 0.0; u[j] = 0.0; gam[j] = 0.0; }
         }
-        if (on) {
+        if (act) {
             // forward variables of frame f: issued first, consumed after the matvec
             double2 a2[NP2];
             if (emit) {
-                const double2* src = il + ((long long)(f - t0) * NP2 << 5);
+                const double2* src = il + ((long long)(on ? f - t0 : 0) * NP2 << 5);
 #pragma unroll
                 for (int jp = 0; jp < NP2; ++jp) a2[jp] = __ldcs(src + (jp << 5));
             }
@@ -557,18 +699,10 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
                     for (int j = 0; j < N; ++j) b[j] = 1.0;
                 }
             } else {
-                double p[N];
                 emission(raw_next, p);
-#pragma unroll
-                for (int j = 0; j < N; ++j) w[j] = p[j] * bt[j];
-#pragma unroll
-                for (int i = 0; i < N; ++i) b[i] = P.A[i * N] * w[0];
-#pragma unroll
-                for (int j = 1; j < N; ++j) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) b[i] = fma(P.A[i * N + j], w[j], b[i]);
-                }
+                back_propagate(b, w, p);
             }
+            const int eb = top_exponent<N>(b);
             if (emit) {
                 // gamma_f = alpha_f o b / S ; xi_f = (alpha_f / S) (x) w   with S = sum_i alpha_f,i b_i
                 double al[N], gi[N];
@@ -580,7 +714,7 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
 #pragma unroll
                 for (int i = 0; i < N; ++i) gi[i] = al[i] * b[i];
                 const double S = tree_sum<N>(gi);
-                const double rS = 1.0 / S;
+                const double rS = (PATH == PATH_CHAIN && !on) ? 0.0 : 1.0 / S;
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     u[i] = al[i] * rS;
@@ -591,21 +725,21 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
 #pragma unroll
                     for (int i = 0; i < N; ++i) a.g0buf[(long long)c * N + i] = gam[i];
                 }
-                if (a.gamma) {
+                if (a.gamma && on) {
                     double* dst = a.gamma + (trow + f) * N;
 #pragma unroll
                     for (int i = 0; i < N; ++i) dst[i] = gam[i];
                 }
-                if (EM == EM_DISC && a.Bnum) {
+                if (EM == EM_DISC && a.Bnum && on) {
                     const int sy = (int)__double_as_longlong(raw);
 #pragma unroll
                     for (int i = 0; i < N; ++i) atomicAdd(a.Bnum + (long long)i * a.M + sy, gam[i]);
                 }
             }
-            // beta only needs to stay in range: exact power-of-two scaling; the sum-normalised vector of the
-            // reference (_hidden.c:104-107) is formed only where it is handed over
-            int shift = 0;
-            if (scale_pow2<N>(b, shift)) {
+            // beta only needs to stay in range: exact power-of-two scaling, and only when it has drifted; the
+            // sum-normalised vector of the reference (_hidden.c:104-107) is formed only where it is handed over
+            if (regular_exponent(eb)) {
+                rescale_pow2<N>(b, eb);
 #pragma unroll
                 for (int i = 0; i < N; ++i) bt[i] = b[i];
             } else {
@@ -626,20 +760,34 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
         if (PATH != PATH_WARM) accumulate(w, u, gam, o_f);
     };
 
-    for (int s = 0; s < total; ++s) {
+    // runs of plain steps between the special frames of the warp's lanes, as in the forward kernel
+    auto next_raw = [&](int s) -> double {
         const double raw = ring[0];                 // emission input of frame f
 #pragma unroll
         for (int k = 0; k + 1 < PF; ++k) ring[k] = ring[k + 1];
         ring[PF - 1] = fetch(s + PF);
+        return raw;
+    };
+    int s = 0;
+    while (s < total) {
         const int f = frame_of(s);
         // lane class: 0 idle, 1 plain frame inside the chain, 2 plain warm-up frame, 3 first / hand-over / frame 0
         const bool on = have && f <= fs && f >= t0;
         const int cls = !on ? 0 : ((f == fs || f == e || f == t0 || f == 0) ? 3 : (f < e ? 1 : 2));
         const unsigned m1 = __ballot_sync(FULL, cls == 1), m2 = __ballot_sync(FULL, cls == 2),
                        m3 = __ballot_sync(FULL, cls == 3);
-        if (m3 || (m1 && m2)) step(BoolTag2<PATH_GENERAL>(), f, raw, on);
-        else if (m1) step(BoolTag2<PATH_CHAIN>(), f, raw, on);
-        else if (m2) step(BoolTag2<PATH_WARM>(), f, raw, on);
+        if (m3 || (m1 && m2) || !(m1 | m2)) {
+            step(BoolTag2<PATH_GENERAL>(), f, next_raw(s), on);
+            ++s;
+            continue;
+        }
+        const int rem = (cls == 1) ? f - t0 - 1 : (cls == 2) ? f - e - 1 : (have && f > fs) ? f - fs - 1 : 0x7fffffff;
+        const int run = 1 + __reduce_min_sync(FULL, rem);
+        if (m1) {
+            for (int k = 0; k < run; ++k, ++s) step(BoolTag2<PATH_CHAIN>(), frame_of(s), next_raw(s), on);
+        } else {
+            for (int k = 0; k < run; ++k, ++s) step(BoolTag2<PATH_WARM>(), frame_of(s), next_raw(s), on);
+        }
     }
 
     // ---- reduce over the lanes that own the same rows (lane bits >= log2 G), then over the block's warps
