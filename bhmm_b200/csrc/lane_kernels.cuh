@@ -58,6 +58,19 @@ constexpr unsigned FULL = 0xffffffffu;
 #define LANE_EXP_TABLE 1     // exp() of the Gaussian emission: 0 = degree-11 polynomial on |r| <= ln2/2; 1 = 32-entry table of
 #endif                       // 2^(j/32) in shared memory + degree-5 polynomial on |r| <= ln2/64 (6 FP64 instructions less
                              // per state; fetching the entry with warp shuffles instead was measured slower)
+#ifndef LANE_UNROLL_F
+#define LANE_UNROLL_F 1      // unroll factor of the run loops over the chain fast path (forward / backward kernel)
+#endif
+#ifndef LANE_UNROLL_B
+#define LANE_UNROLL_B 1
+#endif
+constexpr int kUnrollF = LANE_UNROLL_F, kUnrollB = LANE_UNROLL_B;
+#ifndef LANE_OBS_PREFETCH
+#define LANE_OBS_PREFETCH 1  // prefetch the next cache line of the lane's observations into L1 (the register ring's
+#endif                       // rotation waits for the newest load, so its effective distance is one step)
+#ifndef LANE_XCH_MIN_G
+#define LANE_XCH_MIN_G 4     // lane groups of at least this size exchange their rows of u and gamma through shared memory
+#endif
 #ifndef LANE_G_MID
 #define LANE_G_MID 4         // lanes sharing the xi accumulator rows for 9 <= N <= 12
 #endif
@@ -400,6 +413,10 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
         int t = t0 - maxpre + s;
         if (!have) return 0.0;
         t = min(max(t, tstart), tend - 1);
+#if LANE_OBS_PREFETCH
+        if (EM == EM_GAUSS) prefetch_l1(a.obs + trow + min(t + 16, tend - 1));
+        else prefetch_l1(a.sym + trow + min(t + 32, tend - 1));
+#endif
         if (EM == EM_GAUSS) return __ldg(a.obs + trow + t);
         return __longlong_as_double((long long)__ldg(a.sym + trow + t));
     };
@@ -521,6 +538,7 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
         const int rem = (cls == 1) ? tend - 2 - t : (cls == 2) ? t0 - 2 - t : (have && t < tstart) ? tstart - 1 - t : 0x7fffffff;
         const int run = 1 + __reduce_min_sync(FULL, rem);
         if (m1) {
+#pragma unroll kUnrollF
             for (int k = 0; k < run; ++k, ++s) step(BoolTag2<PATH_CHAIN>(), t0 - maxpre + s, next_raw(s), on);
         } else {
             for (int k = 0; k < run; ++k, ++s) step(BoolTag2<PATH_WARM>(), t0 - maxpre + s, next_raw(s), on);
@@ -599,6 +617,10 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
         int f = frame_of(s);
         if (!have) return 0.0;
         f = min(max(f, t0), T - 1);
+#if LANE_OBS_PREFETCH
+        if (EM == EM_GAUSS) prefetch_l1(a.obs + trow + max(f - 16, t0));
+        else prefetch_l1(a.sym + trow + max(f - 32, t0));
+#endif
         if (EM == EM_GAUSS) return __ldg(a.obs + trow + f);
         return __longlong_as_double((long long)__ldg(a.sym + trow + f));
     };
@@ -611,13 +633,46 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
     };
     double raw_next = 0.0;          // emission input of frame f+1
 
-    // statistics of one frame: lane q owns rows q*NH .. q*NH+NH-1 for every chain of its lane group
+    // statistics of one frame: lane q owns rows q*NH .. q*NH+NH-1 for every chain of its lane group.  The rows of u and
+    // gamma that the partner lanes need depend on the partner's q: picking them out of registers costs a chain of selects
+    // per value, so for G >= LANE_XCH_MIN_G they travel through shared memory instead (every lane stores its vectors
+    // blocked by owner, 16-byte units, and reads block q of its partners: dynamic addressing is free there); w and the
+    // observation, which every partner needs whole, stay on warp shuffles.
+    constexpr bool XCH = (G >= LANE_XCH_MIN_G);
+    constexpr int XU = NH;                       // 16-byte units per block: (u_0..u_NH-1, gamma_0..gamma_NH-1)
+    __shared__ double2 xch[XCH ? (LANE_THREADS / 32) * G * XU * 32 : 1];
+    double2* const xw = xch + (threadIdx.x >> 5) * (G * XU * 32);
     auto accumulate = [&](const double (&w)[N], const double (&u)[N], const double (&gam)[N], double o_f) {
+        if (XCH) {
+#pragma unroll
+            for (int blk = 0; blk < G; ++blk) {
+                double L[2 * NH];
+#pragma unroll
+                for (int ii = 0; ii < NH; ++ii) {
+                    L[ii] = (blk * NH + ii < N) ? u[(blk * NH + ii < N) ? blk * NH + ii : 0] : 0.0;
+                    L[NH + ii] = (blk * NH + ii < N) ? gam[(blk * NH + ii < N) ? blk * NH + ii : 0] : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < XU; ++k) xw[(blk * XU + k) * 32 + lane] = make_double2(L[2 * k], L[2 * k + 1]);
+            }
+            __syncwarp();
+        }
 #pragma unroll
         for (int d = 0; d < G; ++d) {
             double ur[NH], gr[NH];
             double od;
-            if (d == 0) {
+            if (XCH) {
+                double L[2 * NH];
+#pragma unroll
+                for (int k = 0; k < XU; ++k) {
+                    const double2 v = xw[(q * XU + k) * 32 + (lane ^ d)];
+                    L[2 * k] = v.x;
+                    L[2 * k + 1] = v.y;
+                }
+#pragma unroll
+                for (int ii = 0; ii < NH; ++ii) { ur[ii] = L[ii]; gr[ii] = L[NH + ii]; }
+                od = (d == 0) ? o_f : __shfl_xor_sync(FULL, o_f, d);
+            } else if (d == 0) {
 #pragma unroll
                 for (int ii = 0; ii < NH; ++ii) {
                     ur[ii] = pick_row<N, G, NH>(u, q, ii);
@@ -649,6 +704,7 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
                 }
             }
         }
+        if (XCH) __syncwarp();
     };
 
     // w = p o bt, b = A w
@@ -784,6 +840,7 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
         const int rem = (cls == 1) ? f - t0 - 1 : (cls == 2) ? f - e - 1 : (have && f > fs) ? f - fs - 1 : 0x7fffffff;
         const int run = 1 + __reduce_min_sync(FULL, rem);
         if (m1) {
+#pragma unroll kUnrollB
             for (int k = 0; k < run; ++k, ++s) step(BoolTag2<PATH_CHAIN>(), frame_of(s), next_raw(s), on);
         } else {
             for (int k = 0; k < run; ++k, ++s) step(BoolTag2<PATH_WARM>(), frame_of(s), next_raw(s), on);
