@@ -413,6 +413,9 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
         int t = t0 - maxpre + s;
         if (!have) return 0.0;
         t = min(max(t, tstart), tend - 1);
+#ifdef LANE_DEBUG_NOFETCH
+        return 0.37 + 1e-3 * (t & 1023);     // (timing experiment: no observation loads)
+#endif
 #if LANE_OBS_PREFETCH
         if (EM == EM_GAUSS) prefetch_l1(a.obs + trow + min(t + 16, tend - 1));
         else prefetch_l1(a.sym + trow + min(t + 32, tend - 1));
@@ -493,6 +496,9 @@ k_forward_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
                 for (int j = 0; j < N; ++j) dst[j] = al[j];
             } else {
                 double2* dst = il + ((long long)(t - t0) * NP2 << 5);
+#ifdef LANE_DEBUG_NOSTORE
+                if (al[0] == 1.2345e-200)      // (timing experiment: the stores are never executed)
+#endif
 #pragma unroll
                 for (int jp = 0; jp < NP2; ++jp)
                     __stcs(dst + (jp << 5), make_double2(al[2 * jp], (2 * jp + 1 < N) ? al[2 * jp + 1] : 0.0));

@@ -13,6 +13,8 @@ arithmetic happens in libbhmm_b200.so.  There is no CPU path.
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -104,6 +106,11 @@ class TrajectoryBatch(object):
     # -------------------------------------------------------------------------------------------- plumbing
     def _attach(self):
         nbytes = int(lib.bhmm_b200_batch_workspace_bytes(self._handle))
+        self.workspace_bytes = nbytes
+        if os.environ.get('BHMM_B200_OWN_WORKSPACE'):
+            # debugging aid (compute-sanitizer initcheck needs a fresh cudaMalloc): the library allocates its own arena
+            self._workspace = None
+            return
         self._workspace = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
         check(lib.bhmm_b200_batch_attach_workspace(self._handle, C.c_void_p(self._workspace.data_ptr()), nbytes))
         self.workspace_bytes = nbytes
