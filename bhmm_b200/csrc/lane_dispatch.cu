@@ -9,26 +9,24 @@ DECL(1) DECL(2) DECL(3) DECL(4) DECL(5) DECL(6) DECL(7) DECL(8) DECL(9) DECL(10)
 namespace {
 constexpr int LANE_THREADS = 64;   // must match lane_kernels.cuh
 
-// gamma0 = sum over the chains that start a trajectory of their gamma at frame 0.  Fixed partition of the chains
-// over 256 threads and a fixed tree: deterministic.
+// gamma0 = sum over the chains that start a trajectory of their gamma at frame 0.  One block per state; fixed partition
+// of the chains over 256 threads and a fixed tree: deterministic.
 __global__ void k_add_gamma0(Chains ch, int n_total, int N, const double* __restrict__ g0buf, double* __restrict__ stats)
 {
     __shared__ double red[256];
+    const int i = blockIdx.x;
     const int per = (n_total + 255) / 256;
     const int lo = threadIdx.x * per, hi = min(n_total, lo + per);
-    for (int i = 0; i < N; ++i) {
-        double s = 0.0;
-        for (int c = lo; c < hi; ++c)
-            if (ch.t0[c] == 0) s += g0buf[(long long)c * N + i];
-        red[threadIdx.x] = s;
-        __syncthreads();
-        for (int w = 128; w > 0; w >>= 1) {
-            if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) stats[1 + i] += red[0];
+    double s = 0.0;
+    for (int c = lo; c < hi; ++c)
+        if (ch.t0[c] == 0) s += g0buf[(long long)c * N + i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
         __syncthreads();
     }
+    if (threadIdx.x == 0) stats[1 + i] += red[0];
 }
 
 // sums[k] = sum over the partial rows of column k (fixed order): per-state sum o and sum o^2 of the sampled paths
@@ -69,7 +67,7 @@ int launch_lane(const LaneArgs& a, const LaneHostParams& hp, int N, int em, int 
 
 int launch_add_gamma0(const Chains& ch, int n_total, int N, const double* g0buf, double* stats, cudaStream_t st)
 {
-    k_add_gamma0<<<1, 256, 0, st>>>(ch, n_total, N, g0buf, stats);
+    k_add_gamma0<<<N, 256, 0, st>>>(ch, n_total, N, g0buf, stats);
     return BHMM_OK;
 }
 
