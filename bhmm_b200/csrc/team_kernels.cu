@@ -56,6 +56,31 @@ __device__ __forceinline__ bool team_any(bool pred, const TeamGeom& g)
     return __syncthreads_or(pred ? 1 : 0) != 0;
 }
 
+// ra = any(a), rb = any(b) over the caller's team, for predicates with b => a (one barrier in the common case)
+__device__ __forceinline__ void team_any2(bool a, bool b, const TeamGeom& g, bool& ra, bool& rb)
+{
+    if (blockDim.x == 32) {
+        const unsigned ba = __ballot_sync(0xffffffffu, a), bb = __ballot_sync(0xffffffffu, b);
+        ra = (ba & g.mask) != 0u;
+        rb = (bb & g.mask) != 0u;
+        return;
+    }
+    // (__syncthreads_or returns a truth value, not the OR of the operands; b implies a at both call sites, so the
+    // second barrier is only taken on the rare frames without any sizeable density)
+    rb = __syncthreads_or(b ? 1 : 0) != 0;
+    ra = rb ? true : (__syncthreads_or(a ? 1 : 0) != 0);
+}
+
+// A frame whose densities are ALL tiny (below 2^-500: an observation ~26 sigma away from every state) is lifted by
+// 2^600 before it enters the recursion.  The kernels keep alpha / beta unnormalised for one step (the division by the
+// previous frame's sum is folded into the next matvec), so two such frames in a row would otherwise multiply to an
+// underflow, and a single one would push the exchanged vector into the denormal range, where products lose their
+// digits; the reference normalises after every frame and is immune.  A uniform power of two changes nothing downstream
+// (alpha, beta, gamma, xi are ratios); the forward log-likelihood subtracts it again.
+#define TINY_P 0x1p-500
+#define LIFT_P 0x1p+600
+#define LIFT_LOG 415.88830833596718565          /* 600 ln 2 */
+
 __device__ __forceinline__ int block_max(int v)
 {
     if (blockDim.x == 32) return __reduce_max_sync(0xffffffffu, v);
@@ -165,10 +190,11 @@ __global__ void k_forward_team(const FwdArgs a)
             raw_next = fetch(s + 1);
             double p = 0.0;
             if (on && jv && !(init && mode == 2)) p = em_value<EM>(raw, mu, sigma);
-            if (EM != EM_POBS && a.em.ignore_outliers) {
-                const bool anynz = team_any(p != 0.0, g);
-                if (!anynz) p = 1.0;          // outputmodel.py:126-130
-            }
+            bool anynz, anybig;
+            team_any2(p != 0.0, p >= TINY_P, g, anynz, anybig);
+            if (EM != EM_POBS && a.em.ignore_outliers && !anynz) { p = 1.0; anybig = true; }   // outputmodel.py:126-130
+            const bool lifted = anynz && !anybig;
+            if (lifted) p *= LIFT_P;
             const double* xprev = xb + ((s + 1) & 1) * cpb * N + g.team * N;
             double* xcur = xb + (s & 1) * cpb * N + g.team * N;
             double av = 0.0;
@@ -197,7 +223,7 @@ __global__ void k_forward_team(const FwdArgs a)
                 const double outv = (csum != 0.0) ? av / csum : av;
                 if (t >= t0) {
                     if (a.alpha) a.alpha[(trow + t) * N + j] = outv;
-                    if (j == 0) ll += log(csum);
+                    if (j == 0) ll += lifted ? log(csum) - LIFT_LOG : log(csum);
                     if (t == tend - 1) a.hand_end[(long long)c * N + j] = outv;
                 } else if (t == t0 - 1) {
                     a.hand_used[(long long)c * N + j] = outv;
@@ -303,9 +329,11 @@ __global__ void k_backward_team(const BwdArgs a)
 
             double p = 0.0;
             if (on && jv && !isvirt) p = em_value<EM>(raw, mu, sigma);
-            if (EM != EM_POBS && a.em.ignore_outliers) {
-                const bool anynz = team_any(p != 0.0, g);
-                if (!anynz) p = 1.0;
+            {
+                bool anynz, anybig;
+                team_any2(p != 0.0, p >= TINY_P, g, anynz, anybig);
+                if (EM != EM_POBS && a.em.ignore_outliers && !anynz) { p = 1.0; anybig = true; }
+                if (anynz && !anybig) p *= LIFT_P;
             }
             // ---- exchange 1: (w_j, b_j) of frame f
             const int tm = WARP1 ? 0 : g.team;       // WARP1: the idle lanes (j >= N) read team 0's slab too

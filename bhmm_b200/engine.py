@@ -55,6 +55,8 @@ class TrajectoryBatch(object):
         frames per chain / warm-up frames of the time-chunked kernels; 0 = automatic.
     """
 
+    _shared = None      # a SubBatchedTrajectories owner lends its workspace to its groups
+
     def __init__(self, observations, nstates, device=None, chunk=0, warm=0):
         first = np.asarray(observations[0])
         host_dtype = np.int32 if np.issubdtype(first.dtype, np.integer) else np.float64
@@ -65,10 +67,11 @@ class TrajectoryBatch(object):
         self._setup(cat, lengths, nstates, device, chunk, warm)
 
     @classmethod
-    def from_concatenated(cls, rows, lengths, nstates, device=None, chunk=0, warm=0):
+    def from_concatenated(cls, rows, lengths, nstates, device=None, chunk=0, warm=0, _shared=None):
         """Build from one concatenated per-frame array (numpy, or a torch tensor that may already live on the GPU)
         and the list of trajectory lengths."""
         self = cls.__new__(cls)
+        self._shared = _shared
         self._setup(rows, lengths, nstates, device, chunk, warm)
         return self
 
@@ -107,6 +110,9 @@ class TrajectoryBatch(object):
     def _attach(self):
         nbytes = int(lib.bhmm_b200_batch_workspace_bytes(self._handle))
         self.workspace_bytes = nbytes
+        if self._shared is not None:
+            self._workspace = None          # lent by the owner right before every call (_borrow)
+            return
         if os.environ.get('BHMM_B200_OWN_WORKSPACE'):
             # debugging aid (compute-sanitizer initcheck needs a fresh cudaMalloc): the library allocates its own arena
             self._workspace = None
@@ -114,6 +120,12 @@ class TrajectoryBatch(object):
         self._workspace = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
         check(lib.bhmm_b200_batch_attach_workspace(self._handle, C.c_void_p(self._workspace.data_ptr()), nbytes))
         self.workspace_bytes = nbytes
+
+    def _borrow(self, workspace):
+        """(Re-)attach a workspace that other batches use in between: the chain tables are uploaded again."""
+        if workspace.numel() < self.workspace_bytes:
+            raise ValueError('shared workspace too small: %d < %d bytes' % (workspace.numel(), self.workspace_bytes))
+        check(lib.bhmm_b200_batch_attach_workspace(self._handle, C.c_void_p(workspace.data_ptr()), self.workspace_bytes))
 
     def replan(self, chunk=0, warm=0):
         """Change the time-chunking (frames per chain, warm-up frames) and re-carve the workspace."""
@@ -274,3 +286,224 @@ class TrajectoryBatch(object):
         c = counts.cpu().numpy()
         N = self.N
         return dict(C=c[:N * N].reshape(N, N).copy(), n0=c[N * N:N * N + N].copy(), count=c[N * N + N:].copy())
+
+
+class SubBatchedTrajectories(object):
+    """The interface of ``TrajectoryBatch`` for data sets whose forward variables do not fit the GPU at once.
+
+    The trajectories are cut into contiguous groups whose workspaces (forward variables, chain tables, partial
+    statistics) each fit ``max_workspace_bytes``; the groups run one after the other on ONE shared workspace and their
+    sufficient statistics / counts are added, which is exact because trajectories are independent given the model
+    (maximum_likelihood.py:383-385).  Observations of all groups stay resident.  A single trajectory that is too long
+    for the budget is an error (time-sharding of one trajectory is not implemented).
+    """
+
+    def __init__(self, observations, nstates, max_workspace_bytes, device=None, chunk=0, warm=0):
+        first = np.asarray(observations[0])
+        host_dtype = np.int32 if np.issubdtype(first.dtype, np.integer) else np.float64
+        lengths = [len(o) for o in observations]
+        cat = np.concatenate([np.asarray(o, dtype=host_dtype) for o in observations])
+        self._setup(cat, lengths, nstates, max_workspace_bytes, device, chunk, warm)
+
+    @classmethod
+    def from_concatenated(cls, rows, lengths, nstates, max_workspace_bytes, device=None, chunk=0, warm=0):
+        self = cls.__new__(cls)
+        self._setup(rows, lengths, nstates, max_workspace_bytes, device, chunk, warm)
+        return self
+
+    @staticmethod
+    def plan_groups(lengths, nstates, max_workspace_bytes, chunk=0, warm=0):
+        """Greedy contiguous grouping: [(first trajectory, one past the last), ...].  Uses the library's own workspace
+        formula (a batch handle is created, asked for its size and destroyed: host-side work only)."""
+        lengths = np.asarray(lengths, dtype=np.int64)
+
+        def need(a, b):
+            offs = np.zeros(b - a + 1, dtype=np.int64)
+            np.cumsum(lengths[a:b], out=offs[1:])
+            h = C.c_void_p()
+            check(lib.bhmm_b200_batch_create(C.byref(h), offs.ctypes.data_as(C.POINTER(C.c_longlong)), b - a,
+                                             int(nstates), int(chunk), int(warm)))
+            n = int(lib.bhmm_b200_batch_workspace_bytes(h))
+            lib.bhmm_b200_batch_destroy(h)
+            return n
+
+        K = len(lengths)
+        groups, a = [], 0
+        while a < K:
+            if need(a, a + 1) > max_workspace_bytes:
+                raise MemoryError('trajectory %d (%d frames, %d states) needs %d bytes of workspace, more than the '
+                                  'budget of %d' % (a, lengths[a], nstates, need(a, a + 1), max_workspace_bytes))
+            lo, hi = a + 1, K                    # largest b in [lo, hi] with need(a, b) <= budget (need is monotone)
+            while lo < hi:
+                mid = (lo + hi + 1) // 2
+                if need(a, mid) <= max_workspace_bytes:
+                    lo = mid
+                else:
+                    hi = mid - 1
+            groups.append((a, lo))
+            a = lo
+        return groups
+
+    def _setup(self, cat, lengths, nstates, max_workspace_bytes, device, chunk, warm):
+        torch = _torch()
+        self.torch = torch
+        self.N = int(nstates)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lengths = np.asarray(lengths, dtype=np.int64)
+        if len(self.lengths) == 0 or np.any(self.lengths <= 0):
+            raise ValueError('every trajectory needs at least one frame')
+        self.K = len(self.lengths)
+        self.offsets = np.zeros(self.K + 1, dtype=np.int64)
+        np.cumsum(self.lengths, out=self.offsets[1:])
+        self.rows = int(self.offsets[-1])
+        if not torch.is_tensor(cat):
+            cat = torch.from_numpy(np.ascontiguousarray(cat))
+        self.discrete = not cat.dtype.is_floating_point
+        self.obs = cat.to(device=self.device, dtype=torch.int32 if self.discrete else torch.float64)
+        self.groups = self.plan_groups(self.lengths, self.N, int(max_workspace_bytes), chunk, warm)
+        self._workspace = None
+        self._subs = []
+        for a, b in self.groups:
+            lo, hi = int(self.offsets[a]), int(self.offsets[b])
+            sub = TrajectoryBatch.from_concatenated(self.obs[lo:hi], self.lengths[a:b], self.N, device=self.device,
+                                                    chunk=chunk, warm=warm, _shared=self)
+            sub.obs = self.obs[lo:hi]            # a view: the observations are stored once
+            self._subs.append((lo, hi, sub))
+        self.workspace_bytes = max(sub.workspace_bytes for _, _, sub in self._subs)
+        self._workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+        self._stats = torch.zeros(lib.bhmm_b200_stats_len_gaussian(self.N), dtype=torch.float64, device=self.device)
+        self._path = None
+
+    # ---- plumbing
+    def close(self):
+        for _, _, sub in getattr(self, '_subs', []):
+            sub.close()
+        self._subs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _each(self):
+        for lo, hi, sub in self._subs:
+            sub._borrow(self._workspace)
+            yield lo, hi, sub
+
+    def info(self):
+        infos = [sub.info() for _, _, sub in self._subs]
+        out = dict(groups=len(infos))
+        for key in ('chains', 'fixups_fwd', 'fixups_bwd', 'rerun'):
+            out[key] = int(sum(i[key] for i in infos))
+        for key in ('chunk', 'warm'):
+            out[key] = int(max(i[key] for i in infos))
+        for key in ('worst_fwd', 'worst_bwd'):
+            out[key] = float(max(i[key] for i in infos))
+        return out
+
+    @property
+    def uses_lane_kernels(self):
+        return self._subs[0][2].uses_lane_kernels
+
+    def set_profiling(self, on=True):
+        for _, _, sub in self._subs:
+            sub.set_profiling(on)
+
+    def kernel_ms(self):
+        out = dict(forward=0.0, backward_stats=0.0, span=0.0)
+        for _, _, sub in self._subs:
+            for k, v in sub.kernel_ms().items():
+                out[k] += v
+        return out
+
+    def set_observations(self, host_array, non_blocking=True):
+        self.obs.copy_(host_array, non_blocking=non_blocking)
+
+    def split(self, flat):
+        return [flat[self.offsets[k]:self.offsets[k + 1]] for k in range(self.K)]
+
+    def unpack_counts(self, counts):
+        c = counts.cpu().numpy()
+        N = self.N
+        return dict(C=c[:N * N].reshape(N, N).copy(), n0=c[N * N:N * N + N].copy(), count=c[N * N + N:].copy())
+
+    def _path_views(self):
+        if self._path is None:
+            self._path = self.torch.zeros(self.rows, dtype=self.torch.int32, device=self.device)
+            for lo, hi, sub in self._subs:
+                sub._path = self._path[lo:hi]
+        return self._path
+
+    # ---- the operations: run every group, add what is additive
+    def estep_gaussian(self, A, pi, means, sigmas, ignore_outliers=True, gamma_out=None):
+        self._stats.zero_()
+        for lo, hi, sub in self._each():
+            g = gamma_out[lo:hi] if gamma_out is not None else None
+            self._stats += sub.estep_gaussian(A, pi, means, sigmas, ignore_outliers=ignore_outliers, gamma_out=g)
+        return self._stats
+
+    def estep_discrete(self, A, pi, B, ignore_outliers=False, gamma_out=None):
+        self._stats.zero_()
+        Bnum = None
+        for lo, hi, sub in self._each():
+            g = gamma_out[lo:hi] if gamma_out is not None else None
+            st, bn = sub.estep_discrete(A, pi, B, ignore_outliers=ignore_outliers, gamma_out=g)
+            self._stats += st
+            Bnum = bn.clone() if Bnum is None else Bnum.add_(bn)
+        return self._stats, Bnum
+
+    def viterbi_gaussian(self, A, pi, means, sigmas, ignore_outliers=True):
+        path = self._path_views()
+        for lo, hi, sub in self._each():
+            sub.viterbi_gaussian(A, pi, means, sigmas, ignore_outliers=ignore_outliers)
+        return path
+
+    def viterbi_discrete(self, A, pi, B, ignore_outliers=False):
+        path = self._path_views()
+        for lo, hi, sub in self._each():
+            sub.viterbi_discrete(A, pi, B, ignore_outliers=ignore_outliers)
+        return path
+
+    def gibbs_gaussian(self, A, pi, means, sigmas, seed=0, sweep=0, uniforms=None, ignore_outliers=True):
+        path = self._path_views()
+        counts = sums = None
+        ll = 0.0
+        for k, (lo, hi, sub) in enumerate(self._each()):
+            u = uniforms[lo:hi] if uniforms is not None else None
+            # Philox is keyed by (seed, sweep, row within the group): give every group its own stream
+            _, c, s, l = sub.gibbs_gaussian(A, pi, means, sigmas, seed=int(seed) + 7919 * k, sweep=sweep, uniforms=u,
+                                            ignore_outliers=ignore_outliers)
+            counts = c.clone() if counts is None else counts.add_(c)
+            sums = s.clone() if sums is None else sums.add_(s)
+            ll += l
+        return path, counts, sums, ll
+
+    def gibbs_discrete(self, A, pi, B, seed=0, sweep=0, uniforms=None, ignore_outliers=False):
+        path = self._path_views()
+        counts = hist = None
+        ll = 0.0
+        for k, (lo, hi, sub) in enumerate(self._each()):
+            u = uniforms[lo:hi] if uniforms is not None else None
+            _, c, h, l = sub.gibbs_discrete(A, pi, B, seed=int(seed) + 7919 * k, sweep=sweep, uniforms=u,
+                                            ignore_outliers=ignore_outliers)
+            counts = c.clone() if counts is None else counts.add_(c)
+            hist = h.clone() if hist is None else hist.add_(h)
+            ll += l
+        return path, counts, hist, ll
+
+
+def make_batch(observations, nstates, device=None, chunk=0, warm=0, max_workspace_bytes=None):
+    """A ``TrajectoryBatch`` when its workspace fits ``max_workspace_bytes`` (default: 80 % of the free device memory),
+    otherwise a ``SubBatchedTrajectories`` over groups of trajectories."""
+    torch = _torch()
+    if max_workspace_bytes is None:
+        with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+            max_workspace_bytes = int(0.8 * torch.cuda.mem_get_info()[0])
+    lengths = [len(o) for o in observations]
+    if len(lengths) == 0 or min(lengths) <= 0:
+        raise ValueError('every trajectory needs at least one frame')
+    groups = SubBatchedTrajectories.plan_groups(lengths, nstates, int(max_workspace_bytes), chunk, warm)
+    if len(groups) == 1:
+        return TrajectoryBatch(observations, nstates, device=device, chunk=chunk, warm=warm)
+    return SubBatchedTrajectories(observations, nstates, int(max_workspace_bytes), device=device, chunk=chunk, warm=warm)

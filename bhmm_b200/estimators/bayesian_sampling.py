@@ -16,7 +16,7 @@ import time
 import numpy as np
 
 from .. import dist
-from ..engine import TrajectoryBatch
+from ..engine import TrajectoryBatch, make_batch
 from ..util import config
 from ..util.logger import logger
 from ..util import tmatrix as _tmatrix
@@ -74,7 +74,7 @@ class BayesianHMMSampler(object):
             raise ValueError('transition matrix prior mode undefined: ' + str(transition_matrix_prior))
         self.transition_matrix_sampling_steps = transition_matrix_sampling_steps
         self.model.output_model.set_implementation(config.kernel)
-        self._batch = TrajectoryBatch(self.observations, nstates, chunk=chunk, warm=warm) if self.nobs else None
+        self._batch = make_batch(self.observations, nstates, chunk=chunk, warm=warm) if self.nobs else None
         self._sweep = 0
         self._seed = 0
         self.timings = {'hidden': 0.0, 'parameters': 0.0}

@@ -13,7 +13,7 @@ import time
 import numpy as np
 
 from .. import dist
-from ..engine import TrajectoryBatch, unpack_stats
+from ..engine import TrajectoryBatch, make_batch, unpack_stats
 from ..util import config
 from ..util.logger import logger
 from ..util import tmatrix as _tmatrix
@@ -60,7 +60,7 @@ class MaximumLikelihoodEstimator(object):
         self._maxit = maxit
         self._maxit_P = maxit_P
         self._likelihoods = None
-        self._batch = TrajectoryBatch(self._observations, nstates, chunk=chunk, warm=warm) if self._nobs else None
+        self._batch = make_batch(self._observations, nstates, chunk=chunk, warm=warm) if self._nobs else None
         self._hmm.output_model.set_implementation(config.kernel)
         self.count_matrix = None
         self.initial_count = None

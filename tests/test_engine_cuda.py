@@ -299,3 +299,114 @@ def test_lane_family_extremes(eng, oracle_port, N):
     ref_stats = oracle_port.path_stats(batch.split(path.cpu().numpy()), obs, N)
     assert np.array_equal(batch.unpack_counts(counts)['C'], ref_stats['C'])
     batch.close()
+
+
+@pytest.mark.parametrize('case', ['sharp', 'broad', 'mixed', 'denormal_band'])
+def test_scaling_and_tail_extremes(eng, oracle_port, case):
+    """The lane kernels rescale alpha/beta lazily (powers of two, only when the largest component leaves a band) and
+    treat far-tail densities specially (exactly zero below exp(-746), library exp in the denormal band).  Long
+    trajectories whose likelihood per frame is far from one in either direction, and observations placed so that every
+    density of a frame is denormal, must still give the oracle's statistics."""
+    rng = np.random.default_rng(7)
+    N = 4
+    X = rng.random((N, N)) + 0.05
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    if case == 'sharp':            # densities up to 4e5 per frame: the scaled vectors grow by 2^18 per step
+        means, sigmas = np.array([-3e-6, -1e-6, 1e-6, 3e-6]), np.full(N, 1e-6)
+    elif case == 'broad':          # densities of 4e-7 per frame: they shrink by 2^-21 per step
+        means, sigmas = np.array([-3e6, -1e6, 1e6, 3e6]), np.full(N, 1e6)
+    else:
+        means, sigmas = np.array([-3.0, -1.0, 1.0, 3.0]), np.array([1e-3, 0.5, 1.0, 20.0])
+    obs = []
+    for T in (6000, 2500):
+        s = rng.integers(0, N, size=T)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    if case == 'denormal_band':
+        # |o - mu| / sigma of 37.8 .. 38.4 for the broadest state and more for the others: every density of the frame
+        # is denormal or zero, none of the frames is an "outlier" (the row is not all zero)
+        obs[0][1234] = 3.0 + 20.0 * 38.0
+        obs[0][1235] = 3.0 - 20.0 * 38.3
+        obs[1][77] = 3.0 + 20.0 * 37.7
+    batch = eng.TrajectoryBatch(obs, N, chunk=500, warm=64)
+    st = eng.unpack_stats(batch.estep_gaussian(A, pi, means, sigmas).cpu().numpy(), N)
+    ref, wd, wdd = oracle_stats_gaussian(oracle_port, obs, A, pi, means, sigmas)
+    assert np.isfinite(ref['loglik'])
+    if case == 'denormal_band':
+        # A denormal density carries only a few significant bits and exp() rounds differently into that range on the
+        # CPU and on the GPU (both are within one unit of the last -- denormal -- place), so the three frames can only
+        # agree to a few per cent each.  What the test pins is the semantics: the frames are neither dropped (outlier
+        # rule) nor fatal (-inf), which would move the log-likelihood by hundreds.
+        assert abs(st['loglik'] - ref['loglik']) < 0.5
+        np.testing.assert_allclose(st['C'], ref['C'], atol=3.0)
+        np.testing.assert_allclose(st['wsum'], ref['wsum'], atol=3.0)
+    else:
+        assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])
+        np.testing.assert_allclose(st['gamma0'], ref['gamma0'], rtol=1e-9, atol=1e-300)
+        np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9, atol=1e-9 * ref['C'].max())
+        np.testing.assert_allclose(st['wsum'], ref['wsum'], rtol=1e-9, atol=1e-9 * ref['wsum'].max())
+        np.testing.assert_allclose(st['wdd'], wdd, rtol=1e-8, atol=1e-9 * np.abs(wdd).max())
+    assert abs(st['C'].sum() - sum(len(o) - 1 for o in obs)) < 1e-6
+    path, counts, sums, ll = batch.gibbs_gaussian(A, pi, means, sigmas, seed=11, sweep=0)
+    assert abs(ll - st['loglik']) <= RTOL * abs(ref['loglik'])
+    batch.close()
+
+
+def test_lane_kernels_reject_degenerate_sigma(eng, family):
+    """sigma below 1e-100 could overflow the lane kernels' scaling band: refused with an error, never a wrong result."""
+    if family != 'lane':
+        pytest.skip('lane-family guard')
+    obs = [np.zeros(50)]
+    batch = eng.TrajectoryBatch(obs, 2)
+    with pytest.raises(Exception):
+        batch.estep_gaussian(np.full((2, 2), 0.5), np.full(2, 0.5), np.zeros(2), np.array([1e-120, 1.0]))
+    batch.close()
+
+
+def test_sub_batched_trajectories_match_single_batch(eng, oracle_port):
+    """Groups of trajectories run one after the other on a shared, budgeted workspace: statistics add up to those of
+    the single batch (and the oracle), Viterbi paths and Gibbs paths for given uniforms are identical."""
+    import torch
+    rng = np.random.default_rng(21)
+    N = 6
+    X = rng.random((N, N)) + 0.05
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    means, sigmas = np.linspace(-5, 5, N), np.linspace(0.6, 1.4, N)
+    lengths = [15000, 400, 22000, 9000, 1, 31000, 7000, 13000]
+    obs = []
+    for T in lengths:
+        s = rng.integers(0, N, size=T)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    one = eng.TrajectoryBatch(obs, N, chunk=256, warm=64)
+    budget = int(0.45 * one.workspace_bytes)
+    many = eng.SubBatchedTrajectories(obs, N, budget, chunk=256, warm=64)
+    assert len(many.groups) >= 3 and many.workspace_bytes <= budget
+    assert many.groups[0][0] == 0 and many.groups[-1][1] == len(lengths)
+    assert all(a[1] == b[0] for a, b in zip(many.groups, many.groups[1:]))
+    s1 = one.estep_gaussian(A, pi, means, sigmas).cpu().numpy()
+    s2 = many.estep_gaussian(A, pi, means, sigmas).cpu().numpy()
+    np.testing.assert_allclose(s2, s1, rtol=1e-11, atol=1e-11)
+    ref, wd, wdd = oracle_stats_gaussian(oracle_port, obs, A, pi, means, sigmas)
+    st = eng.unpack_stats(s2, N)
+    assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9, atol=1e-12)
+    # a second E-step re-borrows the workspace and gives the same answer
+    np.testing.assert_allclose(many.estep_gaussian(A, pi, means, sigmas).cpu().numpy(), s2, rtol=1e-12, atol=1e-12)
+    p1 = one.viterbi_gaussian(A, pi, means, sigmas).cpu().numpy()
+    p2 = many.viterbi_gaussian(A, pi, means, sigmas).cpu().numpy()
+    assert np.array_equal(p1, p2)
+    u = torch.rand(sum(lengths), dtype=torch.float64, device='cuda')
+    g1 = one.gibbs_gaussian(A, pi, means, sigmas, uniforms=u)
+    g2 = many.gibbs_gaussian(A, pi, means, sigmas, uniforms=u)
+    assert np.array_equal(g1[0].cpu().numpy(), g2[0].cpu().numpy())
+    assert np.array_equal(g1[1].cpu().numpy(), g2[1].cpu().numpy())
+    np.testing.assert_allclose(g2[2].cpu().numpy(), g1[2].cpu().numpy(), rtol=1e-12)
+    assert abs(g1[3] - g2[3]) <= 1e-11 * abs(g1[3])
+    # make_batch picks the plain batch when everything fits
+    assert isinstance(eng.make_batch(obs, N), eng.TrajectoryBatch)
+    assert isinstance(eng.make_batch(obs, N, chunk=256, warm=64, max_workspace_bytes=budget), eng.SubBatchedTrajectories)
+    with pytest.raises(MemoryError):
+        eng.SubBatchedTrajectories(obs, N, 1000)
+    one.close()
+    many.close()
