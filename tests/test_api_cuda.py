@@ -1,0 +1,67 @@
+"""End to end through the reference's user entry points (bhmm/api.py:309-470) on the GPU engine: estimate_hmm without an
+initial model (from-scratch heuristic + Baum-Welch), bayesian_hmm on top of it."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _sample(A, means, sigmas, lengths, seed):
+    rng = np.random.default_rng(seed)
+    N = len(means)
+    cum = np.cumsum(A, axis=1)
+    obs = []
+    for T in lengths:
+        s = np.empty(T, dtype=np.int64)
+        s[0] = rng.integers(0, N)
+        u = rng.random(T)
+        for t in range(1, T):
+            s[t] = min(int(np.searchsorted(cum[s[t - 1]], u[t])), N - 1)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    return obs
+
+
+def test_estimate_hmm_and_bayesian_hmm_gaussian():
+    import bhmm_b200
+    A = np.array([[0.97, 0.02, 0.01], [0.03, 0.94, 0.03], [0.01, 0.04, 0.95]])
+    means, sigmas = np.array([-3.0, 0.0, 3.5]), np.array([0.8, 1.0, 0.6])
+    obs = _sample(A, means, sigmas, [5000, 4000, 6000, 3000], 1)
+    hmm = bhmm_b200.estimate_hmm(obs, 3, reversible=False, accuracy=1e-4, maxit=200)
+    order = np.argsort(hmm.output_model.means)
+    np.testing.assert_allclose(hmm.output_model.means[order], means, atol=0.1)
+    np.testing.assert_allclose(hmm.output_model.sigmas[order], sigmas, rtol=0.1)
+    np.testing.assert_allclose(hmm.transition_matrix[np.ix_(order, order)], A, atol=0.02)
+    # lagged estimate: the transition matrix approximates A^2
+    hmm2 = bhmm_b200.estimate_hmm(obs, 3, lag=2, reversible=False, accuracy=1e-4, maxit=200)
+    o2 = np.argsort(hmm2.output_model.means)
+    np.testing.assert_allclose(hmm2.transition_matrix[np.ix_(o2, o2)], A.dot(A), atol=0.03)
+    assert hmm2._lag == 2
+    post = bhmm_b200.bayesian_hmm(obs, hmm, nsample=6, reversible=False)
+    assert post.nsamples == 6
+    tm = post.transition_matrix
+    assert tm['mean'].shape == (3, 3) and np.allclose(tm['samples'].sum(axis=2), 1.0)
+    np.testing.assert_allclose(tm['mean'][np.ix_(order, order)], A, atol=0.03)
+    np.testing.assert_allclose(post.means['mean'][order], means, atol=0.15)
+    with pytest.raises(NotImplementedError):
+        bhmm_b200.bayesian_hmm(obs, hmm, nsample=1, reversible=True)
+
+
+def test_estimate_hmm_discrete():
+    import bhmm_b200
+    rng = np.random.default_rng(8)
+    A = np.array([[0.96, 0.04], [0.05, 0.95]])
+    B = np.array([[0.5, 0.3, 0.15, 0.05, 0.0, 0.0], [0.0, 0.02, 0.08, 0.2, 0.3, 0.4]])
+    cum, cumB = np.cumsum(A, axis=1), np.cumsum(B, axis=1)
+    obs = []
+    for T in (8000, 6000):
+        s = np.empty(T, dtype=np.int64)
+        s[0] = 0
+        u, v = rng.random(T), rng.random(T)
+        for t in range(1, T):
+            s[t] = min(int(np.searchsorted(cum[s[t - 1]], u[t])), 1)
+        obs.append(np.array([min(int(np.searchsorted(cumB[k], x)), 5) for k, x in zip(s, v)], dtype=np.int64))
+    hmm = bhmm_b200.estimate_hmm(obs, 2, reversible=False, accuracy=1e-4, maxit=300)
+    Bh = hmm.output_model.output_probabilities
+    order = np.argsort(Bh.dot(np.arange(6)))
+    np.testing.assert_allclose(Bh[order], B, atol=0.03)
+    np.testing.assert_allclose(hmm.transition_matrix[np.ix_(order, order)], A, atol=0.02)
