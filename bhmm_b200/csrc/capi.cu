@@ -88,10 +88,10 @@ int auto_chunk(long long rows, int N, int warm)
     if (g_chunk_override > 0) return g_chunk_override;
     int threads, cpb;
     team_shape(N, &threads, &cpb);
-    int sms = 148;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long target = (long long)sms * 32 * cpb;            // chains that fill the machine once
+    // chains that fill the machine ONCE: resident blocks of the most demanding kernel (backward + statistics: two N x N
+    // shared-memory matrices, one or two blocks per SM at N = 100) times chains per block.  More chains than that run
+    // in rounds, and a last round that is mostly empty costs as much as a full one.
+    const long long target = (long long)backward_stats_grid(N, 1 << 28) * cpb;
     long long c = (rows + target - 1) / target;
     c = std::max<long long>(c, 2LL * warm);
     c = std::max<long long>(c, 64);

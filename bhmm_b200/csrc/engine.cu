@@ -119,12 +119,15 @@ void batch_plan(bhmm_b200_batch* b, int chunk, int warm)
 {
     const int w = warm > 0 ? warm : (b->lane ? auto_warm_lane(b->N) : auto_warm(b->N));
     b->chunk = chunk > 0 ? chunk : (b->lane ? auto_chunk_lane(b->rows, b->N, w) : auto_chunk(b->rows, b->N, w));
-    if (chunk <= 0 && b->lane) {
-        // the lane kernels run all chains in ONE wave of resident blocks: a few chains too many (every trajectory rounds
+    if (chunk <= 0) {
+        // the chain kernels run all chains in ONE wave of resident blocks: a few chains too many (every trajectory rounds
         // its chain count up) would double the kernel time, so lengthen the chunk until the count fits
         int sms = 148, dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const long long cap = (long long)sms * lane_blocks_per_sm(b->N, EM_GAUSS) * lane_threads();
+        int tthreads = 32, tcpb = 1;
+        team_shape(b->N, &tthreads, &tcpb);
+        const long long cap = b->lane ? (long long)sms * lane_blocks_per_sm(b->N, EM_GAUSS) * lane_threads()
+                                      : (long long)backward_stats_grid(b->N, 1 << 28) * tcpb;
         for (int it = 0; it < 200; ++it) {
             long long n = 0;
             for (int k = 0; k < b->K; ++k) n += (b->offsets[k + 1] - b->offsets[k] + b->chunk - 1) / b->chunk;

@@ -95,6 +95,31 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// Sums over a team's N shared-memory values with eight independent accumulators: a single running sum is a chain of N
+// dependent FP64 operations (8 cycles each), which at N = 100 was most of a frame's time.
+__device__ __forceinline__ double dot8(const double* __restrict__ x, int sx, const double* __restrict__ y, int sy, int N)
+{
+    double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int i = 0;
+    for (; i + 7 < N; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = fma(x[(i + k) * sx], y[(i + k) * sy], m[k]);
+    }
+    for (; i < N; ++i) m[0] = fma(x[i * sx], y[i * sy], m[0]);
+    return ((m[0] + m[1]) + (m[2] + m[3])) + ((m[4] + m[5]) + (m[6] + m[7]));
+}
+__device__ __forceinline__ double sum8(const double* __restrict__ x, int sx, int N)
+{
+    double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int i = 0;
+    for (; i + 7 < N; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] += x[(i + k) * sx];
+    }
+    for (; i < N; ++i) m[0] += x[i * sx];
+    return ((m[0] + m[1]) + (m[2] + m[3])) + ((m[4] + m[5]) + (m[6] + m[7]));
+}
+
 // Raw emission input of (row, state j): the table entry, the observation, or the symbol's B entry.
 template <int EM>
 __device__ __forceinline__ double em_load(const Emission& em, long long row, int j, int N)
@@ -208,7 +233,7 @@ __global__ void k_forward_team(const FwdArgs a)
                         for (int i = 0; i < 32; ++i)
                             if (i < N) m = fma(xprev[i], Acol[WARP1 ? i : 0], m);
                     } else {
-                        for (int i = 0; i < N; ++i) m = fma(xprev[i], A_s[i * N + j], m);
+                        m = dot8(xprev, 1, A_s + j, N, N);
                     }
                     if (cprev != 0.0) m /= cprev;
                     av = m * p;
@@ -218,7 +243,7 @@ __global__ void k_forward_team(const FwdArgs a)
             __syncthreads();
             double csum = 0.0;
             if (WARP1) csum = warp_sum(av);
-            else if (g.owns) for (int i = 0; i < N; ++i) csum += xcur[i];
+            else if (g.owns) csum = sum8(xcur, 1, N);
             if (on && jv) {
                 const double outv = (csum != 0.0) ? av / csum : av;
                 if (t >= t0) {
@@ -350,9 +375,9 @@ __global__ void k_backward_team(const BwdArgs a)
                 if (sb != 0.0) bnew /= sb;
                 if (!jv) bnew = 0.0;
             } else if (g.owns) {
-                for (int i = 0; i < N; ++i) sb += x1[2 * i + 1];
+                sb = sum8(x1 + 1, 2, N);
                 if (jv) {
-                    for (int i = 0; i < N; ++i) bnew = fma(At_s[i * N + j], x1[2 * i], bnew);   // sum_i' A[j][i'] w_i'
+                    bnew = dot8(At_s + j, N, x1, 2, N);                                         // sum_i' A[j][i'] w_i'
                     if (sb != 0.0) bnew /= sb;
                 }
             }
@@ -379,7 +404,8 @@ __global__ void k_backward_team(const BwdArgs a)
                 }
                 if (g.owns) {
                     if (!WARP1) {
-                        for (int i = 0; i < N; ++i) { S += x2[3 * i]; sbn += x2[3 * i + 2]; }
+                        S = sum8(x2, 3, N);
+                        sbn = sum8(x2 + 2, 3, N);
                     }
                     if (emit && jv) {
                         const long long row = trow + (f - 1);
@@ -393,8 +419,18 @@ __global__ void k_backward_team(const BwdArgs a)
                                 for (int i = 0; i < 32; ++i)
                                     if (i < N) Ccol[(WARP1 && STATS) ? i : 0] = fma(x2[3 * i + 1], wn, Ccol[(WARP1 && STATS) ? i : 0]);
                             } else {
-                                double* Cc = Cacc + g.team * N * N;
-                                for (int i = 0; i < N; ++i) Cc[i * N + j] = fma(x2[3 * i + 1], wn, Cc[i * N + j]);
+                                // column j of the team's xi accumulator: eight read-modify-writes in flight at a time
+                                // (a rolled loop exposes the shared-memory round trip of every single one)
+                                double* Cc = Cacc + g.team * N * N + j;
+                                int i = 0;
+                                for (; i + 7 < N; i += 8) {
+                                    double cv[8], xv[8];
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) { cv[k] = Cc[(i + k) * N]; xv[k] = x2[3 * (i + k) + 1]; }
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) Cc[(i + k) * N] = fma(xv[k], wn, cv[k]);
+                                }
+                                for (; i < N; ++i) Cc[i * N] = fma(x2[3 * i + 1], wn, Cc[i * N]);
                             }
                         }
                         const double gam = g_own / S;
