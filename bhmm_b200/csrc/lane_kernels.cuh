@@ -31,19 +31,14 @@ namespace {
 constexpr int LANE_THREADS = 64;
 constexpr unsigned FULL = 0xffffffffu;
 
-// build-time tunables (tools/build_variants.py sweeps them on the GPU box)
+// build-time tunables (python bhmm_b200/build.py --name=v_x -DLANE_...=... builds a variant library next to the default
+// one; tools/lane_sweep.py with BHMM_B200_LIB=<variant> times it on the GPU box)
 #ifndef LANE_MINB_F
 #define LANE_MINB_F 4        // minimum resident blocks per SM asked of the compiler, forward kernel
 #endif
 #ifndef LANE_MINB_B
 #define LANE_MINB_B 4        // ... backward + statistics kernel
 #endif
-#ifndef LANE_ALPHA_MODE
-#define LANE_ALPHA_MODE 1    // backward kernel's read of the forward variables: 0 = streaming load + prefetch.global.L1
-#endif                       // of the next frame, 1 = plain load + prefetch, 2 = loaded one frame ahead into registers
-#ifndef LANE_PIPE_EMIS
-#define LANE_PIPE_EMIS 0     // emission of the NEXT frame is evaluated during the current step (independent work that
-#endif                       // fills the latency of the step's dependent chain: sums, reciprocals)
 #ifndef LANE_FOLD_NRM
 #define LANE_FOLD_NRM 1      // Gaussian normalisation constant folded into the exponent's argument (one FMA less per state)
 #endif
@@ -52,8 +47,8 @@ constexpr unsigned FULL = 0xffffffffu;
 #endif                       //    (LDS broadcast) instead of the uniform datapath (LDCU / R2UR), whose 63 registers thrash
                              // 2: emission constants from shared memory, transition matrix through the uniform datapath
 #ifndef LANE_KEEP_F
-#define LANE_KEEP_F 40       // forward kernel: this many entries of A stay in registers for the whole kernel (shared-
-#endif                       // memory -> register bandwidth, 8 B per lane and operand, is what bounds the lane kernels)
+#define LANE_KEEP_F 40       // forward kernel: this many entries of A stay in registers for the whole kernel, the rest comes
+#endif                       // from shared memory every step (30 .. 60 measure the same at N = 10)
 #ifndef LANE_EXP_TABLE
 #define LANE_EXP_TABLE 1     // exp() of the Gaussian emission: 0 = degree-11 polynomial on |r| <= ln2/2; 1 = 32-entry table of
 #endif                       // 2^(j/32) in shared memory + degree-5 polynomial on |r| <= ln2/64 (6 FP64 instructions less
