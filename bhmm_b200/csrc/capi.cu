@@ -57,18 +57,23 @@ void Arena::release()
     cap = 0;
 }
 
-void build_plan(const long long* offsets, int K, int chunk, HostPlan& p)
+void build_plan(const long long* offsets, int K, int chunk, HostPlan& p, const long long* own_lo, const long long* own_hi)
 {
     p.row0.clear(); p.len.clear(); p.t0.clear(); p.T.clear();
+    p.first_chain.assign(K, -1); p.last_chain.assign(K, -1);
     p.maxT = 0;
     p.chunked = false;
     for (int k = 0; k < K; ++k) {
         const long long r0 = offsets[k];
         const int T = (int)(offsets[k + 1] - r0);
         p.maxT = std::max(p.maxT, T);
-        for (int t0 = 0; t0 < T; t0 += chunk) {
+        const int lo = own_lo ? (int)std::max<long long>(0, own_lo[k]) : 0;
+        const int hi = own_hi ? (int)std::min<long long>(T, own_hi[k]) : T;
+        for (int t0 = lo; t0 < hi; t0 += chunk) {
+            if (p.first_chain[k] < 0) p.first_chain[k] = (int)p.row0.size();
+            p.last_chain[k] = (int)p.row0.size();
             p.row0.push_back(r0 + t0);
-            p.len.push_back(std::min(chunk, T - t0));
+            p.len.push_back(std::min(chunk, hi - t0));
             p.t0.push_back(t0);
             p.T.push_back(T);
             if (t0 > 0) p.chunked = true;

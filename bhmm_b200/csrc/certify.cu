@@ -26,9 +26,13 @@ __global__ void k_certify(Chains ch, int n_total, int N, int dir, const double* 
     if (dir > 0) {
         if (ch.t0[c] == 0) return;             // starts its trajectory: exact by construction
         nb = c - 1;
+        // first chain of an owned range (time-sharded trajectory): its neighbour lives on another shard, the
+        // hand-over is certified there (bhmm_b200_batch_border_handovers)
+        if (c == 0 || ch.row0[nb] + ch.len[nb] != ch.row0[c]) return;
     } else {
         if (ch.t0[c] + ch.len[c] >= ch.T[c]) return;   // ends its trajectory: exact by construction
         nb = c + 1;
+        if (nb >= n_total || ch.row0[c] + ch.len[c] != ch.row0[nb]) return;
     }
     const double* u = hand_used + (long long)c * N;
     const double* v = hand_end + (long long)nb * N;

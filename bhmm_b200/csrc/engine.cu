@@ -33,6 +33,7 @@ struct bhmm_b200_batch {
     double* d_pi = nullptr;
     double* d_mu = nullptr;
     double* d_sigma = nullptr;
+    std::vector<long long> own_lo, own_hi;   // owned frame range per trajectory (empty: whole trajectories)
     double* d_alpha = nullptr;
     unsigned char* d_F = nullptr;
     double* d_partials = nullptr;
@@ -130,14 +131,18 @@ void batch_plan(bhmm_b200_batch* b, int chunk, int warm)
                                       : (long long)backward_stats_grid(b->N, 1 << 28) * tcpb;
         for (int it = 0; it < 200; ++it) {
             long long n = 0;
-            for (int k = 0; k < b->K; ++k) n += (b->offsets[k + 1] - b->offsets[k] + b->chunk - 1) / b->chunk;
+            for (int k = 0; k < b->K; ++k) {
+                const long long own = b->own_lo.empty() ? b->offsets[k + 1] - b->offsets[k] : b->own_hi[k] - b->own_lo[k];
+                n += (own + b->chunk - 1) / b->chunk;
+            }
             if (n <= cap || b->chunk >= (1 << 30)) break;
             b->chunk = (int)std::min<long long>((long long)b->chunk + std::max(1, b->chunk / 100), 1 << 30);
         }
     }
     b->warm_f = b->warm_b = w;
     b->warm_min = warm > 0 ? warm : 32;       // an explicit warm-up length is a floor for the adaptation
-    build_plan(b->offsets.data(), b->K, b->chunk, b->plan);
+    build_plan(b->offsets.data(), b->K, b->chunk, b->plan, b->own_lo.empty() ? nullptr : b->own_lo.data(),
+               b->own_hi.empty() ? nullptr : b->own_hi.data());
     build_plan(b->offsets.data(), b->K, SEG_FRAMES, b->segplan);
     b->carved = false;
 }
@@ -266,6 +271,7 @@ int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
                  double* loglik_host, cudaStream_t st)
 {
     const int N = b->N;
+    if (!b->own_lo.empty()) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "hidden-path sampling needs whole trajectories (batch has owned ranges)"); return BHMM_ERR_UNSUPPORTED; }
     if (N > 256) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "sampling supports N <= 256"); return BHMM_ERR_UNSUPPORTED; }
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
@@ -331,8 +337,8 @@ int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
 extern "C" int bhmm_b200_stats_len_gaussian(int N) { return 1 + N + N * N + 3 * N; }
 extern "C" int bhmm_b200_stats_len_discrete(int N) { return 1 + N + N * N + 3 * N; }
 
-extern "C" int bhmm_b200_batch_create(bhmm_b200_batch** out, const long long* offsets, int K, int N, int chunk,
-                                      int warm)
+extern "C" int bhmm_b200_batch_create_ranges(bhmm_b200_batch** out, const long long* offsets, const long long* own_lo,
+                                             const long long* own_hi, int K, int N, int chunk, int warm)
 {
     bhmm_set_error(BHMM_OK, "");
     if (!out || !offsets || K < 1 || N < 1 || N > 1024) { bhmm_set_error(BHMM_ERR_INVALID, "bad batch arguments"); return BHMM_ERR_INVALID; }
@@ -354,6 +360,18 @@ extern "C" int bhmm_b200_batch_create(bhmm_b200_batch** out, const long long* of
         b->lane = lane_supported(N, EM_GAUSS) && !(fam && strcmp(fam, "team") == 0);
     }
     b->offsets.assign(offsets, offsets + K + 1);
+    if (own_lo && own_hi) {
+        for (int k = 0; k < K; ++k) {
+            const long long T = offsets[k + 1] - offsets[k];
+            if (own_lo[k] < 0 || own_hi[k] > T || own_lo[k] > own_hi[k]) {
+                delete b;
+                bhmm_set_error(BHMM_ERR_INVALID, "owned range outside its trajectory");
+                return BHMM_ERR_INVALID;
+            }
+        }
+        b->own_lo.assign(own_lo, own_lo + K);
+        b->own_hi.assign(own_hi, own_hi + K);
+    }
     b->rows = offsets[K] - offsets[0];
     if (offsets[0] != 0) { delete b; bhmm_set_error(BHMM_ERR_INVALID, "offsets[0] must be 0"); return BHMM_ERR_INVALID; }
     batch_plan(b, chunk, warm);
@@ -368,6 +386,25 @@ extern "C" void bhmm_b200_batch_destroy(bhmm_b200_batch* b)
     b->disc.release();
     for (int k = 0; k < 4; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
     delete b;
+}
+
+extern "C" int bhmm_b200_batch_create(bhmm_b200_batch** out, const long long* offsets, int K, int N, int chunk,
+                                      int warm)
+{
+    return bhmm_b200_batch_create_ranges(out, offsets, nullptr, nullptr, K, N, chunk, warm);
+}
+
+extern "C" int bhmm_b200_batch_border_handovers(const bhmm_b200_batch* b, int k, double* out)
+{
+    if (!b || !out || k < 0 || k >= b->K || !b->carved) { bhmm_set_error(BHMM_ERR_INVALID, "border_handovers: bad arguments or no E-step yet"); return BHMM_ERR_INVALID; }
+    const int N = b->N, cf = b->plan.first_chain[k], cl = b->plan.last_chain[k];
+    for (int i = 0; i < 4 * N; ++i) out[i] = 0.0;
+    if (cf < 0) return BHMM_OK;                       // no owned frames in this trajectory
+    const double* src[4] = {b->w.hu_f + (size_t)cf * N, b->w.he_f + (size_t)cl * N, b->w.hu_b + (size_t)cl * N,
+                            b->w.he_b + (size_t)cf * N};
+    for (int q = 0; q < 4; ++q)
+        CUDA_TRY(cudaMemcpy(out + q * N, src[q], sizeof(double) * N, cudaMemcpyDeviceToHost));
+    return BHMM_OK;
 }
 
 extern "C" int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm)
@@ -455,6 +492,7 @@ static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const do
                           int* d_path, cudaStream_t st)
 {
     const int N = b->N;
+    if (!b->own_lo.empty()) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "Viterbi needs whole trajectories (batch has owned ranges)"); return BHMM_ERR_UNSUPPORTED; }
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     VitArgs a{};

@@ -47,8 +47,12 @@ struct HostPlan {
     int n = 0;
     int maxT = 0;
     bool chunked = false;       // some chain does not start its trajectory
+    std::vector<int> first_chain, last_chain;   // per trajectory: its first / last chain in the table (-1: none)
 };
-void build_plan(const long long* offsets, int K, int chunk, HostPlan& p);
+// Chains over the OWNED frame range [own_lo[k], own_hi[k]) of every trajectory (NULL: the whole trajectory).  Frames
+// outside the range are a halo: the chains next to the range's borders warm up on them (time-sharded trajectories).
+void build_plan(const long long* offsets, int K, int chunk, HostPlan& p, const long long* own_lo = nullptr,
+                const long long* own_hi = nullptr);
 int auto_warm(int N);
 int auto_chunk(long long rows, int N, int warm);
 

@@ -56,6 +56,7 @@ class TrajectoryBatch(object):
     """
 
     _shared = None      # a SubBatchedTrajectories owner lends its workspace to its groups
+    _own_ranges = None  # owned (lo, hi) frame range per trajectory, None: whole trajectories
 
     def __init__(self, observations, nstates, device=None, chunk=0, warm=0):
         first = np.asarray(observations[0])
@@ -67,11 +68,13 @@ class TrajectoryBatch(object):
         self._setup(cat, lengths, nstates, device, chunk, warm)
 
     @classmethod
-    def from_concatenated(cls, rows, lengths, nstates, device=None, chunk=0, warm=0, _shared=None):
+    def from_concatenated(cls, rows, lengths, nstates, device=None, chunk=0, warm=0, _shared=None, own_ranges=None):
         """Build from one concatenated per-frame array (numpy, or a torch tensor that may already live on the GPU)
-        and the list of trajectory lengths."""
+        and the list of trajectory lengths.  ``own_ranges``: optional list of (lo, hi) per trajectory -- only those
+        frames are owned (statistics, likelihood), the rest is halo (see ``TimeShardedTrajectories``)."""
         self = cls.__new__(cls)
         self._shared = _shared
+        self._own_ranges = own_ranges
         self._setup(rows, lengths, nstates, device, chunk, warm)
         return self
 
@@ -97,8 +100,16 @@ class TrajectoryBatch(object):
             self.obs = cat.to(device=self.device, dtype=torch.int32 if self.discrete else torch.float64).contiguous().clone() \
                 if cat.is_cuda else cat.to(device=self.device, dtype=torch.int32 if self.discrete else torch.float64)
             self._handle = C.c_void_p()
-            rc = lib.bhmm_b200_batch_create(C.byref(self._handle), self.offsets.ctypes.data_as(C.POINTER(C.c_longlong)),
-                                            self.K, self.N, int(chunk), int(warm))
+            if self._own_ranges is None:
+                rc = lib.bhmm_b200_batch_create(C.byref(self._handle), self.offsets.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                                self.K, self.N, int(chunk), int(warm))
+            else:
+                lo = np.ascontiguousarray([r[0] for r in self._own_ranges], dtype=np.int64)
+                hi = np.ascontiguousarray([r[1] for r in self._own_ranges], dtype=np.int64)
+                llp = C.POINTER(C.c_longlong)
+                rc = lib.bhmm_b200_batch_create_ranges(C.byref(self._handle), self.offsets.ctypes.data_as(llp),
+                                                       lo.ctypes.data_as(llp), hi.ctypes.data_as(llp), self.K, self.N,
+                                                       int(chunk), int(warm))
             check(rc)
             self._attach()
         self._stats = torch.zeros(lib.bhmm_b200_stats_len_gaussian(self.N), dtype=torch.float64, device=self.device)
@@ -157,6 +168,13 @@ class TrajectoryBatch(object):
     def uses_lane_kernels(self):
         """True when the small-N one-thread-per-chain kernels run (N <= 16), False for the general-N team kernels."""
         return bool(lib.bhmm_b200_batch_uses_lane_kernels(self._handle))
+
+    def border_handovers(self, k):
+        """(4, N) hand-over vectors at the borders of trajectory k's owned range after an E-step: forward used / forward
+        end / backward used / backward end (include/bhmm_b200.h, bhmm_b200_batch_border_handovers)."""
+        out = np.zeros((4, self.N))
+        check(lib.bhmm_b200_batch_border_handovers(self._handle, int(k), dptr(out)))
+        return out
 
     def set_profiling(self, on=True):
         """Record CUDA events around the forward and the backward+statistics kernels of every E-step."""
@@ -507,3 +525,112 @@ def make_batch(observations, nstates, device=None, chunk=0, warm=0, max_workspac
     if len(groups) == 1:
         return TrajectoryBatch(observations, nstates, device=device, chunk=chunk, warm=warm)
     return SubBatchedTrajectories(observations, nstates, int(max_workspace_bytes), device=device, chunk=chunk, warm=warm)
+
+
+def _rel_mismatch(a, b):
+    """Largest component-wise relative difference of two hand-over vectors (csrc/common.cuh:rel_mismatch)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    m = np.maximum(np.abs(a), np.abs(b))
+    d = np.where(m > 0, np.abs(a - b) / np.where(m > 0, m, 1.0), 0.0)
+    return float(np.max(np.where(np.isnan(d), 1.0, d))) if d.size else 0.0
+
+
+class TimeShardedTrajectories(object):
+    """E-step over trajectories that are cut in TIME across shards (one trajectory too long for one GPU).
+
+    Shard ``rank`` of ``world`` owns the frames [lo, hi) = [T*rank/world, T*(rank+1)/world) of every trajectory and
+    holds them together with ``halo`` frames on either side.  The chains at the borders of the owned range warm up on
+    the halo exactly like chains in the interior of a trajectory do; statistics and log-likelihood cover the owned
+    frames only, so they ADD over shards -- the only exchange is the all-reduce that the trajectory-sharded path already
+    has.  Nothing is assumed about the halo being long enough: after the E-step the warmed-up vector each shard started
+    from is compared with the vector its neighbour actually computed at the same frame (component-wise, relatively);
+    ``certify`` raises when a border disagrees by more than ``tol``.
+
+    One process per shard (``torch.distributed``), or several shards in one process for tests (``combine``).
+    Viterbi and hidden-path sampling need whole trajectories and are not available on shards.
+    """
+
+    def __init__(self, observations, nstates, rank, world, halo=None, device=None, chunk=0, warm=0, tol=1e-11):
+        self.N = int(nstates)
+        self.rank, self.world = int(rank), int(world)
+        self.tol = float(tol)
+        if halo is None:
+            halo = 8 * max(128, 48 * self.N)        # a few automatic warm-up lengths
+        self.halo = int(halo)
+        pieces, lengths, own = [], [], []
+        self.global_ranges = []
+        for o in observations:
+            o = np.asarray(o)
+            T = len(o)
+            lo, hi = (T * self.rank) // self.world, (T * (self.rank + 1)) // self.world
+            a, b = max(0, lo - self.halo), min(T, hi + self.halo)
+            if hi <= lo:                                 # nothing owned: keep one halo frame so that the batch is valid
+                a, b = min(lo, T - 1), min(lo, T - 1) + 1
+            pieces.append(o[a:b])
+            lengths.append(b - a)
+            own.append((lo - a, max(lo, hi) - a))
+            self.global_ranges.append((lo, hi, T))
+        host_dtype = np.int32 if np.issubdtype(np.asarray(observations[0]).dtype, np.integer) else np.float64
+        cat = np.concatenate([np.asarray(p, dtype=host_dtype) for p in pieces])
+        self.batch = TrajectoryBatch.from_concatenated(cat, lengths, self.N, device=device, chunk=chunk, warm=warm,
+                                                       own_ranges=own)
+        self.K = len(lengths)
+
+    def close(self):
+        self.batch.close()
+
+    def info(self):
+        return self.batch.info()
+
+    def estep_gaussian_local(self, A, pi, means, sigmas, ignore_outliers=True):
+        """Local statistics (device tensor) and the (K, 4, N) border hand-overs of this shard."""
+        stats = self.batch.estep_gaussian(A, pi, means, sigmas, ignore_outliers=ignore_outliers)
+        return stats, np.array([self.batch.border_handovers(k) for k in range(self.K)])
+
+    def estep_discrete_local(self, A, pi, B, ignore_outliers=False):
+        stats, Bnum = self.batch.estep_discrete(A, pi, B, ignore_outliers=ignore_outliers)
+        return stats, Bnum, np.array([self.batch.border_handovers(k) for k in range(self.K)])
+
+    @staticmethod
+    def certify(borders_by_rank, ranges_by_rank, tol):
+        """Worst relative mismatch over all shard borders; raises when it exceeds ``tol``.
+        borders_by_rank[r]: (K, 4, N); ranges_by_rank[r]: [(lo, hi, T)] per trajectory."""
+        world = len(borders_by_rank)
+        worst = 0.0
+        K = len(ranges_by_rank[0])
+        for k in range(K):
+            owners = [r for r in range(world) if ranges_by_rank[r][k][1] > ranges_by_rank[r][k][0]]
+            for left, right in zip(owners, owners[1:]):
+                fwd = _rel_mismatch(borders_by_rank[right][k][0], borders_by_rank[left][k][1])
+                bwd = _rel_mismatch(borders_by_rank[left][k][2], borders_by_rank[right][k][3])
+                worst = max(worst, fwd, bwd)
+        if worst > tol:
+            raise RuntimeError('time-sharded E-step: a shard border disagrees by %.3g (tolerance %.3g); the halo is too '
+                               'short for this model -- increase halo=' % (worst, tol))
+        return worst
+
+    @classmethod
+    def combine(cls, shards, local_results):
+        """Single-process use: add the shards' statistics and certify their borders.  Returns (stats, worst)."""
+        stats = None
+        for st, _ in local_results:
+            stats = st.clone() if stats is None else stats.add_(st.to(stats.device))
+        worst = cls.certify([b for _, b in local_results], [s.global_ranges for s in shards], shards[0].tol)
+        return stats, worst
+
+    def estep_gaussian(self, A, pi, means, sigmas, ignore_outliers=True):
+        """Distributed use (one process per shard, torch.distributed initialised): all-reduced statistics and the worst
+        border mismatch."""
+        import torch.distributed as td
+        torch = self.batch.torch
+        stats, borders = self.estep_gaussian_local(A, pi, means, sigmas, ignore_outliers=ignore_outliers)
+        stats = stats.clone()
+        td.all_reduce(stats, op=td.ReduceOp.SUM)
+        mine = torch.from_numpy(borders).to(stats.device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        td.all_gather(gathered, mine)
+        ranges = []
+        for r in range(self.world):
+            ranges.append([((T * r) // self.world, (T * (r + 1)) // self.world, T) for (_, _, T) in self.global_ranges])
+        worst = self.certify([g.cpu().numpy() for g in gathered], ranges, self.tol)
+        return stats, worst

@@ -118,6 +118,21 @@ typedef struct bhmm_b200_batch bhmm_b200_batch;
  * chunk / warm: frames per chain and warm-up frames (0 = automatic).  Scratch memory (forward variables,
  * chain tables, partial statistics) is allocated by the library unless a workspace is attached. */
 int bhmm_b200_batch_create(bhmm_b200_batch** out, const long long* offsets, int K, int N, int chunk, int warm);
+/* Time-sharded trajectories (one trajectory too long for one GPU): this batch OWNS only the frames
+ * [own_lo[k], own_hi[k]) of trajectory k -- statistics, log-likelihood and outputs cover exactly those -- and the
+ * frames around the range are a halo on which the chains next to its borders warm up (forward: from before own_lo,
+ * backward: from after own_hi).  The hand-overs at the borders cannot be certified inside one batch:
+ * bhmm_b200_batch_border_handovers returns, for trajectory k after an E-step, four N-vectors (host) --
+ *   [0] the forward vector the first owned chain started from   (warmed-up alpha at frame own_lo-1)
+ *   [1] the forward vector at the last owned frame              (alpha at own_hi-1)
+ *   [2] the backward vector the last owned chain started from   (warmed-up beta at frame own_hi)
+ *   [3] the backward vector at the first owned frame            (beta at own_lo)
+ * -- so that the caller compares [0] with the previous shard's [1] and [2] with the next shard's [3]
+ * (bhmm_b200.engine.TimeShardedTrajectories does, component-wise and relatively, with the engine's tolerance).
+ * Viterbi and hidden-path sampling need whole trajectories and return BHMM_B200_ERR_UNSUPPORTED on such a batch. */
+int bhmm_b200_batch_create_ranges(bhmm_b200_batch** out, const long long* offsets, const long long* own_lo,
+                                  const long long* own_hi, int K, int N, int chunk, int warm);
+int bhmm_b200_batch_border_handovers(const bhmm_b200_batch* b, int k, double* out);
 void bhmm_b200_batch_destroy(bhmm_b200_batch* b);
 int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm);
 /* 1 when the batch runs the small-N one-thread-per-chain kernels (N <= 16), 0 for the general-N team kernels.

@@ -410,3 +410,43 @@ def test_sub_batched_trajectories_match_single_batch(eng, oracle_port):
         eng.SubBatchedTrajectories(obs, N, 1000)
     one.close()
     many.close()
+
+
+@pytest.mark.parametrize('N,world', [(3, 3), (10, 4), (20, 2)])
+def test_time_sharded_trajectories(eng, oracle_port, N, world):
+    """Trajectories cut in TIME across shards (C5: one trajectory too long for one GPU): every shard owns a frame range
+    plus a halo, the statistics of the shards add up to those of the whole trajectories, and the hand-overs at the shard
+    borders are certified against the neighbour's value.  All shards run in this one process here."""
+    rng = np.random.default_rng(100 + N)
+    X = rng.random((N, N)) + 0.3 / N
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    means, sigmas = np.linspace(-N, N, N), np.linspace(0.7, 1.3, N)
+    obs = []
+    for T in (30000, 8000, 5):
+        s = rng.integers(0, N, size=T)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    shards = [eng.TimeShardedTrajectories(obs, N, r, world, halo=3000) for r in range(world)]
+    assert [g[:2] for g in shards[1].global_ranges][:2] == [(30000 // world, 2 * 30000 // world), (8000 // world, 2 * 8000 // world)]
+    local = [s.estep_gaussian_local(A, pi, means, sigmas) for s in shards]
+    stats, worst = eng.TimeShardedTrajectories.combine(shards, local)
+    assert worst <= 1e-11
+    st = eng.unpack_stats(stats.cpu().numpy(), N)
+    ref, wd, wdd = oracle_stats_gaussian(oracle_port, obs, A, pi, means, sigmas)
+    assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])
+    np.testing.assert_allclose(st['gamma0'], ref['gamma0'], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9, atol=1e-9 * ref['C'].max())
+    np.testing.assert_allclose(st['wsum'], ref['wsum'], rtol=RTOL)
+    np.testing.assert_allclose(st['wdd'], wdd, rtol=1e-9)
+    assert abs(st['C'].sum() - sum(len(o) - 1 for o in obs)) < 1e-6
+    # shards cannot produce whole-trajectory paths
+    with pytest.raises(Exception):
+        shards[0].batch.viterbi_gaussian(A, pi, means, sigmas)
+    for s in shards:
+        s.close()
+    # a halo that is far too short is detected, not silently accepted
+    short = [eng.TimeShardedTrajectories(obs, N, r, world, halo=2, warm=2, chunk=4000) for r in range(world)]
+    with pytest.raises(RuntimeError):
+        eng.TimeShardedTrajectories.combine(short, [s.estep_gaussian_local(A, pi, means, sigmas) for s in short])
+    for s in short:
+        s.close()
