@@ -528,11 +528,18 @@ def make_batch(observations, nstates, device=None, chunk=0, warm=0, max_workspac
 
 
 def _rel_mismatch(a, b):
-    """Largest component-wise relative difference of two hand-over vectors (csrc/common.cuh:rel_mismatch)."""
+    """Largest component-wise relative difference of two hand-over vectors; NaN counts as a full mismatch
+    (csrc/common.cuh:rel_mismatch)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    if np.any(np.isnan(a)) or np.any(np.isnan(b)):
+        return 1.0
     m = np.maximum(np.abs(a), np.abs(b))
-    d = np.where(m > 0, np.abs(a - b) / np.where(m > 0, m, 1.0), 0.0)
-    return float(np.max(np.where(np.isnan(d), 1.0, d))) if d.size else 0.0
+    d = np.zeros_like(m)
+    nz = m > 0
+    d[nz] = np.abs(a - b)[nz] / m[nz]
+    return float(d.max())
 
 
 class TimeShardedTrajectories(object):

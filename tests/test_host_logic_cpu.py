@@ -94,3 +94,35 @@ def test_testsystems_recipe():
     pi0, A0, m0, s0 = ts.perturbed_initial_model(A, np.linspace(-5, 5, 6), 6)
     np.testing.assert_allclose(A0.sum(axis=1), 1.0)
     assert not np.allclose(A0, A0.T)       # asymmetric on purpose: selects the non-reversible M-step
+
+
+def test_time_shard_border_certification_logic():
+    """Host side of the time-sharded E-step (engine.TimeShardedTrajectories.certify): the forward vector a shard started
+    from is compared with the left neighbour's vector at the same frame, the backward one with the right neighbour's;
+    shards that own nothing of a trajectory are skipped; a mismatch above the tolerance raises."""
+    import numpy as np
+    from bhmm_b200.engine import TimeShardedTrajectories as TS, _rel_mismatch
+    assert _rel_mismatch([1.0, 0.0, 2.0], [1.0, 0.0, 2.0]) == 0.0
+    assert abs(_rel_mismatch([1.0, 2.0], [1.0, 2.0 * (1 + 1e-9)]) - 1e-9) < 1e-12
+    assert _rel_mismatch([np.nan, 1.0], [1.0, 1.0]) == 1.0
+    N, world = 3, 3
+    rng = np.random.default_rng(0)
+    fwd_at = {10: rng.random(N), 20: rng.random(N)}      # exact alpha at the frame before each border
+    bwd_at = {10: rng.random(N), 20: rng.random(N)}      # exact beta at the first frame after each border
+    ranges = [[(0, 10, 30), (0, 0, 2)], [(10, 20, 30), (0, 1, 2)], [(20, 30, 30), (1, 2, 2)]]
+    borders = np.zeros((world, 2, 4, N))
+    # trajectory 0: three owners
+    borders[0, 0, 1], borders[1, 0, 0] = fwd_at[10], fwd_at[10] * (1 + 1e-14)
+    borders[1, 0, 1], borders[2, 0, 0] = fwd_at[20], fwd_at[20]
+    borders[0, 0, 2], borders[1, 0, 3] = bwd_at[10], bwd_at[10]
+    borders[1, 0, 2], borders[2, 0, 3] = bwd_at[20] * (1 - 2e-14), bwd_at[20]
+    # trajectory 1 (2 frames): shard 0 owns nothing, shards 1 and 2 one frame each
+    v, w = rng.random(N), rng.random(N)
+    borders[1, 1, 1], borders[2, 1, 0] = v, v
+    borders[1, 1, 2], borders[2, 1, 3] = w, w
+    worst = TS.certify(list(borders), ranges, 1e-11)
+    assert 1e-14 < worst < 1e-13
+    borders[2, 0, 0] = fwd_at[20] * (1 + 1e-6)
+    import pytest
+    with pytest.raises(RuntimeError):
+        TS.certify(list(borders), ranges, 1e-11)
