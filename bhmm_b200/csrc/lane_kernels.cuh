@@ -60,6 +60,12 @@ constexpr unsigned FULL = 0xffffffffu;
 #define LANE_UNROLL_B 1
 #endif
 constexpr int kUnrollF = LANE_UNROLL_F, kUnrollB = LANE_UNROLL_B;
+#ifndef LANE_ALPHA_PREFETCH
+#define LANE_ALPHA_PREFETCH 1        // backward kernel: L1 prefetch of the next step's forward variables for N <= MAXN
+#endif                               // (N = 3: -21 %, N = 8: -10 % kernel time; N = 10: no gain, a step is long enough)
+#ifndef LANE_ALPHA_PREFETCH_MAXN
+#define LANE_ALPHA_PREFETCH_MAXN 8
+#endif
 #ifndef LANE_PF
 #define LANE_PF 1            // depth of the register ring of prefetched observations: with the L1 prefetch of the next cache
                              // line one step ahead is enough (4 -> 1: -1.4 % at N = 10, fewer registers and moves)
@@ -749,6 +755,14 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
                 const double2* src = il + ((long long)(on ? f - t0 : 0) * NP2 << 5);
 #pragma unroll
                 for (int jp = 0; jp < NP2; ++jp) a2[jp] = __ldcs(src + (jp << 5));
+#if LANE_ALPHA_PREFETCH
+                // the forward variables of the NEXT step (frame f-1) into L1: the loads above are consumed only half a
+                // step after they are issued, and for few states a step is too short to cover the DRAM latency
+                if (N <= LANE_ALPHA_PREFETCH_MAXN && on && f > t0) {
+#pragma unroll
+                    for (int jp = 0; jp < NP2; ++jp) prefetch_l1(src - (NP2 << 5) + (jp << 5));
+                }
+#endif
             }
             double b[N];
             if (init) {
