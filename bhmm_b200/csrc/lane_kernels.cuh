@@ -66,6 +66,9 @@ constexpr int kUnrollF = LANE_UNROLL_F, kUnrollB = LANE_UNROLL_B;
 #ifndef LANE_ALPHA_PREFETCH_MAXN
 #define LANE_ALPHA_PREFETCH_MAXN 8
 #endif
+#ifndef LANE_SAMPLE_AHEAD
+#define LANE_SAMPLE_AHEAD 2          // sampler: frames ahead of the L1 prefetch of the forward variables
+#endif
 #ifndef LANE_PF
 #define LANE_PF 1            // depth of the register ring of prefetched observations: with the L1 prefetch of the next cache
                              // line one step ahead is enough (4 -> 1: -1.4 % at N = 10, fewer registers and moves)
@@ -1016,6 +1019,20 @@ k_sample_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
             if (2 * jp + 1 < N) al[2 * jp + 1] = v2.y;
         }
     };
+    // Every step needs its forward variables at once (the draw depends on them), so they are prefetched into L1 two
+    // steps ahead, together with the next cache line of the observations and of the supplied uniforms: without it a
+    // step costs the full DRAM latency (3400 cycles per frame at the C3 shape).
+    auto prefetch_step = [&](int f) {
+        const int fa = f - LANE_SAMPLE_AHEAD;
+        if (fa >= t0) {
+            const double2* src = il + ((long long)(fa - t0) * NP2 << 5);
+#pragma unroll
+            for (int jp = 0; jp < NP2; ++jp) prefetch_l1(src + (jp << 5));
+        }
+        const int fo = max(f - 16, t0);
+        if (EM == EM_GAUSS) prefetch_l1(a.obs + trow + fo);
+        if (a.u_row) prefetch_l1(a.u_row + trow + fo);
+    };
     auto uniform = [&](int f) -> double {
         return a.u_row ? __ldg(a.u_row + trow + f) : lane_philox_uniform(a.seed, a.sweep, trow + f);
     };
@@ -1045,6 +1062,7 @@ k_sample_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
             if (!have || f < t0) continue;
             double al[N];
             load_alpha(f, al);
+            prefetch_step(f);
             const double r = uniform(f);
             const bool last = (f == T - 1);
             if (!coalesced) {
@@ -1086,6 +1104,7 @@ k_sample_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a)
             if (!have || f < t0 || f < coal) continue;
             double al[N];
             load_alpha(f, al);
+            prefetch_step(f);
             const double r = uniform(f);
             const bool last = (f == T - 1);
             const int st = lane_draw<N, EXACT>(al, A_s, prev, r, last, bad);
