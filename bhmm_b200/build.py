@@ -77,7 +77,8 @@ def build(force=False, verbose=False, defines=(), libname=None):
 
 
 if __name__ == '__main__':
-    defs = [a for a in sys.argv[1:] if a.startswith('-D')]
+    # -DNAME=VALUE defines and --nvcc=<flag> extra compiler flags (e.g. --nvcc=-Xptxas --nvcc=-O2) for variant builds
+    defs = [a for a in sys.argv[1:] if a.startswith('-D')] + [a.split('=', 1)[1] for a in sys.argv[1:] if a.startswith('--nvcc=')]
     name = None
     for a in sys.argv[1:]:
         if a.startswith('--name='):
