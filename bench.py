@@ -299,6 +299,12 @@ def run_ours(args):
     ms = float(t.item())
     value = world * rows * args.steps / (ms * 1e-3)
     info = batch.info()
+    # what the slowest rank looked like: launches of the timed region (fix-up sweeps and redone passes show up here) and
+    # kernel time, maximum over ranks
+    rk = torch.tensor([float(launches), kms['forward'] + kms['backward_stats']], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(rk, op=td.ReduceOp.MAX)
+    max_rank_launches, max_rank_kernel_ms = int(rk[0].item()), float(rk[1].item()) / args.steps
 
     # ---- end-to-end: observations start in pinned host memory every step.  Every step's inputs are copied host ->
     # device inside the timed region and its statistics are read back; the copy of step k+1 runs on a second stream
@@ -399,7 +405,9 @@ def run_ours(args):
                        'l2': 'inputs larger than L2: %.1f GB observations + %.1f GB forward variables streamed per step'
                              % (rows * 8 / 1e9, rows * N * 8 / 1e9),
                        'certification': {'fixups_fwd': info['fixups_fwd'], 'fixups_bwd': info['fixups_bwd'],
-                                         'worst_fwd': info['worst_fwd'], 'worst_bwd': info['worst_bwd']}},
+                                         'worst_fwd': info['worst_fwd'], 'worst_bwd': info['worst_bwd'],
+                                         'max_rank_launches': max_rank_launches,
+                                         'max_rank_kernel_ms_per_step': max_rank_kernel_ms}},
             'roofline': {'bound': 'hbm', 'kernel': ('k_backward_stats_%s' if dom == 'backward_stats' else 'k_forward_%s') % family,
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
