@@ -77,6 +77,7 @@ _proto('bhmm_b200_discrete_p_obs_dev', C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_
 _proto('bhmm_b200_batch_create', C.c_int, C.POINTER(_vp), _llp, C.c_int, C.c_int, C.c_int, C.c_int)
 _proto('bhmm_b200_batch_create_ranges', C.c_int, C.POINTER(_vp), _llp, _llp, _llp, C.c_int, C.c_int, C.c_int, C.c_int)
 _proto('bhmm_b200_batch_border_handovers', C.c_int, _vp, C.c_int, _dp)
+_proto('bhmm_b200_adapt_warm', C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _dp)
 _proto('bhmm_b200_batch_destroy', None, _vp)
 _proto('bhmm_b200_batch_replan', C.c_int, _vp, C.c_int, C.c_int)
 _proto('bhmm_b200_batch_uses_lane_kernels', C.c_int, _vp)

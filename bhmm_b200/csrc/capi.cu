@@ -123,19 +123,43 @@ int auto_chunk_lane(long long rows, int N, int warm)
     return (int)std::min<long long>(c, 1 << 30);
 }
 
-int adapt_warm(int current, double need, double worst, bool failed, int warm_min, int warm_cap)
+int adapt_warm(int current, double need, double worst, bool failed, int warm_min, int warm_cap, double* edge)
 {
-    // Keep the warm-up ~15 % above what the hardest hand-over needs.  `need` (= w log tol / log m) is only
-    // informative while the mismatch m is above the rounding-noise floor of two independently rounded filters
-    // (~1e-14); at the floor the warm-up is known to be more than enough, so it shrinks slowly until the mismatch
-    // becomes measurable again (still one decade below the tolerance).
+    // edge[0]: the last warm-up need that was MEASURABLE, edge[1]: passes since it was confirmed.
+    //
+    // Keep the warm-up 12-15 % above what the hardest hand-over needs.  `need` (= w log tol / log m) is only informative
+    // while the mismatch m is above the rounding-noise floor of two independently rounded filters (~1e-14); at the floor
+    // the warm-up is known to be more than enough and shrinks slowly -- but not below 1.12 x the remembered need, which
+    // is held for 20 passes and then decays by 3 % per pass until the mismatch becomes measurable again and confirms
+    // or corrects it.  Without that memory the warm-up oscillates between the floor and the tolerance, and with the
+    // mixing rate changing by a few per cent from one EM iteration (and one rank) to the next a hand-over fails every
+    // 15-30 passes; a failed forward certification costs a fix-up sweep as long as a whole forward kernel (the repaired
+    // chains are walked sequentially) on every rank of the job.  Simulated with 5-8 % jitter of the need
+    // (tests/test_host_logic_cpu.py): failure rate 3-5 % -> below 1 % per pass for about 5 % more warm-up frames.
     double target;
-    if (failed) target = std::max(1.15 * need, current + 32.0);
-    else if (worst <= 1e-14) target = 0.95 * current;
-    else target = std::max(1.15 * need, 0.95 * current);
-    int w = (int)std::ceil(target / 16.0) * 16;
+    if (failed) {
+        if (worst < 0.5) edge[0] = std::max(edge[0], need);      // (m >= 0.5: `need` is only a doubling rule)
+        edge[1] = 0.0;
+        target = std::max(1.2 * need, current + 32.0);
+    } else if (worst <= 1e-14) {
+        edge[1] += 1.0;
+        if (edge[1] > 20.0) edge[0] *= 0.97;
+        target = std::max(0.95 * current, 1.12 * edge[0]);
+    } else {
+        edge[0] = std::max(need, 0.97 * edge[0]);
+        edge[1] = 0.0;
+        target = std::max(std::max(1.15 * need, 1.12 * edge[0]), 0.95 * current);
+    }
+    int w = (int)std::ceil(target / 16.0 - 1e-9) * 16;        // (1.12 x 300 is 336.00000000000006)
     w = std::max(w, warm_min);
     return std::min(w, std::max(warm_cap, 1));
+}
+
+// the policy above as a plain host function (no device needed): state[2] = {remembered need, passes since confirmed}
+extern "C" int bhmm_b200_adapt_warm(int current, double need, double worst, int failed, int warm_min, int warm_cap,
+                                    double* state)
+{
+    return adapt_warm(current, need, worst, failed != 0, warm_min, warm_cap, state);
 }
 
 size_t chainwork_bytes(int n, int N)

@@ -33,6 +33,7 @@ struct bhmm_b200_batch {
     double* d_pi = nullptr;
     double* d_mu = nullptr;
     double* d_sigma = nullptr;
+    double edge_f[2] = {0.0, 0.0}, edge_b[2] = {0.0, 0.0};   // adapt_warm state per direction: remembered need, age
     std::vector<long long> own_lo, own_hi;   // owned frame range per trajectory (empty: whole trajectories)
     double* d_alpha = nullptr;
     unsigned char* d_F = nullptr;
@@ -203,7 +204,7 @@ int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
         RC_TRY(run_forward(b->w, em, emkind, N, b->d_A, b->d_pi, b->d_alpha, b->info, st));
     }
     if (b->profile) cudaEventRecord(b->ev[1], st);
-    if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT);
+    if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT, b->edge_f);
 
     b->w.need_b = 0.0;
     for (int attempt = 0;; ++attempt) {
@@ -228,11 +229,11 @@ int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
         if (!b->w.chunked) break;
         const long long nfail = certify_sync(b->w, N, -1, &b->info.worst_b, st);
         if (nfail < 0) { bhmm_set_error(BHMM_ERR_CUDA, cudaGetErrorString(cudaGetLastError())); return BHMM_ERR_CUDA; }
-        if (nfail == 0) { b->warm_b = adapt_warm(b->warm_b, b->w.need_b, b->info.worst_b, false, b->warm_min, b->plan.maxT); break; }
+        if (nfail == 0) { b->warm_b = adapt_warm(b->warm_b, b->w.need_b, b->info.worst_b, false, b->warm_min, b->plan.maxT, b->edge_b); break; }
         // statistics of a failed pass cannot be patched chain by chain: lengthen the warm-up (at least +32 frames, up to
         // the longest trajectory, which is an exact start) and redo the pass.
         if (b->warm_b >= b->plan.maxT) { bhmm_set_error(BHMM_ERR_NOT_CERTIFIED, "backward hand-overs not certified"); return BHMM_ERR_NOT_CERTIFIED; }
-        b->warm_b = adapt_warm(b->warm_b, b->w.need_b, b->info.worst_b, true, b->warm_min, b->plan.maxT);
+        b->warm_b = adapt_warm(b->warm_b, b->w.need_b, b->info.worst_b, true, b->warm_min, b->plan.maxT, b->edge_b);
         b->info.fix_b += 1;
         b->info.rerun += (double)b->w.n_total;
     }
@@ -288,7 +289,7 @@ int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
             x.ch = ch;
             return launch_lane(x, hp, N, emkind, LANE_FORWARD, s2);
         }, b->info, st));
-        if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT);
+        if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT, b->edge_f);
         CUDA_TRY(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
         CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(long long) * ((size_t)N * N + 2 * N), st));
         Chains all = b->w.ch;
@@ -307,7 +308,7 @@ int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
         }
     } else {
         RC_TRY(run_forward(b->w, em, emkind, N, b->d_A, b->d_pi, b->d_alpha, b->info, st));
-        if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT);
+        if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT, b->edge_f);
         CUDA_TRY(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
         if (d_u) RC_TRY(launch_sample_table(b->d_alpha, b->d_A, d_u, b->d_offsets, b->K, N, b->rows, b->d_F, b->d_err, st));
         else RC_TRY(launch_sample_table_philox(b->d_alpha, b->d_A, seed, sweep, b->d_offsets, b->K, N, b->rows, b->d_F, b->d_err, st));

@@ -72,7 +72,7 @@ struct ChainWork {
     double need_f = 0, need_b = 0;   // certification's estimate of the warm-up the hardest hand-over needs
 };
 // next warm-up length from the current one, the certification's need estimate and the largest mismatch of the pass
-int adapt_warm(int current, double need, double worst, bool failed, int warm_min, int warm_cap);
+int adapt_warm(int current, double need, double worst, bool failed, int warm_min, int warm_cap, double* edge);
 size_t chainwork_bytes(int n_chains, int N);
 // carve ChainWork out of `base` (device) and upload the plan; returns bytes used
 int chainwork_setup(ChainWork& w, const HostPlan& p, int N, int warm, char* base, cudaStream_t st);

@@ -133,6 +133,10 @@ int bhmm_b200_batch_create(bhmm_b200_batch** out, const long long* offsets, int 
 int bhmm_b200_batch_create_ranges(bhmm_b200_batch** out, const long long* offsets, const long long* own_lo,
                                   const long long* own_hi, int K, int N, int chunk, int warm);
 int bhmm_b200_batch_border_handovers(const bhmm_b200_batch* b, int k, double* out);
+/* The warm-up adaptation policy of the batch engine as a plain host function (no device needed; used by the tests):
+ * next warm-up length from the current one, the certification's need estimate (w log tol / log m), the largest
+ * hand-over mismatch m of the pass and whether the pass failed; state[2] = {remembered need, passes since confirmed}. */
+int bhmm_b200_adapt_warm(int current, double need, double worst, int failed, int warm_min, int warm_cap, double* state);
 void bhmm_b200_batch_destroy(bhmm_b200_batch* b);
 int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm);
 /* 1 when the batch runs the small-N one-thread-per-chain kernels (N <= 16), 0 for the general-N team kernels.

@@ -126,3 +126,47 @@ def test_time_shard_border_certification_logic():
     import pytest
     with pytest.raises(RuntimeError):
         TS.certify(list(borders), ranges, 1e-11)
+
+
+def test_warm_up_adaptation_policy():
+    """bhmm_b200_adapt_warm (capi.cu:adapt_warm): a failed pass lengthens the warm-up, a mismatch at the rounding floor
+    shrinks it slowly but not below 1.12 x the remembered need, and under a mixing rate that jitters by 5 % from pass to
+    pass the certification fails in well under 1.5 % of the passes while the warm-up stays within 15 % of the ideal."""
+    import ctypes as C
+    import math
+    import numpy as np
+    from bhmm_b200 import _lib
+    fn = _lib.lib.bhmm_b200_adapt_warm
+
+    def step(cur, need, worst, failed, state, wmin=32, cap=10 ** 6):
+        return fn(int(cur), float(need), float(worst), int(failed), wmin, cap, state.ctypes.data_as(C.POINTER(C.c_double)))
+
+    st = np.zeros(2)
+    assert step(100, 300.0, 1e-5, True, st) == 368              # 1.2 x need, multiple of 16
+    assert st[0] == 300.0
+    assert step(368, 0.0, 3e-15, False, st) == 352              # floor: -5 %, but >= 1.12 x 300 = 336
+    assert step(352, 0.0, 3e-15, False, st) == 336
+    assert step(336, 0.0, 3e-15, False, st) == 336              # held by the remembered need
+    st = np.zeros(2)
+    assert step(64, 2 * 64 + 32, 0.9, True, st) == 192 and st[0] == 0.0     # unmeasurable mismatch: doubling rule only
+    assert step(100, 50.0, 3e-15, False, np.zeros(2), wmin=128) == 128       # explicit floor
+    assert step(1000, 5000.0, 1e-3, True, np.zeros(2), cap=2000) == 2000     # capped at the longest trajectory
+
+    def simulate(jitter, iters=3000, need0=500.0, seed=0):
+        rng = np.random.default_rng(seed)
+        w, fails, wsum = 576, 0, 0
+        state = np.zeros(2)
+        for _ in range(iters):
+            true_need = need0 * (1 + jitter * rng.standard_normal())
+            m = max(10.0 ** (-13.0 * w / true_need), 3e-15 * math.exp(0.5 * rng.standard_normal()))
+            failed = m > 1e-13
+            need = w * math.log(1e-13) / math.log(m) if m < 0.5 else 2 * w + 32
+            fails += failed
+            wsum += w
+            w = step(w, need, m, failed, state)
+        return fails / iters, wsum / iters
+
+    for jitter, max_fail in ((0.03, 0.006), (0.05, 0.015)):
+        fail, mean_w = simulate(jitter)
+        assert fail <= max_fail, (jitter, fail)
+        assert 500.0 * 1.05 < mean_w < 500.0 * 1.30, (jitter, mean_w)
