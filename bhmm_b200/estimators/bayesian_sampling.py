@@ -7,8 +7,9 @@ serial reference when fed the same uniforms) and returns only the integer / mome
 need.  The parameter draws are tiny host math with numpy's global RNG, as in the reference.
 
 Transition-matrix draw: the reference delegates to msmtools.estimation.sample_tmatrix (absent, un-pinned).  The
-non-reversible posterior is row-wise Dirichlet(C_i + prior_i) and is drawn here directly; the reversible sampler is
-not implemented (PARITY-UNPINNED): use reversible=False.
+non-reversible posterior is row-wise Dirichlet(C_i + prior_i) and is drawn here directly; the reversible posterior is
+sampled by a from-scratch Metropolis sampler on symmetric weights (util/tmatrix.py:sample_P_reversible; the reference
+delegates to msmtools, so this part is PARITY-UNPINNED).
 """
 import copy
 import time
@@ -32,10 +33,8 @@ class BayesianHMMSampler(object):
             raise Exception("No observations were provided.")
         if initial_model is None:
             raise NotImplementedError('bhmm_b200 needs initial_model= (bhmm.init_hmm is outside the hot path)')
-        if reversible:
-            raise NotImplementedError('reversible transition-matrix sampling is delegated to msmtools by the reference '
-                                      'and is not part of the hot path; use reversible=False')
         self.reversible = reversible
+        self._np_rng = np.random.default_rng(np.random.randint(0, 2 ** 31 - 1))
         self.stationary = stationary
         self.nstates = nstates
         if shard and dist.world_size() > 1:
@@ -145,13 +144,20 @@ class BayesianHMMSampler(object):
     def _updateTransitionMatrix(self, st):
         """Sample the transition matrix and the initial distribution (:341-373), non-reversible posterior."""
         Cm = st['C'].astype(float) + self.prior_C
-        Tij = np.zeros_like(Cm)
-        for i in range(self.nstates):
-            positive = Cm[i] > 0
-            if not np.any(positive):
-                Tij[i, i] = 1.0
-            else:
-                Tij[i, positive] = np.random.dirichlet(Cm[i, positive])
+        if self.reversible:
+            # from-scratch reversible sampler (the reference calls msmtools here; parity unpinned, util/tmatrix.py)
+            # every draw starts at the reversible maximum-likelihood estimate of the CURRENT counts (their sparsity
+            # pattern may differ from the previous sweep's) and runs transition_matrix_sampling_steps / 50 sweeps
+            Tij = _tmatrix.sample_P_reversible(Cm, nsteps=max(10, self.transition_matrix_sampling_steps // 50),
+                                               rng=self._np_rng)
+        else:
+            Tij = np.zeros_like(Cm)
+            for i in range(self.nstates):
+                positive = Cm[i] > 0
+                if not np.any(positive):
+                    Tij[i, i] = 1.0
+                else:
+                    Tij[i, positive] = np.random.dirichlet(Cm[i, positive])
         if self.stationary:
             p0 = _tmatrix.stationary_distribution(Tij, C=Cm)
         else:

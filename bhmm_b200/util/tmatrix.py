@@ -120,3 +120,62 @@ def estimate_P(C, reversible=True, fixed_statdist=None, maxiter=1000000, maxerr=
             Csub[zero_rows, zero_rows] = 1.0
             P[I] = Csub / Csub.sum(axis=1)[:, None]
     return P
+
+
+def sample_P_reversible(C, nsteps=1000, P0=None, rng=None):
+    """One draw from the posterior of REVERSIBLE transition matrices given the (posterior) count matrix C.
+
+    From scratch -- the reference delegates this to msmtools.estimation.sample_tmatrix (bayesian_sampling.py:355-356),
+    which is absent and un-pinned, so this sampler is PARITY-UNPINNED: it is tested by its defining properties only
+    (samples are stochastic and obey detailed balance, their mean approaches the reversible maximum-likelihood
+    estimate as counts grow, their spread shrinks like 1/sqrt(counts)).
+
+    Parametrisation: a symmetric non-negative weight matrix X with T_ij = x_ij / sum_k x_ik, which is reversible with
+    stationary vector proportional to the row sums of X.  Target: prod_ij T_ij^(c_ij) with respect to the flat measure on
+    the x_ij (i <= j) -- c_ij are the caller's posterior counts, i.e. observed counts plus prior counts, exactly what the
+    reference hands to its sampler.  `nsteps` Metropolis sweeps over the weights on the sparsity pattern of C + C^T,
+    log-normal random-walk proposals (the Jacobian of the log parametrisation is part of the acceptance ratio), started
+    at the reversible maximum-likelihood estimate (or P0); the scale of X, which T does not depend on, is renormalised
+    after every sweep.
+    """
+    rng = np.random.default_rng() if rng is None else rng
+    C = np.asarray(C, dtype=np.float64)
+    n = C.shape[0]
+    if not is_connected(C, strong=True):
+        raise NotImplementedError('Encountered disconnected count matrix with sampling option reversible:\n ' + str(C)
+                                  + '\nUse prior to ensure connectivity or use reversible=False.')
+    if P0 is None:
+        P0 = transition_matrix_reversible(C)
+    pi = stationary_vector(P0)
+    X = pi[:, None] * P0
+    X = 0.5 * (X + X.T)
+    Csym = C + C.T
+    pattern = [(i, j) for i in range(n) for j in range(i, n) if Csym[i, j] > 0 and X[i, j] > 0]
+    rows = X.sum(axis=1)
+    crow = C.sum(axis=1)
+    sigma = 0.5
+    for _ in range(int(nsteps)):
+        for (i, j) in pattern:
+            old = X[i, j]
+            new = old * np.exp(sigma * rng.standard_normal())
+            d = new - old
+            if i == j:
+                ri = rows[i] + d
+                # log f = sum c_ab log x_ab - sum_a crow_a log rows_a ; only x_ii and rows_i change
+                dlog = C[i, i] * np.log(new / old) - crow[i] * np.log(ri / rows[i])
+            else:
+                ri, rj = rows[i] + d, rows[j] + d
+                dlog = (C[i, j] + C[j, i]) * np.log(new / old) - crow[i] * np.log(ri / rows[i]) \
+                    - crow[j] * np.log(rj / rows[j])
+            dlog += np.log(new / old)                    # Jacobian of the log-normal proposal
+            if np.log(rng.random()) < dlog:
+                X[i, j] = new
+                if i == j:
+                    rows[i] = ri
+                else:
+                    X[j, i] = new
+                    rows[i], rows[j] = ri, rj
+        tot = rows.sum()
+        X /= tot
+        rows /= tot
+    return X / rows[:, None]

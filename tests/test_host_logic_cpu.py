@@ -170,3 +170,29 @@ def test_warm_up_adaptation_policy():
         fail, mean_w = simulate(jitter)
         assert fail <= max_fail, (jitter, fail)
         assert 500.0 * 1.05 < mean_w < 500.0 * 1.30, (jitter, mean_w)
+
+
+def test_reversible_transition_matrix_sampler_properties():
+    """util/tmatrix.py:sample_P_reversible replaces msmtools' sampler (absent, parity unpinned): every sample is a
+    stochastic matrix in detailed balance, the sample mean approaches the reversible MLE as counts grow, the spread
+    shrinks like 1/sqrt(counts), and a disconnected count matrix is refused like in the reference."""
+    import numpy as np
+    import pytest
+    from bhmm_b200.util import tmatrix
+    rng = np.random.default_rng(5)
+    P = np.array([[0.90, 0.08, 0.02], [0.10, 0.80, 0.10], [0.02, 0.18, 0.80]])
+    pi = tmatrix.stationary_distribution(P)
+    spreads = []
+    for total in (3e3, 3e5):
+        C = total * pi[:, None] * P + 1.0 / 3          # expected counts + a 'mixed'-like prior
+        mle = tmatrix.transition_matrix_reversible(C)
+        samples = np.array([tmatrix.sample_P_reversible(C, nsteps=30, rng=rng) for _ in range(60)])
+        for T in samples[::10]:
+            assert np.all(T >= 0) and np.allclose(T.sum(axis=1), 1.0)
+            mu = tmatrix.stationary_distribution(T)
+            np.testing.assert_allclose(mu[:, None] * T, (mu[:, None] * T).T, atol=1e-12)
+        np.testing.assert_allclose(samples.mean(axis=0), mle, atol=6.0 / np.sqrt(total) + 1e-3)
+        spreads.append(samples.std(axis=0).max())
+    assert 0 < spreads[1] < spreads[0] / 4                 # 100 x the counts: about 10 x narrower
+    with pytest.raises(NotImplementedError):
+        tmatrix.sample_P_reversible(np.array([[5.0, 0.0], [0.0, 7.0]]), rng=rng)
