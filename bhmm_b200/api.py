@@ -250,8 +250,9 @@ class SampledModels(object):
 
 def bayesian_hmm(observations, estimated_hmm, nsample=100, reversible=True, stationary=False, p0_prior='mixed',
                  transition_matrix_prior='mixed', store_hidden=False, call_back=None):
-    """Posterior sample of HMMs by Gibbs sampling on the GPU engine (api.py:375-470).  Reversible transition-matrix
-    sampling is delegated to msmtools by the reference and is not available here: pass reversible=False."""
+    """Posterior sample of HMMs by Gibbs sampling on the GPU engine (api.py:375-470).  The reference
+    delegates reversible transition-matrix sampling to msmtools (absent): reversible=True uses the from-scratch
+    sampler util/tmatrix.py:sample_P_reversible (parity unpinned); reversible=False draws row-wise Dirichlets."""
     from .estimators.bayesian_sampling import BayesianHMMSampler
     model_type = estimated_hmm.output_model.model_type
     if model_type == 'discrete':

@@ -142,7 +142,7 @@ class BayesianHMMSampler(object):
             om.sample_from_histogram(st['hist'])
 
     def _updateTransitionMatrix(self, st):
-        """Sample the transition matrix and the initial distribution (:341-373), non-reversible posterior."""
+        """Sample the transition matrix and the initial distribution (:341-373)."""
         Cm = st['C'].astype(float) + self.prior_C
         if self.reversible:
             # from-scratch reversible sampler (the reference calls msmtools here; parity unpinned, util/tmatrix.py)

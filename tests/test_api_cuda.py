@@ -42,8 +42,12 @@ def test_estimate_hmm_and_bayesian_hmm_gaussian():
     assert tm['mean'].shape == (3, 3) and np.allclose(tm['samples'].sum(axis=2), 1.0)
     np.testing.assert_allclose(tm['mean'][np.ix_(order, order)], A, atol=0.03)
     np.testing.assert_allclose(post.means['mean'][order], means, atol=0.15)
-    with pytest.raises(NotImplementedError):
-        bhmm_b200.bayesian_hmm(obs, hmm, nsample=1, reversible=True)
+    # reversible posterior (from-scratch sampler, parity unpinned): every sampled matrix is in detailed balance
+    from bhmm_b200.util import tmatrix
+    postr = bhmm_b200.bayesian_hmm(obs, hmm, nsample=3, reversible=True)
+    for T in postr.transition_matrix['samples']:
+        assert tmatrix.is_transition_matrix(T) and tmatrix.is_reversible(T)
+    np.testing.assert_allclose(postr.transition_matrix['mean'][np.ix_(order, order)], A, atol=0.03)
 
 
 def test_estimate_hmm_discrete():

@@ -196,3 +196,32 @@ def test_reversible_transition_matrix_sampler_properties():
     assert 0 < spreads[1] < spreads[0] / 4                 # 100 x the counts: about 10 x narrower
     with pytest.raises(NotImplementedError):
         tmatrix.sample_P_reversible(np.array([[5.0, 0.0], [0.0, 7.0]]), rng=rng)
+
+
+def test_gibbs_transition_matrix_update_reversible_and_not():
+    """BayesianHMMSampler._updateTransitionMatrix (bayesian_sampling.py:341-373) on given path statistics, without a
+    device: the reversible branch hands posterior counts to the from-scratch sampler and yields a model in detailed
+    balance; the non-reversible branch draws row-wise Dirichlets; both leave a valid initial distribution."""
+    import numpy as np
+    from bhmm_b200.estimators.bayesian_sampling import BayesianHMMSampler
+    from bhmm_b200.hmm.generic_hmm import HMM
+    from bhmm_b200.output_models.gaussian import GaussianOutputModel
+    from bhmm_b200.util import tmatrix
+    np.random.seed(3)
+    A = np.array([[0.95, 0.04, 0.01], [0.05, 0.90, 0.05], [0.02, 0.08, 0.90]])
+    pi = tmatrix.stationary_distribution(A)
+    st = {'C': np.round(20000 * pi[:, None] * A).astype(np.int64), 'n0': np.array([3, 1, 0], dtype=np.int64)}
+    for reversible in (True, False):
+        s = BayesianHMMSampler.__new__(BayesianHMMSampler)
+        s.reversible, s.stationary, s.nstates = reversible, False, 3
+        s._np_rng = np.random.default_rng(11)
+        s.prior_C, s.prior_n0 = A.copy(), pi.copy()
+        s.transition_matrix_sampling_steps = 1000
+        s.model = HMM(pi, A, GaussianOutputModel(3, means=[-1.0, 0.0, 1.0], sigmas=[1.0, 1.0, 1.0]))
+        s._updateTransitionMatrix(st)
+        T, p0 = s.model.transition_matrix, s.model.initial_distribution
+        assert tmatrix.is_transition_matrix(T) and not np.array_equal(T, A)
+        np.testing.assert_allclose(T, A, atol=0.02)
+        assert np.all(p0 >= 0) and abs(p0.sum() - 1.0) < 1e-12
+        if reversible:
+            assert tmatrix.is_reversible(T)
