@@ -104,6 +104,15 @@ int launch_backward_team(const BwdArgs& a, int em, bool stats, cudaStream_t st);
 int backward_stats_grid(int N, int n_chains);
 int launch_viterbi_team(const VitArgs& a, int em, cudaStream_t st);
 
+// ---- panel family (panel_kernels.cu): N = 32 on the FP64 tensor pipe, 8 chains per warp; opt-in (BHMM_B200_PANEL=1)
+bool panel_enabled(int N);
+void panel_shape(int* threads, int* chains_per_row);
+int panel_stats_rows(int n_chains);          // rows of `partials` (= warps) a statistics launch over n_chains writes
+bool panel_forward_ok(const FwdArgs& a, int em);
+bool panel_backward_ok(const BwdArgs& a, int em);
+int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st);
+int launch_backward_stats_panel(const BwdArgs& a, int em, cudaStream_t st);
+
 // ---- frame-parallel kernels (frame_kernels.cu)
 int launch_gaussian_pobs(const double* obs, const double* mu, const double* sigma, int N, long long rows,
                          int ignore_outliers, double* pobs, cudaStream_t st);

@@ -1,0 +1,667 @@
+// bhmm_b200/csrc/panel_kernels.cu -- N = 32 chain kernels on the FP64 tensor pipe ("panel" family).
+//
+// STATUS: written at the end of round 1 without GPU time left to run it -- compiled for sm_100a only.  The family is
+// therefore OPT-IN (environment variable BHMM_B200_PANEL=1, read once per process); without it nothing here is launched
+// and N = 32 runs on the team kernels.  tests/test_panel_cuda.py (skipped unless the variable is set) is its parity
+// test; the fragment/index algebra below is checked on the CPU by tests/test_panel_layout_cpu.py.
+//
+// One WARP walks 8 chains at once.  The 8 x 32 panel of the chains' vectors times the 32 x 32 transition matrix is
+// 32 mma.sync.m8n8k4.f64 (DMMA) per frame, with the matrix resident in registers as B fragments.  Lane (g, q),
+// g = lane / 4, q = lane % 4, belongs to chain g of the warp and owns the 8 states
+//     state(k) = 8 (k / 2) + 2 q + (k % 2),   k = 0..7,
+// which is exactly what the accumulator fragments of the four n-tiles hand it (row g, columns 8 nt + 2 q + {0, 1}).
+// The k-steps of the product are ordered so that k-step ks contracts the states {state(ks) : q = 0..3}: the A operand
+// of k-step ks is then the lane's own element k = ks of the previous frame's result -- the recursion needs no shuffle
+// and no shared memory (prototype and measurements: tools/micro/dmma_panel.cu).  A "team" in the sense of
+// team_kernels.cu is here a quad of lanes; sums over the states of a chain are two xor-shuffles.
+//
+// Unlike the team kernels the panel kernels normalise every frame like the reference does (_hidden.c:40-64, :92-108),
+// so no frame is ever lifted; divisions by a chain's sum are one reciprocal and 8 multiplications (one rounding more
+// than the reference's true divisions: 1e-16 relative, the parity bar is 1e-10).
+//
+// Replaces (reference file:line), fused exactly like team_kernels.cu:
+//   k_forward_panel32         _forward  bhmm/hidden/impl_c/_hidden.c:16-66   (+ emission: _gaussian.c:45-70 /
+//                             discrete.py:146-153 / outputmodel.py:119-131)
+//   k_backward_stats_panel32  _backward _hidden.c:69-110 + state_probabilities hidden/api.py:133-188 + state_counts
+//                             :191-211 + _compute_transition_counts _hidden.c:148-183 + the data passes of
+//                             GaussianOutputModel.estimate gaussian.py:214-272 / _update_pout _discrete.c:1-32
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int PN = 32;            // hidden states
+constexpr int PW = 4;             // warps per block
+constexpr int PCH = 8;            // chains per warp
+constexpr int PSTRIDE = 36;       // doubles per chain row of the transposition buffers: (4 q + g) mod 16 distinct per
+                                  // half warp, so the operand loads of the xi product are bank-conflict free
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// sum over the four lanes of a quad; every lane ends with the bitwise identical total
+__device__ __forceinline__ double quad_sum(double v)
+{
+    v += __shfl_xor_sync(FULL, v, 1);
+    v += __shfl_xor_sync(FULL, v, 2);
+    return v;
+}
+
+__device__ __forceinline__ int state_of(int k, int q) { return 8 * (k >> 1) + 2 * q + (k & 1); }
+
+// 8 doubles of a 32-state row, the lane's states: four 16-byte accesses
+__device__ __forceinline__ void load8(const double* __restrict__ row, int q, double (&v)[8])
+{
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const double2 x = *reinterpret_cast<const double2*>(row + 8 * nt + 2 * q);
+        v[2 * nt] = x.x;
+        v[2 * nt + 1] = x.y;
+    }
+}
+__device__ __forceinline__ void store8(double* __restrict__ row, int q, const double (&v)[8])
+{
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<double2*>(row + 8 * nt + 2 * q) = make_double2(v[2 * nt], v[2 * nt + 1]);
+}
+
+// ---- exp() of 8 arguments, evaluated stage by stage so that the 8 dependent chains interleave (same scheme and
+// constants as lane_kernels.cuh:emission_gauss, TB == 0 path): exp(x) = 2^n exp(r), n = rint(x / ln 2), |r| <= ln2 / 2,
+// degree-11 polynomial (< 1 ulp); arguments below -708 or not finite take the library exp() in a rare tail.
+__constant__ double PEXPK[13] = {
+    0x1.af632a0f7e2cep-26, 0x1.28b4101c77212p-22, 0x1.71ddf56d8deb5p-19, 0x1.a01991a10d9aep-16,
+    0x1.a01a01b1461c5p-13, 0x1.6c16c1880029fp-10, 0x1.111111110f21ep-7,  0x1.555555554f0bap-5,
+    0x1.555555555555ap-3,  0x1.0000000000011p-1,
+    1.4426950408889634074, 6.93147180369123816490e-01, 1.90821492927058770002e-10};
+
+__device__ __noinline__ double panel_slow_exp(double x) { return exp(x); }
+
+__device__ __forceinline__ void exp8(const double (&x)[8], double (&p)[8])
+{
+#ifdef PANEL_LIBM_EXP
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p[k] = exp(x[k]);
+#else
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    double t[8], r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = fma(x[k], PEXPK[10], MAGIC);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double n = t[k] - MAGIC;
+        r[k] = fma(n, -PEXPK[11], x[k]);
+        r[k] = fma(n, -PEXPK[12], r[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p[k] = fma(PEXPK[0], r[k], PEXPK[1]);
+#pragma unroll
+    for (int c = 2; c < 10; ++c) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p[k] = fma(p[k], r[k], PEXPK[c]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p[k] = fma(p[k], r[k], 1.0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p[k] = fma(p[k], r[k], 1.0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int ni = __double2loint(t[k]);
+        p[k] = __longlong_as_double(__double_as_longlong(p[k]) + ((long long)ni << 52));
+    }
+    unsigned umax = (unsigned)__double2hiint(x[0]);
+    int smax = __double2hiint(x[0]);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        umax = max(umax, (unsigned)__double2hiint(x[k]));
+        smax = max(smax, __double2hiint(x[k]));
+    }
+    if (umax > 0xC0862000u || smax > 0x40862000) {           // some x < -708, > 708 or not finite
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned hx = (unsigned)__double2hiint(x[k]);
+            if (hx >= 0xC0875000u && hx <= 0xFFF00000u) p[k] = 0.0;              // x <= -746 (or -inf): exactly zero
+            else if ((hx & 0x7fffffffu) > 0x40862000u) p[k] = panel_slow_exp(x[k]);
+        }
+    }
+#endif
+}
+
+// Raw emission input of one frame for one lane: the observation (Gaussian), or the lane's 8 table entries.
+template <int EM>
+struct Raw {
+    double v[EM == EM_GAUSS ? 1 : 8];
+    int sym;
+};
+
+template <int EM>
+__device__ __forceinline__ void raw_load(const Emission& em, long long row, int q, Raw<EM>& r)
+{
+    r.sym = 0;
+    if (EM == EM_GAUSS) {
+        r.v[0] = em.obs[row];
+    } else if (EM == EM_POBS) {
+        double t[8];
+        load8(em.pobs + row * PN, q, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r.v[EM == EM_GAUSS ? 0 : k] = t[k];
+    } else {
+        r.sym = em.sym[row];
+        double t[8];
+        load8(em.Bt + (long long)r.sym * PN, q, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r.v[EM == EM_GAUSS ? 0 : k] = t[k];
+    }
+}
+
+template <int EM>
+__device__ __forceinline__ void raw_prefetch(const Emission& em, long long row, int q)
+{
+    const void* p;
+    if (EM == EM_POBS) p = em.pobs + row * PN + 8 * q;        // the quad touches the row's two 128-byte lines
+    else if (EM == EM_GAUSS) p = em.obs + row;
+    else p = em.sym + row;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// p[k] = density of the lane's state k at this frame.  Gaussian: nrm exp(-((o - mu) isg)^2) with isg = 1 / (sqrt 2 sigma),
+// nrm = 1 / (sqrt(2 pi) sigma) (_gaussian.c:18-20 up to the rounding of the reciprocal), constants from `kc` =
+// [mu (32) | isg (32) | log nrm (32)] in shared memory.
+template <int EM>
+__device__ __forceinline__ void emission8(const Raw<EM>& r, const double* __restrict__ kc, int q, double (&p)[8])
+{
+    if (EM == EM_GAUSS) {
+        double mu[8], isg[8], lnrm[8], x[8];
+        load8(kc, q, mu);
+        load8(kc + PN, q, isg);
+        load8(kc + 2 * PN, q, lnrm);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double d = (r.v[0] - mu[k]) * isg[k];
+            x[k] = fma(-d, d, lnrm[k]);
+        }
+        exp8(x, p);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p[k] = r.v[EM == EM_GAUSS ? 0 : k];
+    }
+}
+
+// outputmodel.py:126-130: a frame whose densities are all zero becomes all one
+template <int EM>
+__device__ __forceinline__ void outlier_rule(const Emission& em, unsigned qmask, double (&p)[8])
+{
+    if (EM == EM_POBS || !em.ignore_outliers) return;
+    bool nz = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) nz = nz || (p[k] != 0.0);
+    const unsigned b = __ballot_sync(FULL, nz);
+    if ((b & qmask) == 0u) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p[k] = 1.0;
+    }
+}
+
+__device__ __forceinline__ void fill_gauss_constants(const Emission& em, double* kc)
+{
+    for (int j = threadIdx.x; j < PN; j += blockDim.x) {
+        const double sg = em.sigma[j];
+        kc[j] = em.mu[j];
+        kc[PN + j] = 1.0 / (sqrt(2.0) * sg);
+        kc[2 * PN + j] = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * sg));
+    }
+}
+
+// Running sum of log c_t as a product that is folded into the sum only when it leaves [2^-400, 2^400]: one
+// multiplication per frame instead of one log().
+struct LogAcc {
+    double ll = 0.0, prod = 1.0;
+    __device__ __forceinline__ void add(double c)
+    {
+        prod *= c;
+        if (!(prod >= 0x1p-400 && prod <= 0x1p+400)) { ll += log(prod); prod = 1.0; }
+    }
+    __device__ __forceinline__ double value() const { return ll + log(prod); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int EM>
+__global__ void __launch_bounds__(PW * 32) k_forward_panel32(const FwdArgs a)
+{
+    __shared__ __align__(16) double kc[3 * PN];
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int gw = blockIdx.x * PW + (threadIdx.x >> 5), nw = gridDim.x * PW;
+    const unsigned qmask = 0xFu << (4 * g);
+    if (EM == EM_GAUSS) fill_gauss_constants(a.em, kc);
+    // B fragments of alpha' = alpha A: k-step ks contracts state_of(ks, q), n-tile nt produces column 8 nt + g
+    double Bf[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) Bf[ks][nt] = a.A[state_of(ks, q) * PN + 8 * nt + g];
+    __syncthreads();
+
+    for (int base = gw * PCH; base < a.ch.n; base += nw * PCH) {
+        const int idx = base + g;
+        const bool have = idx < a.ch.n;
+        int c = -1, len = 0, t0 = 0, tstart = 0, mode = 0;   // mode 0: pi, 1: uniform warm-up, 2: exact vector
+        long long trow = 0;
+        if (have) {
+            c = a.ch.list ? a.ch.list[idx] : idx;
+            len = a.ch.len[c];
+            t0 = a.ch.t0[c];
+            trow = a.ch.row0[c] - t0;
+            if (t0 == 0) { tstart = 0; mode = 0; }
+            else if (a.ch.exact) { tstart = t0 - 1; mode = 2; }
+            else { tstart = max(0, t0 - (a.ch.warmv ? a.ch.warmv[c] : a.ch.warm)); mode = (tstart == 0) ? 0 : 1; }
+        }
+        const int npre = have ? (t0 - tstart) : 0;
+        const int maxpre = __reduce_max_sync(FULL, npre);
+        const int total = maxpre + __reduce_max_sync(FULL, len);
+        const int tend = t0 + len;
+
+        double av[8];                                      // normalised alpha of the previous frame, the lane's states
+#pragma unroll
+        for (int k = 0; k < 8; ++k) av[k] = 0.0;
+        if (have && mode == 2) load8(a.hand_end + (long long)(c - 1) * PN, q, av);
+        LogAcc acc;
+
+        auto fetch = [&](int s, Raw<EM>& r) {
+            int t = t0 - maxpre + s;
+            t = min(max(t, tstart + (mode == 2 ? 1 : 0)), tend - 1);
+            if (have) raw_load<EM>(a.em, trow + t, q, r);
+            else {
+                r.sym = 0;
+#pragma unroll
+                for (int k = 0; k < (EM == EM_GAUSS ? 1 : 8); ++k) r.v[k] = 0.0;
+            }
+        };
+        Raw<EM> raw_next;
+        fetch(0, raw_next);
+
+        for (int s = 0; s < total; ++s) {
+            const int t = t0 - maxpre + s;
+            const bool on = have && t >= tstart && t < tend;
+            const bool init = on && t == tstart;
+            const Raw<EM> raw = raw_next;
+            fetch(s + 1, raw_next);
+            if (have && t + 48 < tend) raw_prefetch<EM>(a.em, trow + max(t, tstart) + 48, q);
+
+            double p[8];
+            emission8<EM>(raw, kc, q, p);
+            outlier_rule<EM>(a.em, qmask, p);
+
+            double d[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) d[k] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma(d[2 * nt], d[2 * nt + 1], av[ks], Bf[ks][nt]);
+
+            double v[8];
+            if (init) {
+                if (mode == 0) {
+                    double pi8[8];
+                    load8(a.pi, q, pi8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = pi8[k] * p[k];
+                } else if (mode == 1) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = p[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = av[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = on ? d[k] * p[k] : 0.0;
+            }
+            const double part = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            const double csum = quad_sum(part);
+            if (on) {
+                const double rc = (csum != 0.0) ? 1.0 / csum : 1.0;      // _hidden.c:31-34, :58-61: divide iff c != 0
+#pragma unroll
+                for (int k = 0; k < 8; ++k) av[k] = v[k] * rc;
+                if (t >= t0) {
+                    if (a.alpha) store8(a.alpha + (trow + t) * PN, q, av);
+                    acc.add(csum);
+                    if (t == tend - 1) store8(a.hand_end + (long long)c * PN, q, av);
+                } else if (t == t0 - 1) {
+                    store8(a.hand_used + (long long)c * PN, q, av);
+                }
+            }
+        }
+        if (have && q == 0) a.chain_ll[c] = acc.value();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward + sufficient statistics (fused E-step)
+// ------------------------------------------------------------------------------------------------
+// Frames f = fstart .. t0+1 downwards; at frame f the lane holds the NORMALISED beta_f of its chain (bn, sum 1).
+//   w_j = p_{f,j} bn_j;   d_i = sum_j A_ij w_j  (32 DMMA, B fragments of A^T);   beta_{f-1} = d / sum d
+//   gamma_{f-1,i} = alpha_{f-1,i} d_i / S,  S = sum_i alpha_{f-1,i} d_i
+//   xi_{f-1}[i][j] = alpha_{f-1,i} A_ij w_j / S   (_hidden.c:168-180: S is the sum of the unnormalised xi)
+// The A-independent part X[i][j] += sum over the warp's 8 chains of u_i w_j, u = alpha_{f-1} / S, is a second 32 x 32 x 8
+// product: 4 x 4 output tiles, two k-steps over the chains, operands transposed through shared memory (each lane needs
+// element [chain 4 kk + q][state 8 t + g] of U and of W).  launch_finalize_stats multiplies by A.
+template <int EM>
+__global__ void __launch_bounds__(PW * 32) k_backward_stats_panel32(const BwdArgs a)
+{
+    __shared__ __align__(16) double kc[3 * PN];
+    __shared__ __align__(16) double tb[PW][2][PCH * PSTRIDE];      // per warp: U, W
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, wib = threadIdx.x >> 5;
+    const int gw = blockIdx.x * PW + wib, nw = gridDim.x * PW;
+    const unsigned qmask = 0xFu << (4 * g);
+    double* Us = tb[wib][0];
+    double* Ws = tb[wib][1];
+    if (EM == EM_GAUSS) fill_gauss_constants(a.em, kc);
+    // B fragments of d = A w: contraction index j = state_of(ks, q), output column i = 8 nt + g
+    double Bt[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) Bt[ks][nt] = a.A[(8 * nt + g) * PN + state_of(ks, q)];
+    double X[4][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { X[mt][nt][0] = 0.0; X[mt][nt][1] = 0.0; }
+    double st_g[8], st_gd[8], st_gdd[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { st_g[k] = 0.0; st_gd[k] = 0.0; st_gdd[k] = 0.0; }
+    // this warp's row of partial statistics: [X (N*N) | gamma0 (N) | sum gamma (N) | sum gamma d (N) | sum gamma d^2 (N)]
+    const int nstat = PN * PN + 4 * PN;
+    double* out = a.partials + (long long)gw * nstat;
+    out[PN * PN + lane] = 0.0;                             // gamma0 is accumulated with atomics by this warp's lanes
+    __syncthreads();
+
+    for (int base = gw * PCH; base < a.ch.n; base += nw * PCH) {
+        const int idx = base + g;
+        const bool have = idx < a.ch.n;
+        int c = -1, len = 0, t0 = 0, T = 0, e = 0, fstart = 0, mode = 0;   // mode 0: uniform (exact or warm-up), 2: exact vector
+        bool virt = false;                                                  // the chain ends its trajectory
+        long long trow = 0;
+        if (have) {
+            c = a.ch.list ? a.ch.list[idx] : idx;
+            len = a.ch.len[c];
+            t0 = a.ch.t0[c];
+            T = a.ch.T[c];
+            trow = a.ch.row0[c] - t0;
+            e = t0 + len;
+            if (e >= T) { virt = true; fstart = T; }
+            else if (a.ch.exact) { fstart = e; mode = 2; }
+            else { fstart = min(T - 1, e + (a.ch.warmv ? a.ch.warmv[c] : a.ch.warm) - 1); }
+        }
+        const int flast = t0 + 1;                           // step f emits frame f-1
+        const int npre = have ? (fstart - (e - 1)) : 0;
+        const int maxpre = __reduce_max_sync(FULL, npre);
+        const int total = maxpre + __reduce_max_sync(FULL, have ? (e - flast) : 0);
+
+        double bn[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bn[k] = 1.0 / PN;      // beta_{T-1} = 1/N (_hidden.c:76-77), also the warm-up start
+        if (have && mode == 2) load8(a.hand_end + (long long)(c + 1) * PN, q, bn);
+
+        auto frame_of = [&](int s) -> int { return (e - 1) + maxpre - s; };
+        auto fetch = [&](int s, Raw<EM>& r) {
+            const int f = min(max(frame_of(s), t0), T - 1);
+            if (have) raw_load<EM>(a.em, trow + f, q, r);
+            else {
+                r.sym = 0;
+#pragma unroll
+                for (int k = 0; k < (EM == EM_GAUSS ? 1 : 8); ++k) r.v[k] = 0.0;
+            }
+        };
+        auto fetch_alpha = [&](int s, double (&al)[8]) {
+            const int f = min(max(frame_of(s) - 1, t0), e - 1);
+            if (have) load8(a.alpha + (trow + f) * PN, q, al);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) al[k] = 0.0;
+            }
+        };
+        Raw<EM> raw_next;
+        double al_next[8];
+        fetch(0, raw_next);
+        fetch_alpha(0, al_next);
+
+        for (int s = 0; s < total; ++s) {
+            const int f = frame_of(s);
+            const bool on = have && f <= fstart && f >= flast;
+            const bool isvirt = on && virt && f == T;       // virtual frame T: beta_{T-1} proportional to one
+            const Raw<EM> raw = raw_next;
+            double al[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) al[k] = al_next[k];
+            fetch(s + 1, raw_next);                         // frame f-1: also the observation / symbol of the emitted frame
+            fetch_alpha(s + 1, al_next);
+            if (have && f - 48 > t0) {
+                raw_prefetch<EM>(a.em, trow + min(f, T - 1) - 48, q);
+                if (f - 48 < e) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.alpha + (trow + f - 48) * PN + 8 * q));
+            }
+
+            double p[8];
+            emission8<EM>(raw, kc, q, p);
+            outlier_rule<EM>(a.em, qmask, p);
+
+            double w[8], d[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { w[k] = (on && !isvirt) ? p[k] * bn[k] : 0.0; d[k] = 0.0; }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma(d[2 * nt], d[2 * nt + 1], w[ks], Bt[ks][nt]);
+            if (isvirt) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) d[k] = 1.0;
+            }
+            if (on && !isvirt && f == e) store8(a.hand_used + (long long)c * PN, q, bn);
+
+            const bool emit = on && (f - 1) < e;            // f-1 >= t0 holds because f >= flast
+            const bool xi = emit && !isvirt;
+            double gq[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gq[k] = emit ? al[k] * d[k] : 0.0;
+            const double S = quad_sum(((gq[0] + gq[1]) + (gq[2] + gq[3])) + ((gq[4] + gq[5]) + (gq[6] + gq[7])));
+            const double sbn = quad_sum(((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7])));
+            const double rS = 1.0 / S;
+
+            // ---- publish u = alpha_{f-1} / S and w for the xi product (zeros from chains that do not emit)
+            const bool any_xi = __any_sync(FULL, xi);
+            if (any_xi) {
+                double u[8], wz[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { u[k] = xi ? al[k] * rS : 0.0; wz[k] = xi ? w[k] : 0.0; }
+                store8(Us + g * PSTRIDE, q, u);
+                store8(Ws + g * PSTRIDE, q, wz);
+            }
+            __syncwarp();
+
+            if (emit) {
+                const long long row = trow + (f - 1);
+                double gam[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { gam[k] = gq[k] * rS; st_g[k] += gam[k]; }
+                if (f - 1 == 0) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) atomicAdd(out + PN * PN + state_of(k, q), gam[k]);
+                }
+                if (EM == EM_GAUSS) {
+                    double mu[8];
+                    load8(kc, q, mu);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const double dd = raw_next.v[0] - mu[k];
+                        st_gd[k] = fma(gam[k], dd, st_gd[k]);
+                        st_gdd[k] = fma(gam[k], dd * dd, st_gdd[k]);
+                    }
+                }
+                if (EM == EM_DISC && a.Bnum) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) atomicAdd(a.Bnum + (long long)state_of(k, q) * a.em.M + raw_next.sym, gam[k]);
+                }
+                if (a.gamma) store8(a.gamma + row * PN, q, gam);
+                if (f - 1 == t0 && t0 > 0) {
+                    const double r2 = (sbn != 0.0) ? 1.0 / sbn : 1.0;
+                    double hb[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) hb[k] = d[k] * r2;
+                    store8(a.hand_end + (long long)c * PN, q, hb);
+                }
+            }
+            if (on) {
+                const double r2 = (sbn != 0.0) ? 1.0 / sbn : 1.0;          // _hidden.c:104-107: divide iff the sum != 0
+#pragma unroll
+                for (int k = 0; k < 8; ++k) bn[k] = d[k] * r2;
+            }
+
+            // ---- X += U^T W over the warp's chains
+            if (any_xi) {
+                double ua[2][4], wb[2][4];
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        ua[kk][t] = Us[(4 * kk + q) * PSTRIDE + 8 * t + g];
+                        wb[kk][t] = Ws[(4 * kk + q) * PSTRIDE + 8 * t + g];
+                    }
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) dmma(X[mt][nt][0], X[mt][nt][1], ua[kk][mt], wb[kk][nt]);
+            }
+            __syncwarp();                                   // the buffers are rewritten by the next step
+        }
+    }
+
+    // ---- this warp's partial statistics
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+            *reinterpret_cast<double2*>(out + (8 * mt + g) * PN + 8 * nt + 2 * q) = make_double2(X[mt][nt][0], X[mt][nt][1]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        // lanes with equal q own the same states: sum over g = lane bits 2..4
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+            st_g[k] += __shfl_xor_sync(FULL, st_g[k], off);
+            st_gd[k] += __shfl_xor_sync(FULL, st_gd[k], off);
+            st_gdd[k] += __shfl_xor_sync(FULL, st_gdd[k], off);
+        }
+    }
+    if (g == 0) {
+        store8(out + PN * PN + PN, q, st_g);
+        store8(out + PN * PN + 2 * PN, q, st_gd);
+        store8(out + PN * PN + 3 * PN, q, st_gdd);
+    }
+}
+
+int panel_sms()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// resident blocks per SM of the statistics kernel, the more register-hungry of the two (sizes one wave of chains)
+int panel_blocks_per_sm()
+{
+    static int per = 0;
+    if (per == 0) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_panel32<EM_GAUSS>, PW * 32, 0) != cudaSuccess
+            || v <= 0) v = 2;
+        per = v;
+    }
+    return per;
+}
+
+int panel_blocks(int n_chains)
+{
+    const long long groups = ((long long)n_chains + PW * PCH - 1) / (PW * PCH);
+    const long long cap = (long long)panel_sms() * panel_blocks_per_sm();
+    return (int)std::max(1LL, std::min(groups, cap));
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+bool panel_enabled(int N)
+{
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("BHMM_B200_PANEL");
+        on = (e && strcmp(e, "1") == 0) ? 1 : 0;
+    }
+    return on == 1 && N == PN;
+}
+
+void panel_shape(int* threads, int* chains_per_block)
+{
+    *threads = PW * 32;
+    *chains_per_block = PCH;     // per partial-statistics row (= warp): backward_stats_grid() counts warps for this family
+}
+
+int panel_stats_rows(int n_chains) { return panel_blocks(n_chains) * PW; }
+
+bool panel_forward_ok(const FwdArgs& a, int em)
+{
+    bool ok = aligned16(a.A) && aligned16(a.pi) && aligned16(a.hand_end) && aligned16(a.hand_used) && (!a.alpha || aligned16(a.alpha));
+    if (em == EM_POBS) ok = ok && aligned16(a.em.pobs);
+    if (em == EM_DISC) ok = ok && aligned16(a.em.Bt);
+    return ok;
+}
+
+bool panel_backward_ok(const BwdArgs& a, int em)
+{
+    bool ok = aligned16(a.A) && aligned16(a.alpha) && aligned16(a.partials) && aligned16(a.hand_end) && aligned16(a.hand_used)
+              && (!a.gamma || aligned16(a.gamma)) && a.grid > 0 && a.grid % PW == 0;
+    if (em == EM_POBS) ok = ok && aligned16(a.em.pobs);
+    if (em == EM_DISC) ok = ok && aligned16(a.em.Bt);
+    return ok;
+}
+
+int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st)
+{
+    if (a.N != PN) return BHMM_ERR_UNSUPPORTED;
+    if (a.ch.n <= 0) return BHMM_OK;
+    const int grid = panel_blocks(a.ch.n);
+    switch (em) {
+        case EM_POBS: k_forward_panel32<EM_POBS><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
+        case EM_GAUSS: k_forward_panel32<EM_GAUSS><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
+        case EM_DISC: k_forward_panel32<EM_DISC><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
+    }
+    return BHMM_ERR_INVALID;
+}
+
+// a.grid = rows of `partials` = warps of the launch (panel_stats_rows); every warp writes its row, chains or not
+int launch_backward_stats_panel(const BwdArgs& a, int em, cudaStream_t st)
+{
+    if (a.N != PN) return BHMM_ERR_UNSUPPORTED;
+    const int grid = a.grid / PW;
+    switch (em) {
+        case EM_POBS: k_backward_stats_panel32<EM_POBS><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
+        case EM_GAUSS: k_backward_stats_panel32<EM_GAUSS><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
+        case EM_DISC: k_backward_stats_panel32<EM_DISC><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
+    }
+    return BHMM_ERR_INVALID;
+}

@@ -614,17 +614,24 @@ int persistent_grid(int groups, int threads, size_t smem)
 
 }  // namespace
 
-void team_shape(int N, int* threads, int* cpb)
+static void team_shape_raw(int N, int* threads, int* cpb)
 {
     if (N <= 32) { *threads = 32; *cpb = 32 / N; }
     else { *threads = ((N + 31) / 32) * 32; *cpb = 1; }
+}
+
+// what the planners see: chains per row of partial statistics (a block here, a warp in the opt-in panel family)
+void team_shape(int N, int* threads, int* cpb)
+{
+    if (panel_enabled(N)) { panel_shape(threads, cpb); return; }
+    team_shape_raw(N, threads, cpb);
 }
 
 template <int EM>
 static int launch_forward_em(const FwdArgs& a, cudaStream_t st)
 {
     int threads, cpb;
-    team_shape(a.N, &threads, &cpb);
+    team_shape_raw(a.N, &threads, &cpb);
     FwdArgs b = a;
     b.cpb = cpb;
     const size_t smem = sizeof(double) * ((size_t)a.N * a.N + 2 * (size_t)cpb * a.N);
@@ -640,6 +647,7 @@ static int launch_forward_em(const FwdArgs& a, cudaStream_t st)
 int launch_forward_team(const FwdArgs& a, int em, cudaStream_t st)
 {
     if (a.N < 1 || a.N > 1024) return BHMM_ERR_UNSUPPORTED;
+    if (panel_enabled(a.N) && panel_forward_ok(a, em)) return launch_forward_panel(a, em, st);
     switch (em) {
         case EM_POBS: return launch_forward_em<EM_POBS>(a, st);
         case EM_GAUSS: return launch_forward_em<EM_GAUSS>(a, st);
@@ -650,8 +658,9 @@ int launch_forward_team(const FwdArgs& a, int em, cudaStream_t st)
 
 int backward_stats_grid(int N, int n_chains)
 {
+    if (panel_enabled(N)) return panel_stats_rows(n_chains);
     int threads, cpb;
-    team_shape(N, &threads, &cpb);
+    team_shape_raw(N, &threads, &cpb);
     const size_t smem = sizeof(double) * ((size_t)N * N + 6 * (size_t)cpb * N + (size_t)cpb * N * N);
     return persistent_grid((n_chains + cpb - 1) / cpb, threads, smem);
 }
@@ -660,7 +669,7 @@ template <int EM, bool STATS>
 static int launch_backward_em(const BwdArgs& a, cudaStream_t st)
 {
     int threads, cpb;
-    team_shape(a.N, &threads, &cpb);
+    team_shape_raw(a.N, &threads, &cpb);
     BwdArgs b = a;
     b.cpb = cpb;
     size_t smem = sizeof(double) * ((size_t)a.N * a.N + 6 * (size_t)cpb * a.N);
@@ -681,6 +690,8 @@ static int launch_backward_em(const BwdArgs& a, cudaStream_t st)
 int launch_backward_team(const BwdArgs& a, int em, bool stats, cudaStream_t st)
 {
     if (a.N < 1 || a.N > 1024) return BHMM_ERR_UNSUPPORTED;
+    // (a launch the panel kernel cannot take -- an unaligned caller buffer -- runs on the team kernel with a.grid blocks)
+    if (stats && panel_enabled(a.N) && panel_backward_ok(a, em)) return launch_backward_stats_panel(a, em, st);
     if (stats) {
         switch (em) {
             case EM_POBS: return launch_backward_em<EM_POBS, true>(a, st);
@@ -701,7 +712,7 @@ template <int EM>
 static int launch_viterbi_em(const VitArgs& a, cudaStream_t st)
 {
     int threads, cpb;
-    team_shape(a.N, &threads, &cpb);
+    team_shape_raw(a.N, &threads, &cpb);
     VitArgs b = a;
     b.cpb = cpb;
     const size_t smem = sizeof(double) * ((size_t)a.N * a.N + 2 * (size_t)cpb * a.N);

@@ -1,0 +1,21 @@
+"""Parity of the opt-in N = 32 panel kernels (BHMM_B200_PANEL=1, panel_kernels.cu) against the oracle.
+
+The kernels were written at the end of round 1 with no GPU time left to run them, so this test only runs when
+BHMM_B200_PANEL_TEST=1 is set (the family is not selected by default either).  The library reads BHMM_B200_PANEL once per
+process, hence the child process; `timeout` bounds a possible hang."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(os.environ.get('BHMM_B200_PANEL_TEST') != '1', reason='panel kernels are opt-in until verified on a B200')
+def test_panel_kernels_match_oracle():
+    r = subprocess.run(['timeout', '600', sys.executable, os.path.join(ROOT, 'tools', 'panel_check.py'), '--quick'],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout[-4000:]

@@ -1,0 +1,151 @@
+"""Parity and timing of the opt-in N = 32 panel kernels (bhmm_b200/csrc/panel_kernels.cu) on a B200.
+
+    timeout 900 python tools/panel_check.py            # parity against the oracle, then timing next to the team kernels
+    timeout 600 python tools/panel_check.py --quick    # parity only (what tests/test_panel_cuda.py runs)
+
+The panel family is selected by BHMM_B200_PANEL=1, which the library reads once per process; this script sets it for
+itself and times the team kernels in a child process without it.  Every GPU call sits under the caller's `timeout`: the
+kernels had never run on hardware when they were written (end of round 1), so treat a hang as a possibility.
+"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+CHILD = '--team-child' in sys.argv
+if not CHILD:
+    os.environ['BHMM_B200_PANEL'] = '1'
+else:
+    os.environ.pop('BHMM_B200_PANEL', None)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+from bhmm_b200.engine import TrajectoryBatch, unpack_stats   # noqa: E402
+from bhmm_b200.util import testsystems as ts                  # noqa: E402
+
+RTOL = 1e-10
+failures = []
+
+
+def check(name, ok, detail=''):
+    print('%-58s %s %s' % (name, 'ok' if ok else 'FAIL', detail), flush=True)
+    if not ok:
+        failures.append(name)
+
+
+def close(a, b, rtol, atol=0.0):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return bool(np.all(np.abs(a - b) <= rtol * np.abs(b) + atol)), float(np.max(np.abs(a - b) / (np.abs(b) + 1e-300)))
+
+
+def timeit(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def timing():
+    N, K, T = 32, 64, 100000
+    pi, A, means, sigmas, O, S = ts.gaussian_observations(N, K, T, seed=5)
+    b = TrajectoryBatch(list(O), N)
+    b.set_profiling(True)
+    ms = timeit(lambda: b.estep_gaussian(A, pi, means, sigmas))
+    st = unpack_stats(b.estep_gaussian(A, pi, means, sigmas).cpu().numpy(), N)
+    print('%s N=32 gaussian K=%d T=%d: E-step %.2f ms -> %.3f G frames/s; kernels %s; info %s; loglik %.10e'
+          % ('team ' if CHILD else 'panel', K, T, ms, K * T / ms / 1e6, b.kernel_ms(), b.info(), st['loglik']), flush=True)
+    b.close()
+
+
+def parity():
+    from oracle.oracle import Oracle
+    import bhmm_b200.hidden as hidden
+    orc = Oracle('port')
+    N = 32
+    rng = np.random.default_rng(41)
+    X = rng.random((N, N)) ** 2 + 1e-3
+    A = X / X.sum(axis=1)[:, None]
+    pi = rng.random(N) + 0.01
+    pi /= pi.sum()
+    means, sigmas = np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
+    # ---- Gaussian E-step: ragged trajectories (one shorter than a chunk, one of a single frame), three chunkings
+    obs = []
+    for Tk in (1500, 1333, 700, 40, 1, 977, 2000, 333, 1200, 64):
+        s = rng.integers(0, N, size=Tk)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(Tk))
+    ref = orc.estep_gaussian(obs, A, pi, means, sigmas)
+    wdd = np.zeros(N)
+    wd = np.zeros(N)
+    for g, o in zip(ref['gammas'], obs):
+        d = o[:, None] - means[None, :]
+        wd += (g * d).sum(axis=0)
+        wdd += (g * d * d).sum(axis=0)
+    for chunk, warm in ((0, 0), (214, 0), (97, 150), (5000, 10)):
+        b = TrajectoryBatch(obs, N, chunk=chunk, warm=warm)
+        gam = torch.zeros((b.rows, N), dtype=torch.float64, device='cuda')
+        st = unpack_stats(b.estep_gaussian(A, pi, means, sigmas, gamma_out=gam).cpu().numpy(), N)
+        tag = 'gaussian chunk=%d warm=%d: ' % (chunk, warm)
+        check(tag + 'loglik', abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik']), '%.12e vs %.12e' % (st['loglik'], ref['loglik']))
+        for key, r, rt, at in (('gamma0', ref['gamma0'], RTOL, 1e-300), ('C', ref['C'], 1e-9, 1e-12 * ref['C'].max()),
+                               ('wsum', ref['wsum'], RTOL, 0.0), ('wd', wd, 1e-9, 1e-9 * np.abs(wd).max()), ('wdd', wdd, 1e-9, 0.0)):
+            ok, worst = close(st[key], r, rt, at)
+            check(tag + key, ok, 'worst rel %.2e' % worst)
+        ok, worst = close(gam.cpu().numpy(), np.vstack(ref['gammas']), 1e-9, 1e-14)
+        check(tag + 'gamma rows', ok, 'worst rel %.2e' % worst)
+        print('    info', b.info(), flush=True)
+        b.close()
+    # ---- outlier rule: an observation 60 sigma away from every state, with and without ignore_outliers
+    o2 = [np.concatenate([obs[0][:300], [400.0], obs[0][300:600]])]
+    b = TrajectoryBatch(o2, N, chunk=100, warm=0)
+    st = unpack_stats(b.estep_gaussian(A, pi, means, sigmas, ignore_outliers=True).cpu().numpy(), N)
+    r2 = orc.estep_gaussian(o2, A, pi, means, sigmas, ignore_outliers=True)
+    check('outlier frame (ignored): loglik', abs(st['loglik'] - r2['loglik']) <= RTOL * abs(r2['loglik']))
+    ok, worst = close(st['C'], r2['C'], 1e-9, 1e-12)
+    check('outlier frame (ignored): C', ok, 'worst rel %.2e' % worst)
+    b.close()
+    # ---- discrete E-step
+    M = 50
+    B = rng.random((N, M)) ** 3 + 1e-4
+    B /= B.sum(axis=1)[:, None]
+    sym = [rng.integers(0, M, size=Tk).astype(np.int32) for Tk in (1800, 1234, 600, 17)]
+    b = TrajectoryBatch(sym, N, chunk=300, warm=0)
+    stats, Bnum = b.estep_discrete(A, pi, B)
+    st = unpack_stats(stats.cpu().numpy(), N)
+    rd = orc.estep_discrete(sym, A, pi, B)
+    check('discrete: loglik', abs(st['loglik'] - rd['loglik']) <= RTOL * abs(rd['loglik']))
+    for key, got, r in (('C', st['C'], rd['C']), ('gamma0', st['gamma0'], rd['gamma0']), ('Bnum', Bnum.cpu().numpy(), rd['Bnum'])):
+        ok, worst = close(got, r, 1e-9, 1e-13)
+        check('discrete: ' + key, ok, 'worst rel %.2e' % worst)
+    b.close()
+    # ---- literal API: forward over a caller's p_obs table (EM_POBS) and the Gibbs sweep's filter
+    pobs = orc.gaussian_p_obs(obs[0], means, sigmas)
+    lp, alpha = hidden.forward(A, pobs, pi)
+    lp_ref, alpha_ref = orc.forward(A, pobs, pi)
+    check('hidden.forward N=32: logprob', abs(lp - lp_ref) <= RTOL * abs(lp_ref))
+    check('hidden.forward N=32: alpha', float(np.max(np.abs(alpha - alpha_ref))) <= 1e-10)
+    b = TrajectoryBatch(obs, N, chunk=214, warm=0)
+    path, counts, sums, ll = b.gibbs_gaussian(A, pi, means, sigmas, seed=7, sweep=0)
+    check('gibbs sweep N=32: loglik of the filter', abs(ll - ref['loglik']) <= RTOL * abs(ref['loglik']))
+    b.close()
+
+
+if __name__ == '__main__':
+    assert torch.cuda.is_available(), 'needs a CUDA device'
+    if CHILD:
+        timing()
+        sys.exit(0)
+    t0 = time.time()
+    parity()
+    print('parity: %d failure(s) in %.1f s' % (len(failures), time.time() - t0), flush=True)
+    if '--quick' not in sys.argv and not failures:
+        timing()
+        subprocess.run([sys.executable, os.path.abspath(__file__), '--team-child'], timeout=600)
+    sys.exit(1 if failures else 0)
