@@ -41,10 +41,24 @@ constexpr int PSTRIDE = 36;       // doubles per chain row of the transposition 
                                   // half warp, so the operand loads of the xi product are bank-conflict free
 constexpr unsigned FULL = 0xffffffffu;
 
+// PANEL_HOST_EMU: the kernels' source compiled for the CPU by tests/emu (every CUDA thread a fiber, collectives emulated)
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 {
+#ifdef PANEL_HOST_EMU
+    emu_dmma(d0, d1, a, b);
+#else
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+#endif
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+#ifdef PANEL_HOST_EMU
+    (void)*reinterpret_cast<const volatile char*>(p);       // the emulation reads the byte: a stray address faults
+#else
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
 }
 
 // sum over the four lanes of a quad; every lane ends with the bitwise identical total
@@ -168,7 +182,7 @@ __device__ __forceinline__ void raw_prefetch(const Emission& em, long long row, 
     if (EM == EM_POBS) p = em.pobs + row * PN + 8 * q;        // the quad touches the row's two 128-byte lines
     else if (EM == EM_GAUSS) p = em.obs + row;
     else p = em.sym + row;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    prefetch_l1(p);
 }
 
 // p[k] = density of the lane's state k at this frame.  Gaussian: nrm exp(-((o - mu) isg)^2) with isg = 1 / (sqrt 2 sigma),
@@ -448,7 +462,7 @@ __global__ void __launch_bounds__(PW * 32) k_backward_stats_panel32(const BwdArg
             fetch_alpha(s + 1, al_next);
             if (have && f - 48 > t0) {
                 raw_prefetch<EM>(a.em, trow + min(f, T - 1) - 48, q);
-                if (f - 48 < e) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.alpha + (trow + f - 48) * PN + 8 * q));
+                if (f - 48 < e) prefetch_l1(a.alpha + (trow + f - 48) * PN + 8 * q);
             }
 
             double p[8];
@@ -570,6 +584,7 @@ __global__ void __launch_bounds__(PW * 32) k_backward_stats_panel32(const BwdArg
     }
 }
 
+#ifndef PANEL_HOST_EMU
 int panel_sms()
 {
     static int n = 0;
@@ -602,8 +617,11 @@ int panel_blocks(int n_chains)
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+#endif   // PANEL_HOST_EMU
 
 }  // namespace
+
+#ifndef PANEL_HOST_EMU
 
 bool panel_enabled(int N)
 {
@@ -665,3 +683,4 @@ int launch_backward_stats_panel(const BwdArgs& a, int em, cudaStream_t st)
     }
     return BHMM_ERR_INVALID;
 }
+#endif   // PANEL_HOST_EMU

@@ -1,0 +1,70 @@
+// tests/emu/panel_emu.cpp -- the panel kernels' SOURCE (bhmm_b200/csrc/panel_kernels.cu) compiled for the CPU on top of
+// warp_emu.h, exported with a flat C interface for tests/test_panel_emulated_cpu.py.  Test infrastructure only.
+//   g++ -O1 -std=c++17 -shared -fPIC -I/usr/local/cuda/include -o panel_emu.so panel_emu.cpp
+#define PANEL_HOST_EMU 1
+#include "warp_emu.h"
+
+#include "../../bhmm_b200/csrc/panel_kernels.cu"
+
+namespace {
+
+Chains make_chains(const long long* row0, const int* len, const int* t0, const int* T, const int* list, int n_run, int warm,
+                   const int* warmv, int exact)
+{
+    Chains ch{};
+    ch.row0 = row0; ch.len = len; ch.t0 = t0; ch.T = T; ch.list = list; ch.n = n_run; ch.warm = warm; ch.warmv = warmv;
+    ch.exact = exact;
+    return ch;
+}
+
+Emission make_emission(const double* pobs, const double* obs, const int* sym, const double* mu, const double* sigma,
+                       const double* Bt, int M, int ignore_outliers)
+{
+    Emission em{};
+    em.pobs = pobs; em.obs = obs; em.sym = sym; em.mu = mu; em.sigma = sigma; em.Bt = Bt; em.M = M;
+    em.ignore_outliers = ignore_outliers;
+    return em;
+}
+
+}  // namespace
+
+extern "C" int panel_emu_warps_per_block() { return PW; }
+
+extern "C" int panel_emu_forward(int em_kind, int grid, const long long* row0, const int* len, const int* t0, const int* T,
+                                 const int* list, int n_run, int warm, const int* warmv, int exact, const double* pobs,
+                                 const double* obs, const int* sym, const double* mu, const double* sigma, const double* Bt,
+                                 int M, int ignore_outliers, const double* A, const double* pi, double* alpha,
+                                 double* chain_ll, double* hand_used, double* hand_end)
+{
+    FwdArgs a{};
+    a.ch = make_chains(row0, len, t0, T, list, n_run, warm, warmv, exact);
+    a.em = make_emission(pobs, obs, sym, mu, sigma, Bt, M, ignore_outliers);
+    a.N = PN; a.A = A; a.pi = pi; a.alpha = alpha; a.chain_ll = chain_ll; a.hand_used = hand_used; a.hand_end = hand_end;
+    switch (em_kind) {
+        case EM_POBS: emu::launch(grid, PW * 32, [&] { k_forward_panel32<EM_POBS>(a); }); return 0;
+        case EM_GAUSS: emu::launch(grid, PW * 32, [&] { k_forward_panel32<EM_GAUSS>(a); }); return 0;
+        case EM_DISC: emu::launch(grid, PW * 32, [&] { k_forward_panel32<EM_DISC>(a); }); return 0;
+    }
+    return 1;
+}
+
+// partials: (grid * PW, 32*32 + 4*32)
+extern "C" int panel_emu_backward_stats(int em_kind, int grid, const long long* row0, const int* len, const int* t0,
+                                        const int* T, const int* list, int n_run, int warm, const int* warmv, int exact,
+                                        const double* pobs, const double* obs, const int* sym, const double* mu,
+                                        const double* sigma, const double* Bt, int M, int ignore_outliers, const double* A,
+                                        const double* alpha, double* gamma, double* Bnum, double* partials,
+                                        double* hand_used, double* hand_end)
+{
+    BwdArgs a{};
+    a.ch = make_chains(row0, len, t0, T, list, n_run, warm, warmv, exact);
+    a.em = make_emission(pobs, obs, sym, mu, sigma, Bt, M, ignore_outliers);
+    a.N = PN; a.grid = grid * PW; a.A = A; a.alpha = alpha; a.gamma = gamma; a.Bnum = Bnum; a.partials = partials;
+    a.hand_used = hand_used; a.hand_end = hand_end;
+    switch (em_kind) {
+        case EM_POBS: emu::launch(grid, PW * 32, [&] { k_backward_stats_panel32<EM_POBS>(a); }); return 0;
+        case EM_GAUSS: emu::launch(grid, PW * 32, [&] { k_backward_stats_panel32<EM_GAUSS>(a); }); return 0;
+        case EM_DISC: emu::launch(grid, PW * 32, [&] { k_backward_stats_panel32<EM_DISC>(a); }); return 0;
+    }
+    return 1;
+}

@@ -1,0 +1,254 @@
+"""The panel kernels' actual CUDA source (bhmm_b200/csrc/panel_kernels.cu) executed on the CPU by tests/emu/warp_emu.h
+(every CUDA thread a fiber, warp collectives and mma.sync.m8n8k4.f64 emulated from their PTX definitions) and compared
+with a plain scaled forward-backward on whole trajectories (the algorithm of bhmm/hidden/impl_c/_hidden.c:16-183).
+
+Written because the kernels could not be run on a GPU in the round they were written in: this executes their control
+flow, indexing and collectives for real -- several blocks, partially filled warps, the persistent stride loop, warm-up
+and exact (fix-up) starts, ragged trajectories, the three emission kinds, the outlier rule -- and would abort on a
+divergent collective (a hang on hardware).  What it cannot show: race conditions between warps, ptxas behaviour, speed.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, 'emu')
+PN = 32
+EM_POBS, EM_GAUSS, EM_DISC = 0, 1, 2
+
+
+@pytest.fixture(scope='module')
+def emu():
+    so = os.path.join(EMU, 'panel_emu.so')
+    deps = [os.path.join(EMU, 'panel_emu.cpp'), os.path.join(EMU, 'warp_emu.h'),
+            os.path.join(HERE, '..', 'bhmm_b200', 'csrc', 'panel_kernels.cu'), os.path.join(HERE, '..', 'bhmm_b200', 'csrc', 'kernels.h'),
+            os.path.join(HERE, '..', 'bhmm_b200', 'csrc', 'common.cuh')]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+        if not os.path.exists(os.path.join(cuda_inc, 'cuda_runtime.h')):
+            pytest.skip('CUDA headers not found')
+        subprocess.run(['g++', '-O1', '-std=c++17', '-shared', '-fPIC', '-w', '-I' + cuda_inc, '-o', so,
+                        os.path.join(EMU, 'panel_emu.cpp')], check=True)
+    return C.CDLL(so)
+
+
+def gauss(o, mu, sigma):
+    return np.exp(-0.5 * ((o - mu) / sigma) ** 2) / (np.sqrt(2 * np.pi) * sigma)
+
+
+def plain_estep(ps, A, pi):
+    """ps: list of (T,N) emission tables.  Per-frame normalised forward-backward, gamma, xi counts."""
+    N = len(pi)
+    out = dict(alpha=[], beta=[], gamma=[], ll=0.0, C=np.zeros((N, N)), g0=np.zeros(N))
+    for p in ps:
+        T = len(p)
+        al, be = np.zeros((T, N)), np.zeros((T, N))
+        for t in range(T):
+            v = pi * p[0] if t == 0 else al[t - 1].dot(A) * p[t]
+            out['ll'] += np.log(v.sum())
+            al[t] = v / v.sum()
+        be[T - 1] = 1.0 / N
+        for t in range(T - 2, -1, -1):
+            v = A.dot(p[t + 1] * be[t + 1])
+            be[t] = v / v.sum()
+        gam = al * be
+        gam /= gam.sum(axis=1)[:, None]
+        for t in range(T - 1):
+            x = al[t][:, None] * A * (p[t + 1] * be[t + 1])[None, :]
+            out['C'] += x / x.sum()
+        out['g0'] += gam[0]
+        out['alpha'].append(al)
+        out['beta'].append(be)
+        out['gamma'].append(gam)
+    for k in ('alpha', 'beta', 'gamma'):
+        out[k] = np.vstack(out[k])
+    return out
+
+
+def make_plan(Ts, chunk):
+    row0, ln, t0, TT, row = [], [], [], [], 0
+    for T in Ts:
+        for a in range(0, T, chunk):
+            row0.append(row + a)
+            ln.append(min(chunk, T - a))
+            t0.append(a)
+            TT.append(T)
+        row += T
+    return (np.array(row0, dtype=np.int64), np.array(ln, dtype=np.int32), np.array(t0, dtype=np.int32),
+            np.array(TT, dtype=np.int32))
+
+
+def ptr(a, t=C.c_double):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+class Run(object):
+    def __init__(self, emu, plan, A, pi, em_kind, obs=None, pobs=None, sym=None, mu=None, sigma=None, Bt=None, M=0,
+                 ignore_outliers=0):
+        self.emu, self.plan, self.A, self.pi, self.kind = emu, plan, np.ascontiguousarray(A), np.ascontiguousarray(pi), em_kind
+        self.em = (ptr(pobs), ptr(obs), ptr(sym, C.c_int), ptr(mu), ptr(sigma), ptr(Bt), C.c_int(M), C.c_int(ignore_outliers))
+        self._keep = (obs, pobs, sym, mu, sigma, Bt)
+        n = len(plan[0])
+        rows = int(plan[0][-1] + plan[1][-1])
+        self.n, self.rows = n, rows
+        self.alpha = np.zeros((rows, PN))
+        self.chain_ll = np.zeros(n)
+        self.hu_f, self.he_f = np.zeros((n, PN)), np.zeros((n, PN))
+        self.hu_b, self.he_b = np.zeros((n, PN)), np.zeros((n, PN))
+
+    def _chains(self, warm, exact, chain_list):
+        row0, ln, t0, TT = self.plan
+        lst = None if chain_list is None else np.array(chain_list, dtype=np.int32)
+        n_run = self.n if lst is None else len(lst)
+        return (ptr(row0, C.c_longlong), ptr(ln, C.c_int), ptr(t0, C.c_int), ptr(TT, C.c_int), ptr(lst, C.c_int),
+                C.c_int(n_run), C.c_int(warm), None, C.c_int(exact)), lst
+
+    def forward(self, grid, warm, exact=0, chain_list=None):
+        ch, keep = self._chains(warm, exact, chain_list)
+        rc = self.emu.panel_emu_forward(C.c_int(self.kind), C.c_int(grid), *ch, *self.em, ptr(self.A), ptr(self.pi),
+                                        ptr(self.alpha), ptr(self.chain_ll), ptr(self.hu_f), ptr(self.he_f))
+        assert rc == 0
+
+    def backward_stats(self, grid, warm, alpha, exact=0, gamma=None, Bnum=None):
+        ch, keep = self._chains(warm, exact, None)
+        pw = self.emu.panel_emu_warps_per_block()
+        partials = np.full((grid * pw, PN * PN + 4 * PN), np.nan)     # every row must be written by its warp
+        rc = self.emu.panel_emu_backward_stats(C.c_int(self.kind), C.c_int(grid), *ch, *self.em, ptr(self.A),
+                                               ptr(np.ascontiguousarray(alpha)), ptr(gamma), ptr(Bnum), ptr(partials),
+                                               ptr(self.hu_b), ptr(self.he_b))
+        assert rc == 0
+        assert not np.isnan(partials).any()
+        s = partials.sum(axis=0)
+        return dict(C=self.A * s[:PN * PN].reshape(PN, PN), g0=s[PN * PN:PN * PN + PN], sg=s[PN * PN + PN:PN * PN + 2 * PN],
+                    sgd=s[PN * PN + 2 * PN:PN * PN + 3 * PN], sgdd=s[PN * PN + 3 * PN:])
+
+
+def model(seed, mixing=3.0):
+    rng = np.random.default_rng(seed)
+    A = rng.random((PN, PN)) + mixing * np.eye(PN)         # fast mixing: a 48-frame warm-up forgets its start
+    A /= A.sum(axis=1)[:, None]
+    pi = rng.random(PN)
+    pi /= pi.sum()
+    return rng, A, pi, np.linspace(-5, 5, PN), np.linspace(0.5, 2.0, PN)
+
+
+def check_handovers(run, ref, plan):
+    row0, ln, t0, TT = plan
+    for c in range(len(row0)):
+        np.testing.assert_allclose(run.he_f[c], ref['alpha'][row0[c] + ln[c] - 1], rtol=1e-10)
+        if t0[c] > 0:
+            np.testing.assert_allclose(run.hu_f[c], ref['alpha'][row0[c] - 1], rtol=1e-10)
+            np.testing.assert_allclose(run.he_b[c], ref['beta'][row0[c]], rtol=1e-10)
+        if t0[c] + ln[c] < TT[c]:
+            np.testing.assert_allclose(run.hu_b[c], ref['beta'][row0[c] + ln[c]], rtol=1e-10)
+
+
+@pytest.mark.parametrize('grid', [2, 1])
+def test_gaussian_estep_warm_up_mode(emu, grid):
+    """42 chains of ragged trajectories (one of a single frame, one shorter than a chunk): grid = 2 leaves the second block
+    partly idle, grid = 1 makes the warps stride over two chain groups."""
+    rng, A, pi, mu, sigma = model(11)
+    Ts = [130, 97, 1, 64, 20, 111, 75, 33, 128, 60, 90, 45]
+    trajs = [mu[rng.integers(0, PN, T)] + 0.7 * rng.standard_normal(T) for T in Ts]
+    obs = np.concatenate(trajs)
+    plan = make_plan(Ts, 24)
+    assert len(plan[0]) == 42
+    ref = plain_estep([gauss(o[:, None], mu[None, :], sigma[None, :]) for o in trajs], A, pi)
+    run = Run(emu, plan, A, pi, EM_GAUSS, obs=obs, mu=mu, sigma=sigma, ignore_outliers=1)
+    run.forward(grid, warm=48)
+    np.testing.assert_allclose(run.alpha, ref['alpha'], rtol=1e-10, atol=1e-300)
+    assert abs(run.chain_ll.sum() - ref['ll']) <= 1e-12 * abs(ref['ll'])
+    gamma = np.zeros((run.rows, PN))
+    st = run.backward_stats(grid, 48, run.alpha, gamma=gamma)
+    np.testing.assert_allclose(gamma, ref['gamma'], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9)
+    np.testing.assert_allclose(st['g0'], ref['g0'], rtol=1e-10)
+    np.testing.assert_allclose(st['sg'], ref['gamma'].sum(axis=0), rtol=1e-10)
+    d = obs[:, None] - mu[None, :]
+    np.testing.assert_allclose(st['sgd'], (ref['gamma'] * d).sum(axis=0), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(st['sgdd'], (ref['gamma'] * d * d).sum(axis=0), rtol=1e-10)
+    assert abs(st['C'].sum() - (sum(Ts) - len(Ts))) < 1e-8
+    check_handovers(run, ref, plan)
+
+
+def test_exact_fix_up_pass_over_a_chain_list(emu):
+    """Slow mixing and a warm-up that is too short: the hand-overs disagree; an exact pass over the listed chains (each
+    starting from its predecessor's recorded last row, in order) repairs them -- the certification's fix-up sweep."""
+    rng, A, pi, mu, sigma = model(5, mixing=40.0)
+    Ts = [90, 70]
+    trajs = [mu[rng.integers(0, PN, T)] + 2.5 * rng.standard_normal(T) for T in Ts]
+    obs = np.concatenate(trajs)
+    plan = make_plan(Ts, 30)
+    ref = plain_estep([gauss(o[:, None], mu[None, :], sigma[None, :]) for o in trajs], A, pi)
+    run = Run(emu, plan, A, pi, EM_GAUSS, obs=obs, mu=mu, sigma=sigma, ignore_outliers=1)
+    run.forward(1, warm=2)
+    assert np.max(np.abs(run.alpha - ref['alpha'])) > 1e-6
+    t0 = plan[2]
+    for c in range(len(t0)):               # chains that do not start a trajectory, one after the other
+        if t0[c] > 0:
+            run.forward(1, warm=2, exact=1, chain_list=[c])
+    np.testing.assert_allclose(run.alpha, ref['alpha'], rtol=1e-10, atol=1e-300)
+    assert abs(run.chain_ll.sum() - ref['ll']) <= 1e-12 * abs(ref['ll'])
+    # exact backward start: every chain enters with the true beta of the frame after it
+    row0, ln = plan[0], plan[1]
+    for c in range(len(t0)):
+        run.he_b[c] = ref['beta'][row0[c]]
+    st = run.backward_stats(1, 2, ref['alpha'], exact=1)
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9)
+    np.testing.assert_allclose(st['sg'], ref['gamma'].sum(axis=0), rtol=1e-10)
+
+
+def test_discrete_and_table_emissions_with_outlier_frames(emu):
+    rng, A, pi, mu, sigma = model(23)
+    M = 12
+    B = rng.random((PN, M)) ** 3 + 1e-4
+    B[:, 7] = 0.0                                           # a symbol no state emits: an outlier frame
+    B /= B.sum(axis=1)[:, None]
+    Ts = [70, 41, 9]
+    syms = [rng.integers(0, M, T).astype(np.int32) for T in Ts]
+    syms[0][33] = 7
+    syms[1][0] = 7
+    sym = np.concatenate(syms)
+    Bt = np.ascontiguousarray(B.T)
+    plan = make_plan(Ts, 16)
+    ps = []
+    for s in syms:
+        p = B[:, s].T.copy()
+        p[p.sum(axis=1) == 0] = 1.0                         # outputmodel.py:126-130
+        ps.append(p)
+    ref = plain_estep(ps, A, pi)
+    run = Run(emu, plan, A, pi, EM_DISC, sym=sym, Bt=Bt, M=M, ignore_outliers=1)
+    run.forward(1, warm=40)
+    np.testing.assert_allclose(run.alpha, ref['alpha'], rtol=1e-10, atol=1e-300)
+    assert abs(run.chain_ll.sum() - ref['ll']) <= 1e-12 * abs(ref['ll'])
+    Bnum = np.zeros((PN, M))
+    st = run.backward_stats(1, 40, run.alpha, Bnum=Bnum)
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9)
+    np.testing.assert_allclose(st['g0'], ref['g0'], rtol=1e-10)
+    want = np.zeros((PN, M))
+    np.add.at(want.T, sym, ref['gamma'])
+    np.testing.assert_allclose(Bnum, want, rtol=1e-9, atol=1e-14)
+    # the same frames through a caller's p_obs table (EM_POBS: no outlier rule inside the kernel)
+    pobs = np.ascontiguousarray(np.vstack(ps))
+    run2 = Run(emu, plan, A, pi, EM_POBS, pobs=pobs)
+    run2.forward(1, warm=40)
+    np.testing.assert_allclose(run2.alpha, ref['alpha'], rtol=1e-10, atol=1e-300)
+    st2 = run2.backward_stats(1, 40, run2.alpha)
+    np.testing.assert_allclose(st2['C'], ref['C'], rtol=1e-9)
+
+
+def test_exp8_tail_far_observations(emu):
+    """Observations tens of sigma away from most states: the polynomial exp's tail (exact zeros below -746, the library
+    exp in the denormal band) must agree with libm's densities."""
+    rng, A, pi, mu, sigma = model(31)
+    T = 40
+    o = np.concatenate([rng.standard_normal(T - 6) * 4.0, [19.0, -19.5, 21.0, 18.7, -20.3, 0.0]])
+    ref = plain_estep([gauss(o[:, None], mu[None, :], sigma[None, :])], A, pi)
+    plan = make_plan([T], 64)
+    run = Run(emu, plan, A, pi, EM_GAUSS, obs=o, mu=mu, sigma=sigma, ignore_outliers=1)
+    run.forward(1, warm=0)
+    np.testing.assert_allclose(run.alpha, ref['alpha'], rtol=1e-9, atol=1e-300)
+    assert abs(run.chain_ll.sum() - ref['ll']) <= 1e-12 * abs(ref['ll'])
