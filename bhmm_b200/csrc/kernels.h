@@ -104,10 +104,11 @@ int launch_backward_team(const BwdArgs& a, int em, bool stats, cudaStream_t st);
 int backward_stats_grid(int N, int n_chains);
 int launch_viterbi_team(const VitArgs& a, int em, cudaStream_t st);
 
-// ---- panel family (panel_kernels.cu): N = 32 on the FP64 tensor pipe, 8 chains per warp; opt-in (BHMM_B200_PANEL=1)
+// ---- panel family (panel_kernels.cu): FP64 tensor pipe, 8 chains per warp (N = 32) or per block (32 < N <= 104);
+// opt-in (BHMM_B200_PANEL=1)
 bool panel_enabled(int N);
-void panel_shape(int* threads, int* chains_per_row);
-int panel_stats_rows(int n_chains);          // rows of `partials` (= warps) a statistics launch over n_chains writes
+void panel_shape(int N, int* threads, int* chains_per_row);
+int panel_stats_rows(int N, int n_chains);   // rows of `partials` a statistics launch over n_chains writes
 bool panel_forward_ok(const FwdArgs& a, int em);
 bool panel_backward_ok(const BwdArgs& a, int em);
 int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st);

@@ -584,6 +584,413 @@ __global__ void __launch_bounds__(PW * 32) k_backward_stats_panel32(const BwdArg
     }
 }
 
+// ================================================================================================
+// "Wide" panel kernels: 32 < N <= 104 (C4: N = 100).  A block of NT warps walks 8 chains; NP = 8 NT padded states.
+// Warp w owns state tile w: lane (g, q) holds, for chain g, the states 8 w + 2 q and 8 w + 2 q + 1, and the warp keeps
+// the matching 8-column slice of the transition matrix as KS = 2 NT B fragments in registers.  The A operands (the
+// previous frame's vector of chain g, all NP states) come from shared memory, where the warps exchange their slices
+// once per frame: ONE block barrier per forward frame, two per backward frame.  The vector is normalised when it is
+// loaded (a = x / c, c the chain's sum read from the same exchange), i.e. the recursion runs on normalised vectors like
+// the reference's (_hidden.c:40-64) and nothing is deferred or lifted.  The outlier rule needs "are all densities of this
+// frame zero", a fact only known after the exchange: every frame publishes its vector twice -- with the densities and
+// with all densities set to one -- plus the per-tile "any density non-zero" flag, and the consumer picks the source.
+// ================================================================================================
+template <int NT>
+struct WideGeom {
+    static constexpr int NP = 8 * NT;
+    static constexpr int KS = 2 * NT;
+    static constexpr int NPS = NP + ((4 - NP % 16 + 16) % 16);   // row stride = 4 mod 16 doubles: conflict-free operand loads
+    // one block per SM: 64 K registers / (32 NT threads), in the allocation unit of 8 (ptxas stops at 128 for 13 warps
+    // when it is only given __launch_bounds__)
+    static constexpr int MAXREG = ((65536 / (32 * NT)) / 8 * 8) > 255 ? 255 : ((65536 / (32 * NT)) / 8 * 8);
+};
+#ifdef PANEL_HOST_EMU
+#define WIDE_KERNEL_ATTR(NT)
+#else
+#define WIDE_KERNEL_ATTR(NT) __maxnreg__(WideGeom<NT>::MAXREG)
+#endif
+
+// density of (row, state) for the wide kernels: one state at a time (2 per lane and frame)
+template <int EM>
+__device__ __forceinline__ double wide_density(const Emission& em, long long row, int state, int N, double o, int sym,
+                                               double mu, double isg, double lnrm)
+{
+    if (EM == EM_GAUSS) {
+        const double d = (o - mu) * isg;
+        return exp(fma(-d, d, lnrm));
+    }
+    if (EM == EM_POBS) return em.pobs[row * N + state];
+    return em.Bt[(long long)sym * N + state];
+}
+
+template <int EM, int NT>
+__global__ void WIDE_KERNEL_ATTR(NT) k_forward_wide(const FwdArgs a)
+{
+    constexpr int NP = WideGeom<NT>::NP, KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS;
+    __shared__ __align__(16) double Sx[2][PCH * NPS];     // the frame's vector with the densities ...
+    __shared__ __align__(16) double Sd[2][PCH * NPS];     // ... and with all densities set to one (outlier rule)
+    __shared__ double red[2][3][NT][PCH];                 // per tile and chain: sum of Sx, sum of Sd, any density != 0
+    const int N = a.N;
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, w = threadIdx.x >> 5;
+    const unsigned qmask = 0xFu << (4 * g);
+    const int s0 = 8 * w + 2 * q;
+    const bool ok0 = s0 < N, ok1 = s0 + 1 < N;
+    double Bf[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const int k = 4 * ks + q, col = 8 * w + g;
+        Bf[ks] = (k < N && col < N) ? a.A[k * N + col] : 0.0;
+    }
+    double mu[2] = {0.0, 0.0}, isg[2] = {1.0, 1.0}, lnrm[2] = {0.0, 0.0};
+    if (EM == EM_GAUSS) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (s0 + r < N) {
+                const double sg = a.em.sigma[s0 + r];
+                mu[r] = a.em.mu[s0 + r];
+                isg[r] = 1.0 / (sqrt(2.0) * sg);
+                lnrm[r] = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * sg));
+            }
+    }
+
+    for (int base = blockIdx.x * PCH; base < a.ch.n; base += gridDim.x * PCH) {
+        const int idx = base + g;
+        const bool have = idx < a.ch.n;
+        int c = -1, len = 0, t0 = 0, tstart = 0, mode = 0;   // mode 0: pi, 1: uniform warm-up, 2: exact vector
+        long long trow = 0;
+        if (have) {
+            c = a.ch.list ? a.ch.list[idx] : idx;
+            len = a.ch.len[c];
+            t0 = a.ch.t0[c];
+            trow = a.ch.row0[c] - t0;
+            if (t0 == 0) { tstart = 0; mode = 0; }
+            else if (a.ch.exact) { tstart = t0 - 1; mode = 2; }
+            else { tstart = max(0, t0 - (a.ch.warmv ? a.ch.warmv[c] : a.ch.warm)); mode = (tstart == 0) ? 0 : 1; }
+        }
+        const int npre = have ? (t0 - tstart) : 0;
+        const int maxpre = __reduce_max_sync(FULL, npre);
+        const int total = maxpre + __reduce_max_sync(FULL, len);
+        const int tend = t0 + len;
+        for (int k = threadIdx.x; k < 2 * PCH * NPS; k += blockDim.x) { (&Sx[0][0])[k] = 0.0; (&Sd[0][0])[k] = 0.0; }
+        for (int k = threadIdx.x; k < 2 * 3 * NT * PCH; k += blockDim.x) (&red[0][0][0][0])[k] = 0.0;
+        __syncthreads();
+
+        double vec[2] = {0.0, 0.0};
+        if (have && mode == 2) {
+            if (ok0) vec[0] = a.hand_end[(long long)(c - 1) * N + s0];
+            if (ok1) vec[1] = a.hand_end[(long long)(c - 1) * N + s0 + 1];
+        }
+        double v[2] = {0.0, 0.0}, dd[2] = {0.0, 0.0};       // the lane's values of the frame in flight: with densities / with ones
+        LogAcc acc;
+        auto frame_row = [&](int s) -> long long {
+            int t = t0 - maxpre + s;
+            t = min(max(t, tstart + (mode == 2 ? 1 : 0)), tend - 1);
+            return trow + t;
+        };
+        double o_next = 0.0;
+        int sym_next = 0;
+        if (have && EM == EM_GAUSS) o_next = a.em.obs[frame_row(0)];
+        if (have && EM == EM_DISC) sym_next = a.em.sym[frame_row(0)];
+
+        for (int s = 0; s <= total; ++s) {
+            const int cur = s & 1, prev = cur ^ 1;
+            // ---- finish frame s-1: the chain's sums are complete, normalise, store
+            double rc = 1.0;
+            bool use_d = false;
+            if (s > 0) {
+                const int tp = t0 - maxpre + s - 1;
+                const bool onp = have && tp >= tstart && tp < tend;
+                double cs = 0.0, cd = 0.0, nz = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < NT; ++w2) { cs += red[prev][0][w2][g]; cd += red[prev][1][w2][g]; nz += red[prev][2][w2][g]; }
+                if (EM != EM_POBS && a.em.ignore_outliers && onp && nz == 0.0) { use_d = true; cs = cd; }   // outputmodel.py:126-130
+                rc = (cs != 0.0) ? 1.0 / cs : 1.0;          // _hidden.c:31-34, :58-61: divide iff c != 0
+                if (onp) {
+                    const double out0 = (use_d ? dd[0] : v[0]) * rc, out1 = (use_d ? dd[1] : v[1]) * rc;
+                    if (tp >= t0) {
+                        if (a.alpha) {
+                            if (ok0) a.alpha[(trow + tp) * N + s0] = out0;
+                            if (ok1) a.alpha[(trow + tp) * N + s0 + 1] = out1;
+                        }
+                        if (w == 0 && q == 0) acc.add(cs);
+                        if (tp == tend - 1) {
+                            if (ok0) a.hand_end[(long long)c * N + s0] = out0;
+                            if (ok1) a.hand_end[(long long)c * N + s0 + 1] = out1;
+                        }
+                    } else if (tp == t0 - 1) {
+                        if (ok0) a.hand_used[(long long)c * N + s0] = out0;
+                        if (ok1) a.hand_used[(long long)c * N + s0 + 1] = out1;
+                    }
+                }
+            }
+            if (s == total) break;
+
+            // ---- frame s
+            const int t = t0 - maxpre + s;
+            const bool on = have && t >= tstart && t < tend;
+            const bool init = on && t == tstart;
+            const long long row = frame_row(s);
+            const double o = o_next;
+            const int sym = sym_next;
+            if (have && EM == EM_GAUSS) o_next = a.em.obs[frame_row(s + 1)];
+            if (have && EM == EM_DISC) sym_next = a.em.sym[frame_row(s + 1)];
+            double p[2] = {0.0, 0.0};
+            if (have) {
+                if (ok0) p[0] = wide_density<EM>(a.em, row, s0, N, o, sym, mu[0], isg[0], lnrm[0]);
+                if (ok1) p[1] = wide_density<EM>(a.em, row, s0 + 1, N, o, sym, mu[1], isg[1], lnrm[1]);
+            }
+            const double* src = (use_d ? Sd[prev] : Sx[prev]) + g * NPS;
+            double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;  // two accumulator pairs halve the dependent DMMA chain
+#pragma unroll
+            for (int ks = 0; ks < KS; ks += 2) {
+                dmma(e0, e1, src[4 * ks + q] * rc, Bf[ks]);
+                dmma(f0, f1, src[4 * ks + 4 + q] * rc, Bf[ks + 1]);
+            }
+            bool nzflag = (p[0] != 0.0) || (p[1] != 0.0);
+            if (init) {
+                if (mode == 0) { dd[0] = ok0 ? a.pi[s0] : 0.0; dd[1] = ok1 ? a.pi[s0 + 1] : 0.0; }
+                else if (mode == 1) { dd[0] = ok0 ? 1.0 : 0.0; dd[1] = ok1 ? 1.0 : 0.0; }
+                else { dd[0] = vec[0]; dd[1] = vec[1]; }
+                if (mode == 2) { v[0] = vec[0]; v[1] = vec[1]; nzflag = true; }
+                else { v[0] = dd[0] * p[0]; v[1] = dd[1] * p[1]; }
+            } else if (on) {
+                dd[0] = e0 + f0; dd[1] = e1 + f1;
+                v[0] = dd[0] * p[0]; v[1] = dd[1] * p[1];
+            } else {
+                dd[0] = dd[1] = v[0] = v[1] = 0.0;
+                nzflag = false;
+            }
+            const double pv = quad_sum(v[0] + v[1]), pd = quad_sum(dd[0] + dd[1]);
+            const bool nzq = (__ballot_sync(FULL, nzflag) & qmask) != 0u;
+            *reinterpret_cast<double2*>(&Sx[cur][g * NPS + s0]) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(&Sd[cur][g * NPS + s0]) = make_double2(dd[0], dd[1]);
+            if (q == 0) { red[cur][0][w][g] = pv; red[cur][1][w][g] = pd; red[cur][2][w][g] = nzq ? 1.0 : 0.0; }
+            __syncthreads();
+        }
+        if (have && w == 0 && q == 0) a.chain_ll[c] = acc.value();
+        __syncthreads();                                    // the buffers are cleared for the next chain group
+    }
+}
+
+// Backward + statistics, wide.  Step for frame f (downwards), chain g, lane's states s0, s0+1:
+//   publish w = p_f bn (and bn itself for the outlier rule)                       -- barrier 1
+//   xi product of the PREVIOUS step: X[:, tile w] += U^T W over the 8 chains (U, W of that step still in shared memory)
+//   d_i = sum_j A_ij w_j for the warp's tile; partial sums of alpha_{f-1} d and of d          -- barrier 2
+//   S, sum d complete: u = alpha_{f-1} / S published, gamma and moments, bn = d / sum d
+template <int EM, int NT>
+__global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide(const BwdArgs a)
+{
+    constexpr int NP = WideGeom<NT>::NP, KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS;
+    __shared__ __align__(16) double Sw[2][PCH * NPS];
+    __shared__ __align__(16) double Sb[2][PCH * NPS];
+    __shared__ __align__(16) double Su[PCH * NPS];
+    __shared__ double red[2][NT][PCH];                     // partial S, partial sum of d
+    __shared__ double redn[NT][PCH];                       // any density != 0
+    const int N = a.N;
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, w = threadIdx.x >> 5;
+    const unsigned qmask = 0xFu << (4 * g);
+    const int s0 = 8 * w + 2 * q;
+    const bool ok0 = s0 < N, ok1 = s0 + 1 < N;
+    double Bt[KS];                                          // d = A w: contraction index j = 4 ks + q, output i = 8 w + g
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const int j = 4 * ks + q, i = 8 * w + g;
+        Bt[ks] = (i < N && j < N) ? a.A[i * N + j] : 0.0;
+    }
+    double X[NT][2];
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) { X[mt][0] = 0.0; X[mt][1] = 0.0; }
+    double mu[2] = {0.0, 0.0}, isg[2] = {1.0, 1.0}, lnrm[2] = {0.0, 0.0};
+    if (EM == EM_GAUSS) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (s0 + r < N) {
+                const double sg = a.em.sigma[s0 + r];
+                mu[r] = a.em.mu[s0 + r];
+                isg[r] = 1.0 / (sqrt(2.0) * sg);
+                lnrm[r] = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * sg));
+            }
+    }
+    double st_g[2] = {0.0, 0.0}, st_gd[2] = {0.0, 0.0}, st_gdd[2] = {0.0, 0.0};
+    const long long nstat = (long long)N * N + 4 * N;
+    double* out = a.partials + (long long)blockIdx.x * nstat;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) out[(long long)N * N + j] = 0.0;   // gamma0: atomics below
+    __syncthreads();
+
+    auto xi_product = [&](int buf) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const double wb = Sw[buf][(4 * kk + q) * NPS + 8 * w + g];
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt) dmma(X[mt][0], X[mt][1], Su[(4 * kk + q) * NPS + 8 * mt + g], wb);
+        }
+    };
+
+    for (int base = blockIdx.x * PCH; base < a.ch.n; base += gridDim.x * PCH) {
+        const int idx = base + g;
+        const bool have = idx < a.ch.n;
+        int c = -1, len = 0, t0 = 0, T = 0, e = 0, fstart = 0, mode = 0;
+        bool virt = false;
+        long long trow = 0;
+        if (have) {
+            c = a.ch.list ? a.ch.list[idx] : idx;
+            len = a.ch.len[c];
+            t0 = a.ch.t0[c];
+            T = a.ch.T[c];
+            trow = a.ch.row0[c] - t0;
+            e = t0 + len;
+            if (e >= T) { virt = true; fstart = T; }
+            else if (a.ch.exact) { fstart = e; mode = 2; }
+            else { fstart = min(T - 1, e + (a.ch.warmv ? a.ch.warmv[c] : a.ch.warm) - 1); }
+        }
+        const int flast = t0 + 1;
+        const int npre = have ? (fstart - (e - 1)) : 0;
+        const int maxpre = __reduce_max_sync(FULL, npre);
+        const int total = maxpre + __reduce_max_sync(FULL, have ? (e - flast) : 0);
+        for (int k = threadIdx.x; k < 2 * PCH * NPS; k += blockDim.x) { (&Sw[0][0])[k] = 0.0; (&Sb[0][0])[k] = 0.0; }
+        for (int k = threadIdx.x; k < PCH * NPS; k += blockDim.x) Su[k] = 0.0;
+        __syncthreads();
+
+        double bn[2] = {ok0 ? 1.0 / N : 0.0, ok1 ? 1.0 / N : 0.0};   // beta_{T-1} = 1/N (_hidden.c:76-77); warm-up start
+        if (have && mode == 2) {
+            if (ok0) bn[0] = a.hand_end[(long long)(c + 1) * N + s0];
+            if (ok1) bn[1] = a.hand_end[(long long)(c + 1) * N + s0 + 1];
+        }
+        auto frame_of = [&](int s) -> int { return (e - 1) + maxpre - s; };
+        auto em_row = [&](int s) -> long long { return trow + min(max(frame_of(s), t0), T - 1); };
+        auto al_row = [&](int s) -> long long { return trow + min(max(frame_of(s) - 1, t0), e - 1); };
+        double o_next = 0.0, al_next[2] = {0.0, 0.0};
+        int sym_next = 0;
+        if (have) {
+            if (EM == EM_GAUSS) o_next = a.em.obs[em_row(0)];
+            if (EM == EM_DISC) sym_next = a.em.sym[em_row(0)];
+            if (ok0) al_next[0] = a.alpha[al_row(0) * N + s0];
+            if (ok1) al_next[1] = a.alpha[al_row(0) * N + s0 + 1];
+        }
+        bool pending_xi = false;                            // the previous step published a non-zero U
+
+        for (int s = 0; s < total; ++s) {
+            const int cur = s & 1;
+            const int f = frame_of(s);
+            const bool on = have && f <= fstart && f >= flast;
+            const bool isvirt = on && virt && f == T;
+            const long long row = em_row(s);
+            const double o = o_next, al0 = al_next[0], al1 = al_next[1];
+            const int sym = sym_next;
+            if (have) {
+                if (EM == EM_GAUSS) o_next = a.em.obs[em_row(s + 1)];      // frame f-1: also the emitted frame's observation
+                if (EM == EM_DISC) sym_next = a.em.sym[em_row(s + 1)];
+                if (ok0) al_next[0] = a.alpha[al_row(s + 1) * N + s0];
+                if (ok1) al_next[1] = a.alpha[al_row(s + 1) * N + s0 + 1];
+            }
+            double p[2] = {0.0, 0.0};
+            if (have) {
+                if (ok0) p[0] = wide_density<EM>(a.em, row, s0, N, o, sym, mu[0], isg[0], lnrm[0]);
+                if (ok1) p[1] = wide_density<EM>(a.em, row, s0 + 1, N, o, sym, mu[1], isg[1], lnrm[1]);
+            }
+            const bool act = on && !isvirt;
+            double wv[2] = {act ? p[0] * bn[0] : 0.0, act ? p[1] * bn[1] : 0.0};
+            const double bv[2] = {act ? bn[0] : 0.0, act ? bn[1] : 0.0};
+            const bool nzq = (__ballot_sync(FULL, (p[0] != 0.0) || (p[1] != 0.0)) & qmask) != 0u;
+            *reinterpret_cast<double2*>(&Sw[cur][g * NPS + s0]) = make_double2(wv[0], wv[1]);
+            *reinterpret_cast<double2*>(&Sb[cur][g * NPS + s0]) = make_double2(bv[0], bv[1]);
+            if (q == 0) redn[w][g] = nzq ? 1.0 : 0.0;
+            __syncthreads();                                // ---- barrier 1
+
+            if (pending_xi) xi_product(cur ^ 1);
+
+            double nz = 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < NT; ++w2) nz += redn[w2][g];
+            const bool use_b = (EM != EM_POBS) && a.em.ignore_outliers && act && nz == 0.0;   // outputmodel.py:126-130
+            const double* src = (use_b ? Sb[cur] : Sw[cur]) + g * NPS;
+            double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks += 2) {
+                dmma(e0, e1, src[4 * ks + q], Bt[ks]);
+                dmma(f0, f1, src[4 * ks + 4 + q], Bt[ks + 1]);
+            }
+            double d[2] = {e0 + f0, e1 + f1};
+            if (isvirt) { d[0] = ok0 ? 1.0 : 0.0; d[1] = ok1 ? 1.0 : 0.0; }
+            if (use_b) {                                    // the xi product of the next step reads W from Sw
+                wv[0] = bv[0]; wv[1] = bv[1];
+                *reinterpret_cast<double2*>(&Sw[cur][g * NPS + s0]) = make_double2(wv[0], wv[1]);
+            }
+            if (act && f == e) {
+                if (ok0) a.hand_used[(long long)c * N + s0] = bn[0];
+                if (ok1) a.hand_used[(long long)c * N + s0 + 1] = bn[1];
+            }
+            const bool emit = on && (f - 1) < e;
+            const bool xi = emit && !isvirt;
+            const double gq0 = emit ? al0 * d[0] : 0.0, gq1 = emit ? al1 * d[1] : 0.0;
+            const double pS = quad_sum(gq0 + gq1), pb = quad_sum(d[0] + d[1]);
+            if (q == 0) { red[0][w][g] = pS; red[1][w][g] = pb; }
+            __syncthreads();                                // ---- barrier 2
+
+            double S = 0.0, sbn = 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < NT; ++w2) { S += red[0][w2][g]; sbn += red[1][w2][g]; }
+            const double rS = 1.0 / S;
+            *reinterpret_cast<double2*>(&Su[g * NPS + s0]) = make_double2(xi ? al0 * rS : 0.0, xi ? al1 * rS : 0.0);
+            pending_xi = __any_sync(FULL, xi);
+            if (emit) {
+                const long long orow = trow + (f - 1);
+                const double gam[2] = {gq0 * rS, gq1 * rS};
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (s0 + r >= N) continue;
+                    st_g[r] += gam[r];
+                    if (f - 1 == 0) atomicAdd(out + (long long)N * N + s0 + r, gam[r]);
+                    if (EM == EM_GAUSS) {
+                        const double dv = o_next - mu[r];
+                        st_gd[r] = fma(gam[r], dv, st_gd[r]);
+                        st_gdd[r] = fma(gam[r], dv * dv, st_gdd[r]);
+                    }
+                    if (EM == EM_DISC && a.Bnum) atomicAdd(a.Bnum + (long long)(s0 + r) * a.em.M + sym_next, gam[r]);
+                    if (a.gamma) a.gamma[orow * N + s0 + r] = gam[r];
+                }
+                if (f - 1 == t0 && t0 > 0) {
+                    const double r2 = (sbn != 0.0) ? 1.0 / sbn : 1.0;
+                    if (ok0) a.hand_end[(long long)c * N + s0] = d[0] * r2;
+                    if (ok1) a.hand_end[(long long)c * N + s0 + 1] = d[1] * r2;
+                }
+            }
+            if (on) {
+                const double r2 = (sbn != 0.0) ? 1.0 / sbn : 1.0;          // _hidden.c:104-107
+                bn[0] = d[0] * r2;
+                bn[1] = d[1] * r2;
+            }
+        }
+        __syncthreads();
+        if (pending_xi) xi_product((total - 1) & 1);
+        __syncthreads();                                    // the buffers are cleared for the next chain group
+    }
+
+    // ---- the block's row of partial statistics: [X (N*N) | gamma0 (N) | sum gamma | sum gamma d | sum gamma d^2]
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+        const int i = 8 * mt + g;
+        if (i < N) {
+            if (ok0) out[(long long)i * N + s0] = X[mt][0];
+            if (ok1) out[(long long)i * N + s0 + 1] = X[mt][1];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+            st_g[r] += __shfl_xor_sync(FULL, st_g[r], off);
+            st_gd[r] += __shfl_xor_sync(FULL, st_gd[r], off);
+            st_gdd[r] += __shfl_xor_sync(FULL, st_gdd[r], off);
+        }
+        if (g == 0 && s0 + r < N) {
+            out[(long long)N * N + N + s0 + r] = st_g[r];
+            out[(long long)N * N + 2 * N + s0 + r] = st_gd[r];
+            out[(long long)N * N + 3 * N + s0 + r] = st_gdd[r];
+        }
+    }
+}
+
 #ifndef PANEL_HOST_EMU
 int panel_sms()
 {
@@ -616,13 +1023,53 @@ int panel_blocks(int n_chains)
     return (int)std::max(1LL, std::min(groups, cap));
 }
 
+// wide kernels: state tiles (= warps per block) for N, 0 if N is not served
+int wide_tiles(int N) { return (N <= 32) ? 0 : (N <= 64 ? 8 : (N <= 104 ? 13 : 0)); }
+
+int wide_blocks_per_sm(int NT)
+{
+    static int per8 = 0, per13 = 0;
+    int& per = (NT == 8) ? per8 : per13;
+    if (per == 0) {
+        int v = 0;
+        cudaError_t e = (NT == 8)
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 8>, 8 * 32, 0)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 13>, 13 * 32, 0);
+        per = (e == cudaSuccess && v > 0) ? v : 1;
+    }
+    return per;
+}
+
+int wide_blocks(int NT, int n_chains)
+{
+    const long long groups = ((long long)n_chains + PCH - 1) / PCH;
+    const long long cap = (long long)panel_sms() * wide_blocks_per_sm(NT);
+    return (int)std::max(1LL, std::min(groups, cap));
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int EM>
+int launch_forward_wide_em(const FwdArgs& a, int NT, cudaStream_t st)
+{
+    const int grid = wide_blocks(NT, a.ch.n);
+    if (NT == 8) k_forward_wide<EM, 8><<<grid, 8 * 32, 0, st>>>(a);
+    else k_forward_wide<EM, 13><<<grid, 13 * 32, 0, st>>>(a);
+    return BHMM_OK;
+}
+
+template <int EM>
+int launch_backward_wide_em(const BwdArgs& a, int NT, cudaStream_t st)
+{
+    if (NT == 8) k_backward_stats_wide<EM, 8><<<a.grid, 8 * 32, 0, st>>>(a);
+    else k_backward_stats_wide<EM, 13><<<a.grid, 13 * 32, 0, st>>>(a);
+    return BHMM_OK;
+}
 #endif   // PANEL_HOST_EMU
 
 }  // namespace
 
 #ifndef PANEL_HOST_EMU
-
 bool panel_enabled(int N)
 {
     static int on = -1;
@@ -630,19 +1077,24 @@ bool panel_enabled(int N)
         const char* e = getenv("BHMM_B200_PANEL");
         on = (e && strcmp(e, "1") == 0) ? 1 : 0;
     }
-    return on == 1 && N == PN;
+    return on == 1 && (N == PN || wide_tiles(N) > 0);
 }
 
-void panel_shape(int* threads, int* chains_per_block)
+// threads per block and chains per row of partial statistics (N = 32: a row per warp; wide: a row per block)
+void panel_shape(int N, int* threads, int* chains_per_row)
 {
-    *threads = PW * 32;
-    *chains_per_block = PCH;     // per partial-statistics row (= warp): backward_stats_grid() counts warps for this family
+    *threads = (N == PN) ? PW * 32 : wide_tiles(N) * 32;
+    *chains_per_row = PCH;
 }
 
-int panel_stats_rows(int n_chains) { return panel_blocks(n_chains) * PW; }
+int panel_stats_rows(int N, int n_chains)
+{
+    return (N == PN) ? panel_blocks(n_chains) * PW : wide_blocks(wide_tiles(N), n_chains);
+}
 
 bool panel_forward_ok(const FwdArgs& a, int em)
 {
+    if (a.N != PN) return wide_tiles(a.N) > 0;             // the wide kernels use scalar global accesses only
     bool ok = aligned16(a.A) && aligned16(a.pi) && aligned16(a.hand_end) && aligned16(a.hand_used) && (!a.alpha || aligned16(a.alpha));
     if (em == EM_POBS) ok = ok && aligned16(a.em.pobs);
     if (em == EM_DISC) ok = ok && aligned16(a.em.Bt);
@@ -651,6 +1103,7 @@ bool panel_forward_ok(const FwdArgs& a, int em)
 
 bool panel_backward_ok(const BwdArgs& a, int em)
 {
+    if (a.N != PN) return wide_tiles(a.N) > 0 && a.grid > 0;
     bool ok = aligned16(a.A) && aligned16(a.alpha) && aligned16(a.partials) && aligned16(a.hand_end) && aligned16(a.hand_used)
               && (!a.gamma || aligned16(a.gamma)) && a.grid > 0 && a.grid % PW == 0;
     if (em == EM_POBS) ok = ok && aligned16(a.em.pobs);
@@ -660,8 +1113,17 @@ bool panel_backward_ok(const BwdArgs& a, int em)
 
 int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st)
 {
-    if (a.N != PN) return BHMM_ERR_UNSUPPORTED;
     if (a.ch.n <= 0) return BHMM_OK;
+    if (a.N != PN) {
+        const int NT = wide_tiles(a.N);
+        if (NT == 0) return BHMM_ERR_UNSUPPORTED;
+        switch (em) {
+            case EM_POBS: return launch_forward_wide_em<EM_POBS>(a, NT, st);
+            case EM_GAUSS: return launch_forward_wide_em<EM_GAUSS>(a, NT, st);
+            case EM_DISC: return launch_forward_wide_em<EM_DISC>(a, NT, st);
+        }
+        return BHMM_ERR_INVALID;
+    }
     const int grid = panel_blocks(a.ch.n);
     switch (em) {
         case EM_POBS: k_forward_panel32<EM_POBS><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
@@ -671,10 +1133,20 @@ int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st)
     return BHMM_ERR_INVALID;
 }
 
-// a.grid = rows of `partials` = warps of the launch (panel_stats_rows); every warp writes its row, chains or not
+// a.grid = rows of `partials` (panel_stats_rows): warps of the launch at N = 32, blocks for the wide kernels; every
+// row is written, chains or not
 int launch_backward_stats_panel(const BwdArgs& a, int em, cudaStream_t st)
 {
-    if (a.N != PN) return BHMM_ERR_UNSUPPORTED;
+    if (a.N != PN) {
+        const int NT = wide_tiles(a.N);
+        if (NT == 0) return BHMM_ERR_UNSUPPORTED;
+        switch (em) {
+            case EM_POBS: return launch_backward_wide_em<EM_POBS>(a, NT, st);
+            case EM_GAUSS: return launch_backward_wide_em<EM_GAUSS>(a, NT, st);
+            case EM_DISC: return launch_backward_wide_em<EM_DISC>(a, NT, st);
+        }
+        return BHMM_ERR_INVALID;
+    }
     const int grid = a.grid / PW;
     switch (em) {
         case EM_POBS: k_backward_stats_panel32<EM_POBS><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;

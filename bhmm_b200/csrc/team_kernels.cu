@@ -623,7 +623,7 @@ static void team_shape_raw(int N, int* threads, int* cpb)
 // what the planners see: chains per row of partial statistics (a block here, a warp in the opt-in panel family)
 void team_shape(int N, int* threads, int* cpb)
 {
-    if (panel_enabled(N)) { panel_shape(threads, cpb); return; }
+    if (panel_enabled(N)) { panel_shape(N, threads, cpb); return; }
     team_shape_raw(N, threads, cpb);
 }
 
@@ -658,7 +658,7 @@ int launch_forward_team(const FwdArgs& a, int em, cudaStream_t st)
 
 int backward_stats_grid(int N, int n_chains)
 {
-    if (panel_enabled(N)) return panel_stats_rows(n_chains);
+    if (panel_enabled(N)) return panel_stats_rows(N, n_chains);
     int threads, cpb;
     team_shape_raw(N, &threads, &cpb);
     const size_t smem = sizeof(double) * ((size_t)N * N + 6 * (size_t)cpb * N + (size_t)cpb * N * N);

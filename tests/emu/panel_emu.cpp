@@ -30,7 +30,7 @@ Emission make_emission(const double* pobs, const double* obs, const int* sym, co
 
 extern "C" int panel_emu_warps_per_block() { return PW; }
 
-extern "C" int panel_emu_forward(int em_kind, int grid, const long long* row0, const int* len, const int* t0, const int* T,
+extern "C" int panel_emu_forward(int N, int em_kind, int grid, const long long* row0, const int* len, const int* t0, const int* T,
                                  const int* list, int n_run, int warm, const int* warmv, int exact, const double* pobs,
                                  const double* obs, const int* sym, const double* mu, const double* sigma, const double* Bt,
                                  int M, int ignore_outliers, const double* A, const double* pi, double* alpha,
@@ -39,7 +39,21 @@ extern "C" int panel_emu_forward(int em_kind, int grid, const long long* row0, c
     FwdArgs a{};
     a.ch = make_chains(row0, len, t0, T, list, n_run, warm, warmv, exact);
     a.em = make_emission(pobs, obs, sym, mu, sigma, Bt, M, ignore_outliers);
-    a.N = PN; a.A = A; a.pi = pi; a.alpha = alpha; a.chain_ll = chain_ll; a.hand_used = hand_used; a.hand_end = hand_end;
+    a.N = N; a.A = A; a.pi = pi; a.alpha = alpha; a.chain_ll = chain_ll; a.hand_used = hand_used; a.hand_end = hand_end;
+    if (N != PN) {
+        const int NT = (N <= 64) ? 8 : 13;
+        if (N <= 32 || N > 104) return 2;
+#define FWD_WIDE(EMK) \
+        if (NT == 8) emu::launch(grid, 8 * 32, [&] { k_forward_wide<EMK, 8>(a); }); \
+        else emu::launch(grid, 13 * 32, [&] { k_forward_wide<EMK, 13>(a); }); \
+        return 0;
+        switch (em_kind) {
+            case EM_POBS: FWD_WIDE(EM_POBS)
+            case EM_GAUSS: FWD_WIDE(EM_GAUSS)
+            case EM_DISC: FWD_WIDE(EM_DISC)
+        }
+        return 1;
+    }
     switch (em_kind) {
         case EM_POBS: emu::launch(grid, PW * 32, [&] { k_forward_panel32<EM_POBS>(a); }); return 0;
         case EM_GAUSS: emu::launch(grid, PW * 32, [&] { k_forward_panel32<EM_GAUSS>(a); }); return 0;
@@ -48,8 +62,8 @@ extern "C" int panel_emu_forward(int em_kind, int grid, const long long* row0, c
     return 1;
 }
 
-// partials: (grid * PW, 32*32 + 4*32)
-extern "C" int panel_emu_backward_stats(int em_kind, int grid, const long long* row0, const int* len, const int* t0,
+// partials: N = 32: (grid * PW, N*N + 4N), one row per warp; wide kernels: (grid, N*N + 4N), one row per block
+extern "C" int panel_emu_backward_stats(int N, int em_kind, int grid, const long long* row0, const int* len, const int* t0,
                                         const int* T, const int* list, int n_run, int warm, const int* warmv, int exact,
                                         const double* pobs, const double* obs, const int* sym, const double* mu,
                                         const double* sigma, const double* Bt, int M, int ignore_outliers, const double* A,
@@ -59,8 +73,22 @@ extern "C" int panel_emu_backward_stats(int em_kind, int grid, const long long* 
     BwdArgs a{};
     a.ch = make_chains(row0, len, t0, T, list, n_run, warm, warmv, exact);
     a.em = make_emission(pobs, obs, sym, mu, sigma, Bt, M, ignore_outliers);
-    a.N = PN; a.grid = grid * PW; a.A = A; a.alpha = alpha; a.gamma = gamma; a.Bnum = Bnum; a.partials = partials;
+    a.N = N; a.grid = (N == PN) ? grid * PW : grid; a.A = A; a.alpha = alpha; a.gamma = gamma; a.Bnum = Bnum; a.partials = partials;
     a.hand_used = hand_used; a.hand_end = hand_end;
+    if (N != PN) {
+        const int NT = (N <= 64) ? 8 : 13;
+        if (N <= 32 || N > 104) return 2;
+#define BWD_WIDE(EMK) \
+        if (NT == 8) emu::launch(grid, 8 * 32, [&] { k_backward_stats_wide<EMK, 8>(a); }); \
+        else emu::launch(grid, 13 * 32, [&] { k_backward_stats_wide<EMK, 13>(a); }); \
+        return 0;
+        switch (em_kind) {
+            case EM_POBS: BWD_WIDE(EM_POBS)
+            case EM_GAUSS: BWD_WIDE(EM_GAUSS)
+            case EM_DISC: BWD_WIDE(EM_DISC)
+        }
+        return 1;
+    }
     switch (em_kind) {
         case EM_POBS: emu::launch(grid, PW * 32, [&] { k_backward_stats_panel32<EM_POBS>(a); }); return 0;
         case EM_GAUSS: emu::launch(grid, PW * 32, [&] { k_backward_stats_panel32<EM_GAUSS>(a); }); return 0;

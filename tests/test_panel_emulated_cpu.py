@@ -89,6 +89,7 @@ class Run(object):
     def __init__(self, emu, plan, A, pi, em_kind, obs=None, pobs=None, sym=None, mu=None, sigma=None, Bt=None, M=0,
                  ignore_outliers=0):
         self.emu, self.plan, self.A, self.pi, self.kind = emu, plan, np.ascontiguousarray(A), np.ascontiguousarray(pi), em_kind
+        self.N = PN = len(pi)
         self.em = (ptr(pobs), ptr(obs), ptr(sym, C.c_int), ptr(mu), ptr(sigma), ptr(Bt), C.c_int(M), C.c_int(ignore_outliers))
         self._keep = (obs, pobs, sym, mu, sigma, Bt)
         n = len(plan[0])
@@ -108,15 +109,16 @@ class Run(object):
 
     def forward(self, grid, warm, exact=0, chain_list=None):
         ch, keep = self._chains(warm, exact, chain_list)
-        rc = self.emu.panel_emu_forward(C.c_int(self.kind), C.c_int(grid), *ch, *self.em, ptr(self.A), ptr(self.pi),
+        rc = self.emu.panel_emu_forward(C.c_int(self.N), C.c_int(self.kind), C.c_int(grid), *ch, *self.em, ptr(self.A), ptr(self.pi),
                                         ptr(self.alpha), ptr(self.chain_ll), ptr(self.hu_f), ptr(self.he_f))
         assert rc == 0
 
     def backward_stats(self, grid, warm, alpha, exact=0, gamma=None, Bnum=None):
         ch, keep = self._chains(warm, exact, None)
-        pw = self.emu.panel_emu_warps_per_block()
-        partials = np.full((grid * pw, PN * PN + 4 * PN), np.nan)     # every row must be written by its warp
-        rc = self.emu.panel_emu_backward_stats(C.c_int(self.kind), C.c_int(grid), *ch, *self.em, ptr(self.A),
+        PN = self.N
+        pw = self.emu.panel_emu_warps_per_block() if PN == 32 else 1
+        partials = np.full((grid * pw, PN * PN + 4 * PN), np.nan)     # every row must be written by its warp / block
+        rc = self.emu.panel_emu_backward_stats(C.c_int(PN), C.c_int(self.kind), C.c_int(grid), *ch, *self.em, ptr(self.A),
                                                ptr(np.ascontiguousarray(alpha)), ptr(gamma), ptr(Bnum), ptr(partials),
                                                ptr(self.hu_b), ptr(self.he_b))
         assert rc == 0
@@ -126,13 +128,13 @@ class Run(object):
                     sgd=s[PN * PN + 2 * PN:PN * PN + 3 * PN], sgdd=s[PN * PN + 3 * PN:])
 
 
-def model(seed, mixing=3.0):
+def model(seed, mixing=3.0, N=PN):
     rng = np.random.default_rng(seed)
-    A = rng.random((PN, PN)) + mixing * np.eye(PN)         # fast mixing: a 48-frame warm-up forgets its start
+    A = rng.random((N, N)) + mixing * np.eye(N)            # fast mixing: a 48-frame warm-up forgets its start
     A /= A.sum(axis=1)[:, None]
-    pi = rng.random(PN)
+    pi = rng.random(N)
     pi /= pi.sum()
-    return rng, A, pi, np.linspace(-5, 5, PN), np.linspace(0.5, 2.0, PN)
+    return rng, A, pi, np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
 
 
 def check_handovers(run, ref, plan):
@@ -252,3 +254,82 @@ def test_exp8_tail_far_observations(emu):
     run.forward(1, warm=0)
     np.testing.assert_allclose(run.alpha, ref['alpha'], rtol=1e-9, atol=1e-300)
     assert abs(run.chain_ll.sum() - ref['ll']) <= 1e-12 * abs(ref['ll'])
+
+
+# ------------------------------------------------------------------------------------------------ wide kernels, 32 < N <= 104
+@pytest.mark.parametrize('N,grid', [(100, 2), (37, 1), (64, 1)])
+def test_wide_gaussian_estep(emu, N, grid):
+    """k_forward_wide / k_backward_stats_wide: a block of N/8 warps per 8 chains, state tiles exchanged through shared memory.
+    N = 100 (C4's state count, padded to 104: 13 warps), an odd N with a half-empty last tile, and a full 64."""
+    rng, A, pi, mu, sigma = model(100 + N, N=N)
+    Ts = [50, 33, 1, 41, 18, 29]
+    trajs = [mu[rng.integers(0, N, T)] + 0.7 * rng.standard_normal(T) for T in Ts]
+    trajs[3][7] = 400.0                                     # far from every state: all densities underflow (outlier rule)
+    obs = np.concatenate(trajs)
+    plan = make_plan(Ts, 13)
+    ps = []
+    for o in trajs:
+        p = gauss(o[:, None], mu[None, :], sigma[None, :])
+        p[p.sum(axis=1) == 0] = 1.0
+        ps.append(p)
+    ref = plain_estep(ps, A, pi)
+    run = Run(emu, plan, A, pi, EM_GAUSS, obs=obs, mu=mu, sigma=sigma, ignore_outliers=1)
+    run.forward(grid, warm=30)
+    np.testing.assert_allclose(run.alpha, ref['alpha'], rtol=1e-10, atol=1e-300)
+    assert abs(run.chain_ll.sum() - ref['ll']) <= 1e-12 * abs(ref['ll'])
+    gamma = np.zeros((run.rows, N))
+    st = run.backward_stats(grid, 30, run.alpha, gamma=gamma)
+    np.testing.assert_allclose(gamma, ref['gamma'], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(st['g0'], ref['g0'], rtol=1e-10)
+    np.testing.assert_allclose(st['sg'], ref['gamma'].sum(axis=0), rtol=1e-10)
+    d = obs[:, None] - mu[None, :]
+    np.testing.assert_allclose(st['sgdd'], (ref['gamma'] * d * d).sum(axis=0), rtol=1e-10)
+    np.testing.assert_allclose(st['sgd'], (ref['gamma'] * d).sum(axis=0), rtol=1e-9, atol=1e-7)
+    assert abs(st['C'].sum() - (sum(Ts) - len(Ts))) < 1e-8
+    row0, ln, t0, TT = plan
+    for c in range(len(row0)):
+        np.testing.assert_allclose(run.he_f[c], ref['alpha'][row0[c] + ln[c] - 1], rtol=1e-10, atol=1e-300)
+        if t0[c] > 0:
+            np.testing.assert_allclose(run.hu_f[c], ref['alpha'][row0[c] - 1], rtol=1e-10, atol=1e-300)
+            np.testing.assert_allclose(run.he_b[c], ref['beta'][row0[c]], rtol=1e-10)
+        if t0[c] + ln[c] < TT[c]:
+            np.testing.assert_allclose(run.hu_b[c], ref['beta'][row0[c] + ln[c]], rtol=1e-10)
+
+
+def test_wide_discrete_c4_shape_and_fix_up(emu):
+    """N = 100 states, discrete symbols (the C4 model family) with a symbol no state emits, B-numerators, and an exact
+    fix-up pass over a chain list after a warm-up that is too short."""
+    N, M = 100, 30
+    rng, A, pi, mu, sigma = model(77, mixing=25.0, N=N)
+    B = rng.random((N, M)) ** 3 + 1e-4
+    B[:, 5] = 0.0
+    B /= B.sum(axis=1)[:, None]
+    Ts = [40, 26]
+    syms = [rng.integers(0, M, T).astype(np.int32) for T in Ts]
+    syms[0][17] = 5
+    sym = np.concatenate(syms)
+    Bt = np.ascontiguousarray(B.T)
+    plan = make_plan(Ts, 11)
+    ps = []
+    for s_ in syms:
+        p = B[:, s_].T.copy()
+        p[p.sum(axis=1) == 0] = 1.0
+        ps.append(p)
+    ref = plain_estep(ps, A, pi)
+    run = Run(emu, plan, A, pi, EM_DISC, sym=sym, Bt=Bt, M=M, ignore_outliers=1)
+    run.forward(1, warm=1)
+    assert np.max(np.abs(run.alpha - ref['alpha'])) > 1e-8
+    t0 = plan[2]
+    for c in range(len(t0)):
+        if t0[c] > 0:
+            run.forward(1, warm=1, exact=1, chain_list=[c])
+    np.testing.assert_allclose(run.alpha, ref['alpha'], rtol=1e-10, atol=1e-300)
+    assert abs(run.chain_ll.sum() - ref['ll']) <= 1e-12 * abs(ref['ll'])
+    Bnum = np.zeros((N, M))
+    st = run.backward_stats(1, 60, ref['alpha'], Bnum=Bnum)            # warm-up longer than the trajectories: exact
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(st['g0'], ref['g0'], rtol=1e-10)
+    want = np.zeros((N, M))
+    np.add.at(want.T, sym, ref['gamma'])
+    np.testing.assert_allclose(Bnum, want, rtol=1e-9, atol=1e-14)

@@ -1,4 +1,4 @@
-"""Parity and timing of the opt-in N = 32 panel kernels (bhmm_b200/csrc/panel_kernels.cu) on a B200.
+"""Parity and timing of the opt-in panel kernels (bhmm_b200/csrc/panel_kernels.cu: N = 32 and 32 < N <= 104) on a B200.
 
     timeout 900 python tools/panel_check.py            # parity against the oracle, then timing next to the team kernels
     timeout 600 python tools/panel_check.py --quick    # parity only (what tests/test_panel_cuda.py runs)
@@ -51,6 +51,71 @@ def timeit(fn, reps=3):
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
+
+
+def timing_wide():
+    """C4 shape (reduced trajectory count): N = 100 discrete, M = 1000."""
+    N, M, K, T = 100, 1000, 32, 100000
+    pi, A, B, O, S = ts.discrete_observations(N, M, K, T, seed=4)
+    b = TrajectoryBatch(list(O), N)
+    b.set_profiling(True)
+    ms = timeit(lambda: b.estep_discrete(A, pi, B), reps=2)
+    st = unpack_stats(b.estep_discrete(A, pi, B)[0].cpu().numpy(), N)
+    print('%s N=100 discrete M=1000 K=%d T=%d: E-step %.2f ms -> %.4f G frames/s; kernels %s; info %s; loglik %.10e'
+          % ('team ' if CHILD else 'panel', K, T, ms, K * T / ms / 1e6, b.kernel_ms(), b.info(), st['loglik']), flush=True)
+    b.close()
+
+
+def parity_wide():
+    """32 < N <= 104: the wide kernels (a block of N/8 warps per 8 chains)."""
+    from oracle.oracle import Oracle
+    orc = Oracle('port')
+    rng = np.random.default_rng(43)
+    for N in (100, 37, 64):
+        X = rng.random((N, N)) ** 2 + 1e-3
+        A = X / X.sum(axis=1)[:, None]
+        pi = rng.random(N) + 0.01
+        pi /= pi.sum()
+        means, sigmas = np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
+        obs = []
+        for Tk in (900, 777, 40, 1, 333, 1200):
+            s = rng.integers(0, N, size=Tk)
+            obs.append(means[s] + sigmas[s] * rng.standard_normal(Tk))
+        ref = orc.estep_gaussian(obs, A, pi, means, sigmas)
+        wdd = np.zeros(N)
+        for g, o in zip(ref['gammas'], obs):
+            d = o[:, None] - means[None, :]
+            wdd += (g * d * d).sum(axis=0)
+        for chunk, warm in ((0, 0), (150, 0)):
+            b = TrajectoryBatch(obs, N, chunk=chunk, warm=warm)
+            gam = torch.zeros((b.rows, N), dtype=torch.float64, device='cuda')
+            st = unpack_stats(b.estep_gaussian(A, pi, means, sigmas, gamma_out=gam).cpu().numpy(), N)
+            tag = 'wide N=%d gaussian chunk=%d: ' % (N, chunk)
+            check(tag + 'loglik', abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik']), '%.12e vs %.12e' % (st['loglik'], ref['loglik']))
+            for key, r, rt, at in (('gamma0', ref['gamma0'], RTOL, 1e-300), ('C', ref['C'], 1e-9, 1e-12 * ref['C'].max()),
+                                   ('wsum', ref['wsum'], RTOL, 0.0), ('wdd', wdd, 1e-9, 0.0)):
+                ok, worst = close(st[key], r, rt, at)
+                check(tag + key, ok, 'worst rel %.2e' % worst)
+            ok, worst = close(gam.cpu().numpy(), np.vstack(ref['gammas']), 1e-9, 1e-14)
+            check(tag + 'gamma rows', ok, 'worst rel %.2e' % worst)
+            b.close()
+    # discrete, the C4 model family
+    N, M = 100, 200
+    X = rng.random((N, N)) ** 2 + 1e-3
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    B = rng.random((N, M)) ** 3 + 1e-4
+    B /= B.sum(axis=1)[:, None]
+    sym = [rng.integers(0, M, size=Tk).astype(np.int32) for Tk in (1500, 801, 60)]
+    b = TrajectoryBatch(sym, N, chunk=200, warm=0)
+    stats, Bnum = b.estep_discrete(A, pi, B)
+    st = unpack_stats(stats.cpu().numpy(), N)
+    rd = orc.estep_discrete(sym, A, pi, B)
+    check('wide N=100 discrete: loglik', abs(st['loglik'] - rd['loglik']) <= RTOL * abs(rd['loglik']))
+    for key, got, r in (('C', st['C'], rd['C']), ('gamma0', st['gamma0'], rd['gamma0']), ('Bnum', Bnum.cpu().numpy(), rd['Bnum'])):
+        ok, worst = close(got, r, 1e-9, 1e-13)
+        check('wide N=100 discrete: ' + key, ok, 'worst rel %.2e' % worst)
+    b.close()
 
 
 def timing():
@@ -141,11 +206,14 @@ if __name__ == '__main__':
     assert torch.cuda.is_available(), 'needs a CUDA device'
     if CHILD:
         timing()
+        timing_wide()
         sys.exit(0)
     t0 = time.time()
     parity()
+    parity_wide()
     print('parity: %d failure(s) in %.1f s' % (len(failures), time.time() - t0), flush=True)
     if '--quick' not in sys.argv and not failures:
         timing()
+        timing_wide()
         subprocess.run([sys.executable, os.path.abspath(__file__), '--team-child'], timeout=600)
     sys.exit(1 if failures else 0)
