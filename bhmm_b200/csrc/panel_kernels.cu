@@ -700,9 +700,15 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_forward_wide(const FwdArgs a)
             if (s > 0) {
                 const int tp = t0 - maxpre + s - 1;
                 const bool onp = have && tp >= tstart && tp < tend;
+                // every quad sums the NT tile partials of its chain: lane q takes tiles q, q+4, ... (the same order in
+                // every warp, so all warps derive the bitwise identical chain sum)
                 double cs = 0.0, cd = 0.0, nz = 0.0;
 #pragma unroll
-                for (int w2 = 0; w2 < NT; ++w2) { cs += red[prev][0][w2][g]; cd += red[prev][1][w2][g]; nz += red[prev][2][w2][g]; }
+                for (int w2 = 0; w2 < NT; w2 += 4)
+                    if (w2 + q < NT) { cs += red[prev][0][w2 + q][g]; cd += red[prev][1][w2 + q][g]; nz += red[prev][2][w2 + q][g]; }
+                cs = quad_sum(cs);
+                cd = quad_sum(cd);
+                nz = quad_sum(nz);
                 if (EM != EM_POBS && a.em.ignore_outliers && onp && nz == 0.0) { use_d = true; cs = cd; }   // outputmodel.py:126-130
                 rc = (cs != 0.0) ? 1.0 / cs : 1.0;          // _hidden.c:31-34, :58-61: divide iff c != 0
                 if (onp) {
@@ -901,7 +907,9 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide(const BwdArgs a)
 
             double nz = 0.0;
 #pragma unroll
-            for (int w2 = 0; w2 < NT; ++w2) nz += redn[w2][g];
+            for (int w2 = 0; w2 < NT; w2 += 4)
+                if (w2 + q < NT) nz += redn[w2 + q][g];
+            nz = quad_sum(nz);
             const bool use_b = (EM != EM_POBS) && a.em.ignore_outliers && act && nz == 0.0;   // outputmodel.py:126-130
             const double* src = (use_b ? Sb[cur] : Sw[cur]) + g * NPS;
             double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
@@ -929,7 +937,10 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide(const BwdArgs a)
 
             double S = 0.0, sbn = 0.0;
 #pragma unroll
-            for (int w2 = 0; w2 < NT; ++w2) { S += red[0][w2][g]; sbn += red[1][w2][g]; }
+            for (int w2 = 0; w2 < NT; w2 += 4)
+                if (w2 + q < NT) { S += red[0][w2 + q][g]; sbn += red[1][w2 + q][g]; }
+            S = quad_sum(S);
+            sbn = quad_sum(sbn);
             const double rS = 1.0 / S;
             *reinterpret_cast<double2*>(&Su[g * NPS + s0]) = make_double2(xi ? al0 * rS : 0.0, xi ? al1 * rS : 0.0);
             pending_xi = __any_sync(FULL, xi);
