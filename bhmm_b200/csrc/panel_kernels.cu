@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(PW * 32) k_forward_panel32(const FwdArgs a)
             const bool init = on && t == tstart;
             const Raw<EM> raw = raw_next;
             fetch(s + 1, raw_next);
-            if (have && t + 48 < tend) raw_prefetch<EM>(a.em, trow + max(t, tstart) + 48, q);
+            if (have && max(t, tstart) + 48 < tend) raw_prefetch<EM>(a.em, trow + max(t, tstart) + 48, q);
 
             double p[8];
             emission8<EM>(raw, kc, q, p);
@@ -610,17 +610,25 @@ struct WideGeom {
 #define WIDE_KERNEL_ATTR(NT) __maxnreg__(WideGeom<NT>::MAXREG)
 #endif
 
-// density of (row, state) for the wide kernels: one state at a time (2 per lane and frame)
-template <int EM>
-__device__ __forceinline__ double wide_density(const Emission& em, long long row, int state, int N, double o, int sym,
-                                               double mu, double isg, double lnrm)
+// Emission pipeline of the wide kernels (2 states per lane and frame).  Gaussian: the observation is fetched one frame
+// ahead and the two densities are evaluated in the frame.  Table / discrete: the two densities themselves are fetched one
+// frame ahead, and for the discrete model the symbol that addresses them one frame before that, so neither dependent load
+// sits on a frame's critical path.
+__device__ __forceinline__ void wide_gauss2(double o, const double (&mu)[2], const double (&isg)[2], const double (&lnrm)[2],
+                                            bool ok0, bool ok1, double (&p)[2])
 {
-    if (EM == EM_GAUSS) {
-        const double d = (o - mu) * isg;
-        return exp(fma(-d, d, lnrm));
-    }
-    if (EM == EM_POBS) return em.pobs[row * N + state];
-    return em.Bt[(long long)sym * N + state];
+    const double d0 = (o - mu[0]) * isg[0], d1 = (o - mu[1]) * isg[1];
+    p[0] = ok0 ? exp(fma(-d0, d0, lnrm[0])) : 0.0;
+    p[1] = ok1 ? exp(fma(-d1, d1, lnrm[1])) : 0.0;
+}
+
+template <int EM>
+__device__ __forceinline__ void wide_table2(const Emission& em, long long row, int sym, int N, int s0, bool ok0, bool ok1,
+                                            double (&p)[2])
+{
+    const double* src = (EM == EM_POBS) ? em.pobs + row * N : em.Bt + (long long)sym * N;
+    p[0] = ok0 ? src[s0] : 0.0;
+    p[1] = ok1 ? src[s0 + 1] : 0.0;
 }
 
 template <int EM, int NT>
@@ -687,10 +695,16 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_forward_wide(const FwdArgs a)
             t = min(max(t, tstart + (mode == 2 ? 1 : 0)), tend - 1);
             return trow + t;
         };
-        double o_next = 0.0;
-        int sym_next = 0;
-        if (have && EM == EM_GAUSS) o_next = a.em.obs[frame_row(0)];
-        if (have && EM == EM_DISC) sym_next = a.em.sym[frame_row(0)];
+        double o_next = 0.0, pn[2] = {0.0, 0.0};
+        int symA = 0;                                       // discrete: symbol of the frame after the one whose densities are in pn
+        if (have) {
+            if (EM == EM_GAUSS) o_next = a.em.obs[frame_row(0)];
+            if (EM == EM_DISC) {
+                wide_table2<EM>(a.em, 0, a.em.sym[frame_row(0)], N, s0, ok0, ok1, pn);
+                symA = a.em.sym[frame_row(1)];
+            }
+            if (EM == EM_POBS) wide_table2<EM>(a.em, frame_row(0), 0, N, s0, ok0, ok1, pn);
+        }
 
         for (int s = 0; s <= total; ++s) {
             const int cur = s & 1, prev = cur ^ 1;
@@ -735,15 +749,21 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_forward_wide(const FwdArgs a)
             const int t = t0 - maxpre + s;
             const bool on = have && t >= tstart && t < tend;
             const bool init = on && t == tstart;
-            const long long row = frame_row(s);
-            const double o = o_next;
-            const int sym = sym_next;
-            if (have && EM == EM_GAUSS) o_next = a.em.obs[frame_row(s + 1)];
-            if (have && EM == EM_DISC) sym_next = a.em.sym[frame_row(s + 1)];
             double p[2] = {0.0, 0.0};
             if (have) {
-                if (ok0) p[0] = wide_density<EM>(a.em, row, s0, N, o, sym, mu[0], isg[0], lnrm[0]);
-                if (ok1) p[1] = wide_density<EM>(a.em, row, s0 + 1, N, o, sym, mu[1], isg[1], lnrm[1]);
+                if (EM == EM_GAUSS) {
+                    const double o = o_next;
+                    o_next = a.em.obs[frame_row(s + 1)];
+                    wide_gauss2(o, mu, isg, lnrm, ok0, ok1, p);
+                } else {
+                    p[0] = pn[0]; p[1] = pn[1];
+                    if (EM == EM_DISC) {
+                        wide_table2<EM>(a.em, 0, symA, N, s0, ok0, ok1, pn);
+                        symA = a.em.sym[frame_row(s + 2)];
+                    } else {
+                        wide_table2<EM>(a.em, frame_row(s + 1), 0, N, s0, ok0, ok1, pn);
+                    }
+                }
             }
             const double* src = (use_d ? Sd[prev] : Sx[prev]) + g * NPS;
             double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;  // two accumulator pairs halve the dependent DMMA chain
@@ -865,11 +885,15 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide(const BwdArgs a)
         auto frame_of = [&](int s) -> int { return (e - 1) + maxpre - s; };
         auto em_row = [&](int s) -> long long { return trow + min(max(frame_of(s), t0), T - 1); };
         auto al_row = [&](int s) -> long long { return trow + min(max(frame_of(s) - 1, t0), e - 1); };
-        double o_next = 0.0, al_next[2] = {0.0, 0.0};
-        int sym_next = 0;
+        double o_next = 0.0, al_next[2] = {0.0, 0.0}, pn[2] = {0.0, 0.0};
+        int symA = 0;                                       // discrete: symbol of the step after the one whose densities are in pn
         if (have) {
             if (EM == EM_GAUSS) o_next = a.em.obs[em_row(0)];
-            if (EM == EM_DISC) sym_next = a.em.sym[em_row(0)];
+            if (EM == EM_DISC) {
+                wide_table2<EM>(a.em, 0, a.em.sym[em_row(0)], N, s0, ok0, ok1, pn);
+                symA = a.em.sym[em_row(1)];
+            }
+            if (EM == EM_POBS) wide_table2<EM>(a.em, em_row(0), 0, N, s0, ok0, ok1, pn);
             if (ok0) al_next[0] = a.alpha[al_row(0) * N + s0];
             if (ok1) al_next[1] = a.alpha[al_row(0) * N + s0 + 1];
         }
@@ -880,19 +904,26 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide(const BwdArgs a)
             const int f = frame_of(s);
             const bool on = have && f <= fstart && f >= flast;
             const bool isvirt = on && virt && f == T;
-            const long long row = em_row(s);
-            const double o = o_next, al0 = al_next[0], al1 = al_next[1];
-            const int sym = sym_next;
+            const double al0 = al_next[0], al1 = al_next[1];
+            double p[2] = {0.0, 0.0};
+            int sym_emit = 0;                               // symbol of frame f-1, the frame this step emits
             if (have) {
-                if (EM == EM_GAUSS) o_next = a.em.obs[em_row(s + 1)];      // frame f-1: also the emitted frame's observation
-                if (EM == EM_DISC) sym_next = a.em.sym[em_row(s + 1)];
                 if (ok0) al_next[0] = a.alpha[al_row(s + 1) * N + s0];
                 if (ok1) al_next[1] = a.alpha[al_row(s + 1) * N + s0 + 1];
-            }
-            double p[2] = {0.0, 0.0};
-            if (have) {
-                if (ok0) p[0] = wide_density<EM>(a.em, row, s0, N, o, sym, mu[0], isg[0], lnrm[0]);
-                if (ok1) p[1] = wide_density<EM>(a.em, row, s0 + 1, N, o, sym, mu[1], isg[1], lnrm[1]);
+                if (EM == EM_GAUSS) {
+                    const double o = o_next;
+                    o_next = a.em.obs[em_row(s + 1)];       // frame f-1: also the emitted frame's observation
+                    wide_gauss2(o, mu, isg, lnrm, ok0, ok1, p);
+                } else {
+                    p[0] = pn[0]; p[1] = pn[1];
+                    if (EM == EM_DISC) {
+                        sym_emit = symA;
+                        wide_table2<EM>(a.em, 0, symA, N, s0, ok0, ok1, pn);
+                        symA = a.em.sym[em_row(s + 2)];
+                    } else {
+                        wide_table2<EM>(a.em, em_row(s + 1), 0, N, s0, ok0, ok1, pn);
+                    }
+                }
             }
             const bool act = on && !isvirt;
             double wv[2] = {act ? p[0] * bn[0] : 0.0, act ? p[1] * bn[1] : 0.0};
@@ -957,7 +988,7 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide(const BwdArgs a)
                         st_gd[r] = fma(gam[r], dv, st_gd[r]);
                         st_gdd[r] = fma(gam[r], dv * dv, st_gdd[r]);
                     }
-                    if (EM == EM_DISC && a.Bnum) atomicAdd(a.Bnum + (long long)(s0 + r) * a.em.M + sym_next, gam[r]);
+                    if (EM == EM_DISC && a.Bnum) atomicAdd(a.Bnum + (long long)(s0 + r) * a.em.M + sym_emit, gam[r]);
                     if (a.gamma) a.gamma[orow * N + s0 + r] = gam[r];
                 }
                 if (f - 1 == t0 && t0 > 0) {
