@@ -1065,21 +1065,25 @@ int panel_blocks(int n_chains)
     return (int)std::max(1LL, std::min(groups, cap));
 }
 
-// wide kernels: state tiles (= warps per block) for N, 0 if N is not served
-int wide_tiles(int N) { return (N <= 32) ? 0 : (N <= 64 ? 8 : (N <= 104 ? 13 : 0)); }
+// wide kernels: state tiles (= warps per block) for N, 0 if N is not served (N <= 16 belongs to the lane family)
+int wide_tiles(int N) { return (N <= 16) ? 0 : (N <= 32 ? 4 : (N <= 64 ? 8 : (N <= 104 ? 13 : 0))); }
+
+#define WIDE_DISPATCH(NTV, CALL4, CALL8, CALL13) \
+    do { if ((NTV) == 4) { CALL4; } else if ((NTV) == 8) { CALL8; } else { CALL13; } } while (0)
 
 int wide_blocks_per_sm(int NT)
 {
-    static int per8 = 0, per13 = 0;
-    int& per = (NT == 8) ? per8 : per13;
-    if (per == 0) {
+    static int per[17] = {0};
+    if (per[NT] == 0) {
         int v = 0;
-        cudaError_t e = (NT == 8)
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 8>, 8 * 32, 0)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 13>, 13 * 32, 0);
-        per = (e == cudaSuccess && v > 0) ? v : 1;
+        cudaError_t e = cudaErrorUnknown;
+        WIDE_DISPATCH(NT,
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 4>, 4 * 32, 0),
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 8>, 8 * 32, 0),
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 13>, 13 * 32, 0));
+        per[NT] = (e == cudaSuccess && v > 0) ? v : 1;
     }
-    return per;
+    return per[NT];
 }
 
 int wide_blocks(int NT, int n_chains)
@@ -1095,16 +1099,17 @@ template <int EM>
 int launch_forward_wide_em(const FwdArgs& a, int NT, cudaStream_t st)
 {
     const int grid = wide_blocks(NT, a.ch.n);
-    if (NT == 8) k_forward_wide<EM, 8><<<grid, 8 * 32, 0, st>>>(a);
-    else k_forward_wide<EM, 13><<<grid, 13 * 32, 0, st>>>(a);
+    WIDE_DISPATCH(NT, (k_forward_wide<EM, 4><<<grid, 4 * 32, 0, st>>>(a)), (k_forward_wide<EM, 8><<<grid, 8 * 32, 0, st>>>(a)),
+                  (k_forward_wide<EM, 13><<<grid, 13 * 32, 0, st>>>(a)));
     return BHMM_OK;
 }
 
 template <int EM>
 int launch_backward_wide_em(const BwdArgs& a, int NT, cudaStream_t st)
 {
-    if (NT == 8) k_backward_stats_wide<EM, 8><<<a.grid, 8 * 32, 0, st>>>(a);
-    else k_backward_stats_wide<EM, 13><<<a.grid, 13 * 32, 0, st>>>(a);
+    WIDE_DISPATCH(NT, (k_backward_stats_wide<EM, 4><<<a.grid, 4 * 32, 0, st>>>(a)),
+                  (k_backward_stats_wide<EM, 8><<<a.grid, 8 * 32, 0, st>>>(a)),
+                  (k_backward_stats_wide<EM, 13><<<a.grid, 13 * 32, 0, st>>>(a)));
     return BHMM_OK;
 }
 #endif   // PANEL_HOST_EMU
@@ -1112,31 +1117,36 @@ int launch_backward_wide_em(const BwdArgs& a, int NT, cudaStream_t st)
 }  // namespace
 
 #ifndef PANEL_HOST_EMU
-bool panel_enabled(int N)
+// BHMM_B200_PANEL: unset / 0 = off; 1 = N = 32 on the one-warp-per-8-chains kernels, 17 <= N <= 104 otherwise on the wide
+// kernels; 2 = N = 32 on the wide kernels too (4 warps per 8 chains: a third of the registers, more resident warps)
+static int panel_mode()
 {
-    static int on = -1;
-    if (on < 0) {
+    static int mode = -1;
+    if (mode < 0) {
         const char* e = getenv("BHMM_B200_PANEL");
-        on = (e && strcmp(e, "1") == 0) ? 1 : 0;
+        mode = (e && strcmp(e, "1") == 0) ? 1 : ((e && strcmp(e, "2") == 0) ? 2 : 0);
     }
-    return on == 1 && (N == PN || wide_tiles(N) > 0);
+    return mode;
 }
+static bool use_panel32(int N) { return N == PN && panel_mode() == 1; }
+
+bool panel_enabled(int N) { return panel_mode() > 0 && wide_tiles(N) > 0; }
 
 // threads per block and chains per row of partial statistics (N = 32: a row per warp; wide: a row per block)
 void panel_shape(int N, int* threads, int* chains_per_row)
 {
-    *threads = (N == PN) ? PW * 32 : wide_tiles(N) * 32;
+    *threads = use_panel32(N) ? PW * 32 : wide_tiles(N) * 32;
     *chains_per_row = PCH;
 }
 
 int panel_stats_rows(int N, int n_chains)
 {
-    return (N == PN) ? panel_blocks(n_chains) * PW : wide_blocks(wide_tiles(N), n_chains);
+    return use_panel32(N) ? panel_blocks(n_chains) * PW : wide_blocks(wide_tiles(N), n_chains);
 }
 
 bool panel_forward_ok(const FwdArgs& a, int em)
 {
-    if (a.N != PN) return wide_tiles(a.N) > 0;             // the wide kernels use scalar global accesses only
+    if (!use_panel32(a.N)) return wide_tiles(a.N) > 0;     // the wide kernels use scalar global accesses only
     bool ok = aligned16(a.A) && aligned16(a.pi) && aligned16(a.hand_end) && aligned16(a.hand_used) && (!a.alpha || aligned16(a.alpha));
     if (em == EM_POBS) ok = ok && aligned16(a.em.pobs);
     if (em == EM_DISC) ok = ok && aligned16(a.em.Bt);
@@ -1145,7 +1155,7 @@ bool panel_forward_ok(const FwdArgs& a, int em)
 
 bool panel_backward_ok(const BwdArgs& a, int em)
 {
-    if (a.N != PN) return wide_tiles(a.N) > 0 && a.grid > 0;
+    if (!use_panel32(a.N)) return wide_tiles(a.N) > 0 && a.grid > 0;
     bool ok = aligned16(a.A) && aligned16(a.alpha) && aligned16(a.partials) && aligned16(a.hand_end) && aligned16(a.hand_used)
               && (!a.gamma || aligned16(a.gamma)) && a.grid > 0 && a.grid % PW == 0;
     if (em == EM_POBS) ok = ok && aligned16(a.em.pobs);
@@ -1156,7 +1166,7 @@ bool panel_backward_ok(const BwdArgs& a, int em)
 int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st)
 {
     if (a.ch.n <= 0) return BHMM_OK;
-    if (a.N != PN) {
+    if (!use_panel32(a.N)) {
         const int NT = wide_tiles(a.N);
         if (NT == 0) return BHMM_ERR_UNSUPPORTED;
         switch (em) {
@@ -1179,7 +1189,7 @@ int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st)
 // row is written, chains or not
 int launch_backward_stats_panel(const BwdArgs& a, int em, cudaStream_t st)
 {
-    if (a.N != PN) {
+    if (!use_panel32(a.N)) {
         const int NT = wide_tiles(a.N);
         if (NT == 0) return BHMM_ERR_UNSUPPORTED;
         switch (em) {

@@ -28,6 +28,8 @@ Emission make_emission(const double* pobs, const double* obs, const int* sym, co
 
 }  // namespace
 
+static int g_force_wide = 0;     // N = 32 on the wide kernels (BHMM_B200_PANEL=2)
+extern "C" void panel_emu_force_wide(int on) { g_force_wide = on; }
 extern "C" int panel_emu_warps_per_block() { return PW; }
 
 extern "C" int panel_emu_forward(int N, int em_kind, int grid, const long long* row0, const int* len, const int* t0, const int* T,
@@ -40,11 +42,12 @@ extern "C" int panel_emu_forward(int N, int em_kind, int grid, const long long* 
     a.ch = make_chains(row0, len, t0, T, list, n_run, warm, warmv, exact);
     a.em = make_emission(pobs, obs, sym, mu, sigma, Bt, M, ignore_outliers);
     a.N = N; a.A = A; a.pi = pi; a.alpha = alpha; a.chain_ll = chain_ll; a.hand_used = hand_used; a.hand_end = hand_end;
-    if (N != PN) {
-        const int NT = (N <= 64) ? 8 : 13;
-        if (N <= 32 || N > 104) return 2;
+    if (N != PN || g_force_wide) {
+        const int NT = (N <= 32) ? 4 : ((N <= 64) ? 8 : 13);
+        if (N <= 16 || N > 104) return 2;
 #define FWD_WIDE(EMK) \
-        if (NT == 8) emu::launch(grid, 8 * 32, [&] { k_forward_wide<EMK, 8>(a); }); \
+        if (NT == 4) emu::launch(grid, 4 * 32, [&] { k_forward_wide<EMK, 4>(a); }); \
+        else if (NT == 8) emu::launch(grid, 8 * 32, [&] { k_forward_wide<EMK, 8>(a); }); \
         else emu::launch(grid, 13 * 32, [&] { k_forward_wide<EMK, 13>(a); }); \
         return 0;
         switch (em_kind) {
@@ -73,13 +76,14 @@ extern "C" int panel_emu_backward_stats(int N, int em_kind, int grid, const long
     BwdArgs a{};
     a.ch = make_chains(row0, len, t0, T, list, n_run, warm, warmv, exact);
     a.em = make_emission(pobs, obs, sym, mu, sigma, Bt, M, ignore_outliers);
-    a.N = N; a.grid = (N == PN) ? grid * PW : grid; a.A = A; a.alpha = alpha; a.gamma = gamma; a.Bnum = Bnum; a.partials = partials;
+    a.N = N; a.grid = (N == PN && !g_force_wide) ? grid * PW : grid; a.A = A; a.alpha = alpha; a.gamma = gamma; a.Bnum = Bnum; a.partials = partials;
     a.hand_used = hand_used; a.hand_end = hand_end;
-    if (N != PN) {
-        const int NT = (N <= 64) ? 8 : 13;
-        if (N <= 32 || N > 104) return 2;
+    if (N != PN || g_force_wide) {
+        const int NT = (N <= 32) ? 4 : ((N <= 64) ? 8 : 13);
+        if (N <= 16 || N > 104) return 2;
 #define BWD_WIDE(EMK) \
-        if (NT == 8) emu::launch(grid, 8 * 32, [&] { k_backward_stats_wide<EMK, 8>(a); }); \
+        if (NT == 4) emu::launch(grid, 4 * 32, [&] { k_backward_stats_wide<EMK, 4>(a); }); \
+        else if (NT == 8) emu::launch(grid, 8 * 32, [&] { k_backward_stats_wide<EMK, 8>(a); }); \
         else emu::launch(grid, 13 * 32, [&] { k_backward_stats_wide<EMK, 13>(a); }); \
         return 0;
         switch (em_kind) {

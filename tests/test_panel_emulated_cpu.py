@@ -35,6 +35,14 @@ def emu():
     return C.CDLL(so)
 
 
+@pytest.fixture
+def request_cleanup():
+    todo = []
+    yield todo
+    for fn in todo:
+        fn()
+
+
 def gauss(o, mu, sigma):
     return np.exp(-0.5 * ((o - mu) / sigma) ** 2) / (np.sqrt(2 * np.pi) * sigma)
 
@@ -90,6 +98,7 @@ class Run(object):
                  ignore_outliers=0):
         self.emu, self.plan, self.A, self.pi, self.kind = emu, plan, np.ascontiguousarray(A), np.ascontiguousarray(pi), em_kind
         self.N = PN = len(pi)
+        self.wide32 = False
         self.em = (ptr(pobs), ptr(obs), ptr(sym, C.c_int), ptr(mu), ptr(sigma), ptr(Bt), C.c_int(M), C.c_int(ignore_outliers))
         self._keep = (obs, pobs, sym, mu, sigma, Bt)
         n = len(plan[0])
@@ -116,7 +125,7 @@ class Run(object):
     def backward_stats(self, grid, warm, alpha, exact=0, gamma=None, Bnum=None):
         ch, keep = self._chains(warm, exact, None)
         PN = self.N
-        pw = self.emu.panel_emu_warps_per_block() if PN == 32 else 1
+        pw = self.emu.panel_emu_warps_per_block() if (PN == 32 and not self.wide32) else 1
         partials = np.full((grid * pw, PN * PN + 4 * PN), np.nan)     # every row must be written by its warp / block
         rc = self.emu.panel_emu_backward_stats(C.c_int(PN), C.c_int(self.kind), C.c_int(grid), *ch, *self.em, ptr(self.A),
                                                ptr(np.ascontiguousarray(alpha)), ptr(gamma), ptr(Bnum), ptr(partials),
@@ -257,10 +266,11 @@ def test_exp8_tail_far_observations(emu):
 
 
 # ------------------------------------------------------------------------------------------------ wide kernels, 32 < N <= 104
-@pytest.mark.parametrize('N,grid', [(100, 2), (37, 1), (64, 1)])
-def test_wide_gaussian_estep(emu, N, grid):
+@pytest.mark.parametrize('N,grid', [(100, 2), (37, 1), (64, 1), (32, 2), (21, 1)])
+def test_wide_gaussian_estep(emu, N, grid, request_cleanup):
     """k_forward_wide / k_backward_stats_wide: a block of N/8 warps per 8 chains, state tiles exchanged through shared memory.
-    N = 100 (C4's state count, padded to 104: 13 warps), an odd N with a half-empty last tile, and a full 64."""
+    N = 100 (C4's state count, padded to 104: 13 warps), an odd N with a half-empty last tile, a full 64, and the 4-warp
+    instance at N = 32 (the alternative to the one-warp kernels there) and N = 21."""
     rng, A, pi, mu, sigma = model(100 + N, N=N)
     Ts = [50, 33, 1, 41, 18, 29]
     trajs = [mu[rng.integers(0, N, T)] + 0.7 * rng.standard_normal(T) for T in Ts]
@@ -274,6 +284,9 @@ def test_wide_gaussian_estep(emu, N, grid):
         ps.append(p)
     ref = plain_estep(ps, A, pi)
     run = Run(emu, plan, A, pi, EM_GAUSS, obs=obs, mu=mu, sigma=sigma, ignore_outliers=1)
+    run.wide32 = True
+    emu.panel_emu_force_wide(1)                             # N = 32 on the wide kernels too (BHMM_B200_PANEL=2)
+    request_cleanup.append(lambda: emu.panel_emu_force_wide(0))
     run.forward(grid, warm=30)
     np.testing.assert_allclose(run.alpha, ref['alpha'], rtol=1e-10, atol=1e-300)
     assert abs(run.chain_ll.sum() - ref['ll']) <= 1e-12 * abs(ref['ll'])

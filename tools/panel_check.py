@@ -2,6 +2,7 @@
 
     timeout 900 python tools/panel_check.py            # parity against the oracle, then timing next to the team kernels
     timeout 600 python tools/panel_check.py --quick    # parity only (what tests/test_panel_cuda.py runs)
+    timeout 900 python tools/panel_check.py --mode=2   # N = 32 on the 4-warp wide kernels (BHMM_B200_PANEL=2)
 
 The panel family is selected by BHMM_B200_PANEL=1, which the library reads once per process; this script sets it for
 itself and times the team kernels in a child process without it.  Every GPU call sits under the caller's `timeout`: the
@@ -15,8 +16,9 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 CHILD = '--team-child' in sys.argv
+MODE = '2' if '--mode=2' in sys.argv else '1'      # 2: N = 32 on the 4-warp wide kernels instead of the one-warp kernels
 if not CHILD:
-    os.environ['BHMM_B200_PANEL'] = '1'
+    os.environ['BHMM_B200_PANEL'] = MODE
 else:
     os.environ.pop('BHMM_B200_PANEL', None)
 
@@ -71,7 +73,7 @@ def parity_wide():
     from oracle.oracle import Oracle
     orc = Oracle('port')
     rng = np.random.default_rng(43)
-    for N in (100, 37, 64):
+    for N in (100, 37, 64, 21):
         X = rng.random((N, N)) ** 2 + 1e-3
         A = X / X.sum(axis=1)[:, None]
         pi = rng.random(N) + 0.01
@@ -126,7 +128,7 @@ def timing():
     ms = timeit(lambda: b.estep_gaussian(A, pi, means, sigmas))
     st = unpack_stats(b.estep_gaussian(A, pi, means, sigmas).cpu().numpy(), N)
     print('%s N=32 gaussian K=%d T=%d: E-step %.2f ms -> %.3f G frames/s; kernels %s; info %s; loglik %.10e'
-          % ('team ' if CHILD else 'panel', K, T, ms, K * T / ms / 1e6, b.kernel_ms(), b.info(), st['loglik']), flush=True)
+          % ('team ' if CHILD else 'panel mode ' + MODE, K, T, ms, K * T / ms / 1e6, b.kernel_ms(), b.info(), st['loglik']), flush=True)
     b.close()
 
 
