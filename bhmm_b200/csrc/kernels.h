@@ -113,6 +113,8 @@ bool panel_forward_ok(const FwdArgs& a, int em);
 bool panel_backward_ok(const BwdArgs& a, int em);
 int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st);
 int launch_backward_stats_panel(const BwdArgs& a, int em, cudaStream_t st);
+bool panel_viterbi_ok(int N);                // 32 < N <= 104: Viterbi with the matrix column in registers
+int launch_viterbi_panel(const VitArgs& a, int em, cudaStream_t st);
 
 // ---- frame-parallel kernels (frame_kernels.cu)
 int launch_gaussian_pobs(const double* obs, const double* mu, const double* sigma, int N, long long rows,

@@ -1033,6 +1033,105 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide(const BwdArgs a)
     }
 }
 
+// ================================================================================================
+// Viterbi for 32 < N <= 104 with the transition-matrix column in registers (same opt-in as the panel kernels).
+// k_viterbi_team walks its two N-long loops (first-maximum scan, sequential row sum) one shared-memory round trip at a
+// time: ~6000 cycles per frame at N = 100 (C4: 4.27 s for 4096 x 1e5 frames).  Here thread j keeps A[:, j] in registers, the
+// scan runs as four independent first-maximum scans over index blocks that are combined in block order with the same
+// strict '>' (the earliest index among equal maxima wins either way, _hidden.c:186-200), and the row sum -- sequential by
+// definition of bit-exactness (_hidden.c:254-259) -- is an unrolled chain of additions fed by 16-byte loads.  Padded states
+// hold exact zeros, which neither win a strict comparison against a non-negative maximum nor change a sum.
+// Output: the shifted back-pointer map F[t][s'] of k_viterbi_team's CHASE mode (uint8), resolved by the k_chase_* kernels.
+// ================================================================================================
+template <int EM, int NMAX>
+__global__ void __launch_bounds__(((NMAX + 31) / 32) * 32) k_viterbi_regs(const VitArgs a)
+{
+    constexpr int Q = NMAX / 4;
+    __shared__ __align__(16) double ub[NMAX];              // unnormalised row
+    __shared__ __align__(16) double vb[NMAX];              // normalised row
+    const int N = a.N, j = threadIdx.x;
+    const bool jv = j < N;
+    double Acol[NMAX];
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) Acol[i] = (jv && i < N) ? a.A[i * N + j] : 0.0;
+    double mu = 0.0, sigma = 1.0;
+    if (EM == EM_GAUSS && jv) { mu = a.em.mu[j]; sigma = a.em.sigma[j]; }
+    const double pi_j = jv ? a.pi[j] : 0.0;
+    unsigned char* bp = reinterpret_cast<unsigned char*>(a.backptr);
+    for (int i = threadIdx.x; i < NMAX; i += blockDim.x) { ub[i] = 0.0; vb[i] = 0.0; }
+    __syncthreads();
+
+    auto em_raw = [&](long long row) -> double {
+        if (EM == EM_POBS) return a.em.pobs[row * N + j];
+        if (EM == EM_GAUSS) return a.em.obs[row];
+        return a.em.Bt[(long long)a.em.sym[row] * N + j];
+    };
+
+    for (int k = blockIdx.x; k < a.K; k += gridDim.x) {
+        const long long row0 = a.offsets[k];
+        const int T = (int)(a.offsets[k + 1] - row0);
+        double raw_next = (jv && T > 0) ? em_raw(row0) : 0.0;
+        for (int t = 0; t < T; ++t) {
+            const double raw = raw_next;
+            if (jv && t + 1 < T) raw_next = em_raw(row0 + t + 1);
+            double p = 0.0;
+            if (jv) p = (EM == EM_GAUSS) ? gauss_pdf(raw, mu, sigma) : raw;
+            if (EM != EM_POBS && a.em.ignore_outliers) {
+                if (!__syncthreads_or(p != 0.0 ? 1 : 0)) p = jv ? 1.0 : 0.0;       // outputmodel.py:126-130
+            }
+            double vn = 0.0;
+            int best = 0;
+            if (t == 0) {
+                vn = __dmul_rn(p, pi_j);
+            } else {
+                double m[4], vbest[4], abest[4];
+                int bi[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    vbest[b] = vb[b * Q];
+                    abest[b] = Acol[b * Q];
+                    m[b] = __dmul_rn(vbest[b], abest[b]);
+                    bi[b] = b * Q;
+                }
+#pragma unroll
+                for (int ii = 1; ii < Q; ++ii) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const double v = vb[b * Q + ii];
+                        const double h = __dmul_rn(v, Acol[b * Q + ii]);
+                        if (h > m[b]) { m[b] = h; bi[b] = b * Q + ii; vbest[b] = v; abest[b] = Acol[b * Q + ii]; }
+                    }
+                }
+                double mm = m[0], vsel = vbest[0], asel = abest[0];
+                best = bi[0];
+#pragma unroll
+                for (int b = 1; b < 4; ++b)
+                    if (m[b] > mm) { mm = m[b]; best = bi[b]; vsel = vbest[b]; asel = abest[b]; }
+                if (jv) {
+                    bp[(row0 + t - 1) * N + j] = (unsigned char)best;
+                    vn = __dmul_rn(__dmul_rn(p, vsel), asel);                    // (p_j v_best) A[best][j], _hidden.c:247-250
+                }
+            }
+            if (jv) ub[j] = vn;
+            __syncthreads();
+            double ssum = 0.0;
+#pragma unroll
+            for (int i = 0; i < NMAX; ++i) ssum = __dadd_rn(ssum, ub[i]);        // j-sequential, + 0.0 for the padding
+            if (jv) vb[j] = __ddiv_rn(vn, ssum);
+            __syncthreads();
+        }
+        // path[T-1] = first maximum of the last row (_hidden.c:268): the last row of the map holds it for every s'
+        if (T > 0) {
+            int best = 0;
+            double m = vb[0];
+            for (int i = 1; i < N; ++i)
+                if (vb[i] > m) { m = vb[i]; best = i; }
+            if (jv) bp[(row0 + T - 1) * N + j] = (unsigned char)best;
+        }
+        __syncthreads();
+    }
+}
+
 #ifndef PANEL_HOST_EMU
 int panel_sms()
 {
@@ -1142,6 +1241,34 @@ void panel_shape(int N, int* threads, int* chains_per_row)
 int panel_stats_rows(int N, int n_chains)
 {
     return use_panel32(N) ? panel_blocks(n_chains) * PW : wide_blocks(wide_tiles(N), n_chains);
+}
+
+// Viterbi with the matrix column in registers: 32 < N <= 104 (N <= 32 keeps the packed one-warp teams)
+bool panel_viterbi_ok(int N) { return panel_mode() > 0 && N > 32 && N <= 104; }
+
+template <int EM>
+static int launch_viterbi_regs_em(const VitArgs& a, cudaStream_t st)
+{
+    if (a.K <= 0) return BHMM_OK;
+    int per = 0;
+    if (a.N <= 64) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_viterbi_regs<EM, 64>, 64, 0) != cudaSuccess || per <= 0) per = 1;
+        k_viterbi_regs<EM, 64><<<(int)std::min<long long>(a.K, (long long)panel_sms() * per), 64, 0, st>>>(a);
+    } else {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_viterbi_regs<EM, 104>, 128, 0) != cudaSuccess || per <= 0) per = 1;
+        k_viterbi_regs<EM, 104><<<(int)std::min<long long>(a.K, (long long)panel_sms() * per), 128, 0, st>>>(a);
+    }
+    return BHMM_OK;
+}
+
+int launch_viterbi_panel(const VitArgs& a, int em, cudaStream_t st)
+{
+    switch (em) {
+        case EM_POBS: return launch_viterbi_regs_em<EM_POBS>(a, st);
+        case EM_GAUSS: return launch_viterbi_regs_em<EM_GAUSS>(a, st);
+        case EM_DISC: return launch_viterbi_regs_em<EM_DISC>(a, st);
+    }
+    return BHMM_ERR_INVALID;
 }
 
 bool panel_forward_ok(const FwdArgs& a, int em)

@@ -734,6 +734,7 @@ static int launch_viterbi_em(const VitArgs& a, cudaStream_t st)
 int launch_viterbi_team(const VitArgs& a, int em, cudaStream_t st)
 {
     if (a.N < 1 || a.N > 1024) return BHMM_ERR_UNSUPPORTED;
+    if (panel_viterbi_ok(a.N)) return launch_viterbi_panel(a, em, st);
     switch (em) {
         case EM_POBS: return launch_viterbi_em<EM_POBS>(a, st);
         case EM_GAUSS: return launch_viterbi_em<EM_GAUSS>(a, st);

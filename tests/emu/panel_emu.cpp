@@ -100,3 +100,24 @@ extern "C" int panel_emu_backward_stats(int N, int em_kind, int grid, const long
     }
     return 1;
 }
+
+// Viterbi with the matrix column in registers; backptr: (rows, N) uint8 shifted back-pointer map (CHASE layout)
+extern "C" int panel_emu_viterbi(int N, int em_kind, int grid, int K, const long long* offsets, const double* pobs,
+                                 const double* obs, const int* sym, const double* mu, const double* sigma, const double* Bt,
+                                 int M, int ignore_outliers, const double* A, const double* pi, unsigned char* backptr)
+{
+    VitArgs a{};
+    a.em = make_emission(pobs, obs, sym, mu, sigma, Bt, M, ignore_outliers);
+    a.N = N; a.K = K; a.offsets = offsets; a.A = A; a.pi = pi; a.backptr = backptr; a.path = nullptr;
+    if (N <= 32 || N > 104) return 2;
+#define VIT(EMK) \
+    if (N <= 64) emu::launch(grid, 64, [&] { k_viterbi_regs<EMK, 64>(a); }); \
+    else emu::launch(grid, 128, [&] { k_viterbi_regs<EMK, 104>(a); }); \
+    return 0;
+    switch (em_kind) {
+        case EM_POBS: VIT(EM_POBS)
+        case EM_GAUSS: VIT(EM_GAUSS)
+        case EM_DISC: VIT(EM_DISC)
+    }
+    return 1;
+}

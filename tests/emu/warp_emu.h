@@ -129,6 +129,20 @@ inline void launch(int grid, int threads, const std::function<void()>& kernel_bo
 #define gridDim (emu::grid_dim())
 
 inline void __syncthreads() { emu::rendezvous(emu::block_group()); }
+inline int __syncthreads_or(int pred)
+{
+    static int acc[2];
+    static unsigned long phase = 0;
+    // two rendez-vous: everybody contributes, everybody reads; the accumulator alternates so that a fast fiber's next call
+    // cannot clear a value a slow fiber has not read yet
+    const unsigned long my = phase;
+    if (pred) acc[my & 1] = 1;
+    emu::rendezvous(emu::block_group());
+    const int r = acc[my & 1];
+    if (phase == my) { phase = my + 1; acc[(my + 1) & 1] = 0; }
+    emu::rendezvous(emu::block_group());
+    return r;
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::rendezvous(emu::my_warp().g); }
 
 inline double __shfl_xor_sync(unsigned, double v, int off)
@@ -177,6 +191,9 @@ inline void emu_dmma(double& d0, double& d1, double a, double b)
     }
     emu::rendezvous(w.g);
 }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 inline double atomicAdd(double* p, double v) { const double o = *p; *p = o + v; return o; }
 inline int __double2hiint(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(b >> 32); }
 inline int __double2loint(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(b & 0xffffffff); }

@@ -346,3 +346,74 @@ def test_wide_discrete_c4_shape_and_fix_up(emu):
     want = np.zeros((N, M))
     np.add.at(want.T, sym, ref['gamma'])
     np.testing.assert_allclose(Bnum, want, rtol=1e-9, atol=1e-14)
+
+
+# ------------------------------------------------------------------------------------------------ Viterbi, 32 < N <= 104
+def _resolve(F, T):
+    """Path from the shifted back-pointer map (CHASE layout of k_viterbi_team / k_viterbi_regs)."""
+    path = np.zeros(T, dtype=np.int32)
+    path[T - 1] = F[T - 1, 0]
+    for t in range(T - 2, -1, -1):
+        path[t] = F[t, path[t + 1]]
+    return path
+
+
+@pytest.mark.parametrize('N', [100, 40, 64])
+def test_viterbi_regs_is_bit_exact(emu, oracle_port, N):
+    """k_viterbi_regs (matrix column in registers, four interleaved first-maximum scans, unrolled sequential row sum) against
+    the oracle's restatement of _compute_viterbi (_hidden.c:203-281): identical paths, including exact ties (a model with
+    repeated rows / columns and repeated emission values makes ties common) and an outlier frame in the discrete model."""
+    rng = np.random.default_rng(N)
+    M = 9
+    X = rng.integers(1, 4, size=(N, N)).astype(float)       # small integers: many exactly equal products
+    X += 6.0 * np.eye(N)
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    B = rng.integers(0, 3, size=(N, M)).astype(float) + 0.0
+    B[:, 4] = 0.0
+    B[:, 0] += 1.0
+    B /= B.sum(axis=1)[:, None]
+    Ts = [57, 1, 23, 40, 2]
+    syms = [rng.integers(0, M, T).astype(np.int32) for T in Ts]
+    syms[0][20] = 4                                         # no state emits symbol 4
+    sym = np.concatenate(syms)
+    offsets = np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64)
+    Bt = np.ascontiguousarray(B.T)
+    A = np.ascontiguousarray(A)
+    rows = int(offsets[-1])
+    for grid in (2, 7):
+        F = np.full((rows, N), 255, dtype=np.uint8)
+        rc = emu.panel_emu_viterbi(C.c_int(N), C.c_int(EM_DISC), C.c_int(grid), C.c_int(len(Ts)), ptr(offsets, C.c_longlong),
+                                   None, None, ptr(sym, C.c_int), None, None, ptr(Bt), C.c_int(M), C.c_int(1), ptr(A),
+                                   ptr(pi), F.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        assert rc == 0
+        for k, T in enumerate(Ts):
+            pobs = oracle_port.discrete_p_obs(syms[k], B)
+            pobs[pobs.sum(axis=1) == 0] = 1.0
+            want = oracle_port.viterbi(A, pobs, pi)
+            got = _resolve(F[offsets[k]:offsets[k + 1]], T)
+            assert np.array_equal(got, want), (N, grid, k)
+    # structural ties ACROSS the four scan blocks: a rank-one transition matrix and emission rows that repeat with period 3,
+    # so every state has N/3 exact twins and only the first-maximum rule decides
+    A1 = np.full((N, N), 1.0 / N)
+    B1 = np.array([[0.5, 0.25, 0.25], [0.25, 0.5, 0.25], [0.125, 0.125, 0.75]])[np.arange(N) % 3]
+    s1 = rng.integers(0, 3, 50).astype(np.int32)
+    off1 = np.array([0, 50], dtype=np.int64)
+    F = np.zeros((50, N), dtype=np.uint8)
+    rc = emu.panel_emu_viterbi(C.c_int(N), C.c_int(EM_DISC), C.c_int(1), C.c_int(1), ptr(off1, C.c_longlong), None, None,
+                               ptr(s1, C.c_int), None, None, ptr(np.ascontiguousarray(B1.T)), C.c_int(3), C.c_int(0),
+                               ptr(A1), ptr(pi), F.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    assert rc == 0
+    want = oracle_port.viterbi(A1, oracle_port.discrete_p_obs(s1, B1), pi)
+    assert np.array_equal(_resolve(F, 50), want)
+    assert len(set(want.tolist())) <= 3 and want.max() <= 2          # always the FIRST of the twins
+    # caller's table (EM_POBS), continuous densities
+    T = 35
+    pobs = np.ascontiguousarray(rng.random((T, N)) ** 4)
+    F = np.zeros((T, N), dtype=np.uint8)
+    off1 = np.array([0, T], dtype=np.int64)
+    rc = emu.panel_emu_viterbi(C.c_int(N), C.c_int(EM_POBS), C.c_int(1), C.c_int(1), ptr(off1, C.c_longlong), ptr(pobs),
+                               None, None, None, None, None, C.c_int(0), C.c_int(0), ptr(A), ptr(pi),
+                               F.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    assert rc == 0
+    assert np.array_equal(_resolve(F, T), oracle_port.viterbi(A, pobs, pi))

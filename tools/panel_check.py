@@ -65,6 +65,8 @@ def timing_wide():
     st = unpack_stats(b.estep_discrete(A, pi, B)[0].cpu().numpy(), N)
     print('%s N=100 discrete M=1000 K=%d T=%d: E-step %.2f ms -> %.4f G frames/s; kernels %s; info %s; loglik %.10e'
           % ('team ' if CHILD else 'panel', K, T, ms, K * T / ms / 1e6, b.kernel_ms(), b.info(), st['loglik']), flush=True)
+    ms = timeit(lambda: b.viterbi_discrete(A, pi, B), reps=1)
+    print('      Viterbi %.2f ms -> %.4f G frames/s' % (ms, K * T / ms / 1e6), flush=True)
     b.close()
 
 
@@ -113,6 +115,9 @@ def parity_wide():
     stats, Bnum = b.estep_discrete(A, pi, B)
     st = unpack_stats(stats.cpu().numpy(), N)
     rd = orc.estep_discrete(sym, A, pi, B)
+    paths = b.split(b.viterbi_discrete(A, pi, B).cpu().numpy())
+    check('viterbi N=100 discrete (matrix column in registers): paths bit-exact',
+          all(np.array_equal(p_, orc.viterbi(A, orc.discrete_p_obs(o_, B), pi)) for o_, p_ in zip(sym, paths)))
     check('wide N=100 discrete: loglik', abs(st['loglik'] - rd['loglik']) <= RTOL * abs(rd['loglik']))
     for key, got, r in (('C', st['C'], rd['C']), ('gamma0', st['gamma0'], rd['gamma0']), ('Bnum', Bnum.cpu().numpy(), rd['Bnum'])):
         ok, worst = close(got, r, 1e-9, 1e-13)
