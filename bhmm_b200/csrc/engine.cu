@@ -496,11 +496,40 @@ static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const do
     if (!b->own_lo.empty()) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "Viterbi needs whole trajectories (batch has owned ranges)"); return BHMM_ERR_UNSUPPORTED; }
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
-    VitArgs a{};
-    a.em = em; a.N = N; a.K = b->K; a.offsets = b->d_offsets; a.A = b->d_A; a.pi = b->d_pi;
-    a.backptr = b->d_F; a.path = d_path;
-    RC_TRY(launch_viterbi_team(a, emkind, st));
-    LAUNCHED(1);
+    // Opt-in (BHMM_B200_PANEL): trajectories that the plan cuts into chains (one very long trajectory, C5) run their
+    // max-product recursions chain-parallel with certified hand-overs; if any decision's margin is too small to be
+    // certified, or the hand-overs cannot be certified, the sequential kernel below recomputes the whole map.
+    bool map_done = false;
+    if (panel_viterbi_chain_ok(N) && b->w.chunked) {
+        CUDA_TRY(cudaMemsetAsync(b->d_err + 1, 0, sizeof(int), st));
+        VitChainArgs va{};
+        va.em = em; va.N = N; va.A = b->d_A; va.pi = b->d_pi; va.backptr = b->d_F;
+        va.hand_used = b->w.hu_f; va.hand_end = b->w.he_f; va.flagged = b->d_err + 1;
+        va.margin_min = 1e-9;                               // four orders above the certification tolerance (1e-13)
+        b->w.ch.warm = b->warm_f;
+        const int rc = run_chains_certified(b->w, N, +1, [&](const Chains& ch, cudaStream_t s2) {
+            VitChainArgs x = va;
+            x.ch = ch;
+            return launch_viterbi_chain(x, emkind, s2);
+        }, b->info, st);
+        if (rc == BHMM_OK) {
+            int flagged = 0;
+            CUDA_TRY(cudaMemcpyAsync(&flagged, b->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            map_done = (flagged == 0);
+        } else if (rc != BHMM_ERR_NOT_CERTIFIED) {
+            return rc;
+        } else {
+            bhmm_set_error(BHMM_OK, "");
+        }
+    }
+    if (!map_done) {
+        VitArgs a{};
+        a.em = em; a.N = N; a.K = b->K; a.offsets = b->d_offsets; a.A = b->d_A; a.pi = b->d_pi;
+        a.backptr = b->d_F; a.path = d_path;
+        RC_TRY(launch_viterbi_team(a, emkind, st));
+        LAUNCHED(1);
+    }
     if (N <= 256) {     // uint8 maps written by the kernel: resolve the paths by segment-wise map composition
         RC_TRY(launch_chase(b->d_F, b->seg, N, b->seg_map, b->seg_enter, d_path, st));
         LAUNCHED(3);

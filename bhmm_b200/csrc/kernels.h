@@ -43,6 +43,22 @@ struct VitArgs {
     int* path;               // (rows) int32 output
 };
 
+// Time-chunked Viterbi (panel_kernels.cu:k_viterbi_chain32): the chains of a long trajectory run their max-product
+// recursions in parallel after a warm-up, hand-overs are certified like the forward filter's, and every decision's margin
+// between best and second-best candidate is tracked so that the certified hand-over tolerance cannot have changed it.
+struct VitChainArgs {
+    Chains ch;
+    Emission em;
+    int N;
+    const double* A;
+    const double* pi;
+    void* backptr;           // (rows, N) uint8 shifted back-pointer map (CHASE layout of k_viterbi_team)
+    double* hand_used;       // (n_chains_total, N): normalised max-product vector at t0-1 the chain was started from
+    double* hand_end;        // (n_chains_total, N): the chain's vector at its last frame
+    int* flagged;            // device counter: chains with a decision whose relative margin is below margin_min
+    double margin_min;
+};
+
 // ---- lane family (lane_kernels.cu): one thread per chain, N <= LANE_MAX_N
 constexpr int LANE_MAX_N = 16;
 template <int N>
@@ -115,6 +131,8 @@ int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st);
 int launch_backward_stats_panel(const BwdArgs& a, int em, cudaStream_t st);
 bool panel_viterbi_ok(int N);                // 32 < N <= 104: Viterbi with the matrix column in registers
 int launch_viterbi_panel(const VitArgs& a, int em, cudaStream_t st);
+bool panel_viterbi_chain_ok(int N);          // N <= 32: time-chunked Viterbi for trajectories cut into chains
+int launch_viterbi_chain(const VitChainArgs& a, int em, cudaStream_t st);
 
 // ---- frame-parallel kernels (frame_kernels.cu)
 int launch_gaussian_pobs(const double* obs, const double* mu, const double* sigma, int N, long long rows,

@@ -1132,6 +1132,142 @@ __global__ void __launch_bounds__(((NMAX + 31) / 32) * 32) k_viterbi_regs(const 
     }
 }
 
+// ================================================================================================
+// Time-chunked Viterbi, N <= 32 (C5: one trajectory of 1e9 frames, where the strictly sequential recursion of
+// k_viterbi_team would take minutes).  One warp per chain, lane j = state j, A[:, j] in registers.  A chain that does not
+// start its trajectory warms its normalised max-product vector up on the frames before it (the max-product filter forgets
+// its start like the sum-product one once the survivor paths have coalesced); the hand-over is certified afterwards by
+// the same component-wise relative comparison as the forward filter's (certify.cu), with exact re-runs of the chains that
+// fail.  Arithmetic per frame is exactly k_viterbi_team's (_hidden.c:229-265 operation order).  Because a certified
+// hand-over still differs from the sequential one in the last digits, a decision (arg max over predecessors) is only
+// provably the sequential one if its best and second-best candidates differ by more than that: every chain tracks the
+// smallest relative margin of its own decisions and counts itself in `flagged` when it falls below margin_min -- the caller
+// then falls back to the sequential kernel, so a returned path is always the reference's.
+// ================================================================================================
+template <int EM>
+__global__ void __launch_bounds__(PW * 32) k_viterbi_chain32(const VitChainArgs a)
+{
+    __shared__ __align__(16) double ub[PW][32];
+    __shared__ __align__(16) double vb[PW][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gw = blockIdx.x * PW + wib, nw = gridDim.x * PW;
+    const int N = a.N, j = lane;
+    const bool jv = j < N;
+    double* u = ub[wib];
+    double* v = vb[wib];
+    double Acol[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) Acol[i] = (jv && i < N) ? a.A[i * N + j] : 0.0;
+    double mu = 0.0, sigma = 1.0;
+    if (EM == EM_GAUSS && jv) { mu = a.em.mu[j]; sigma = a.em.sigma[j]; }
+    const double pi_j = jv ? a.pi[j] : 0.0;
+    unsigned char* bp = reinterpret_cast<unsigned char*>(a.backptr);
+
+    auto em_raw = [&](long long row) -> double {
+        if (EM == EM_POBS) return a.em.pobs[row * N + j];
+        if (EM == EM_GAUSS) return a.em.obs[row];
+        return a.em.Bt[(long long)a.em.sym[row] * N + j];
+    };
+
+    for (int idx = gw; idx < a.ch.n; idx += nw) {
+        const int c = a.ch.list ? a.ch.list[idx] : idx;
+        const int len = a.ch.len[c], t0 = a.ch.t0[c], T = a.ch.T[c];
+        const long long trow = a.ch.row0[c] - t0;
+        const int tend = t0 + len;
+        int tstart = 0, mode = 0;                           // mode 0: pi at frame 0, 1: uniform warm-up start, 2: exact vector
+        if (t0 == 0) { tstart = 0; mode = 0; }
+        else if (a.ch.exact) { tstart = t0 - 1; mode = 2; }
+        else { tstart = max(0, t0 - (a.ch.warmv ? a.ch.warmv[c] : a.ch.warm)); mode = (tstart == 0) ? 0 : 1; }
+        u[lane] = 0.0;
+        v[lane] = 0.0;
+        __syncwarp();
+        if (mode == 2) {
+            if (jv) {
+                const double x = a.hand_end[(long long)(c - 1) * N + j];
+                v[j] = x;
+                a.hand_used[(long long)c * N + j] = x;
+            }
+            __syncwarp();
+        }
+        double minmargin = 1.0;
+        const int tfirst = (mode == 2) ? t0 : tstart;
+        double raw_next = jv ? em_raw(trow + tfirst) : 0.0;
+        for (int t = tfirst; t < tend; ++t) {
+            const double raw = raw_next;
+            if (jv && t + 1 < tend) raw_next = em_raw(trow + t + 1);
+            double p = 0.0;
+            if (jv) p = (EM == EM_GAUSS) ? gauss_pdf(raw, mu, sigma) : raw;
+            if (EM != EM_POBS && a.em.ignore_outliers) {
+                if (!__any_sync(FULL, p != 0.0)) p = jv ? 1.0 : 0.0;              // outputmodel.py:126-130
+            }
+            double vn;
+            if (t == tstart && mode != 2) {
+                vn = (mode == 0) ? __dmul_rn(p, pi_j) : p;
+            } else {
+                double m[4], m2[4], vbest[4], abest[4];
+                int bi[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    vbest[b] = v[8 * b];
+                    abest[b] = Acol[8 * b];
+                    m[b] = __dmul_rn(vbest[b], abest[b]);
+                    m2[b] = -1.0;
+                    bi[b] = 8 * b;
+                }
+#pragma unroll
+                for (int ii = 1; ii < 8; ++ii) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const double x = v[8 * b + ii];
+                        const double h = __dmul_rn(x, Acol[8 * b + ii]);
+                        if (h > m[b]) { m2[b] = m[b]; m[b] = h; bi[b] = 8 * b + ii; vbest[b] = x; abest[b] = Acol[8 * b + ii]; }
+                        else if (h > m2[b]) m2[b] = h;
+                    }
+                }
+                double mm = m[0], second = m2[0], vsel = vbest[0], asel = abest[0];
+                int best = bi[0];
+#pragma unroll
+                for (int b = 1; b < 4; ++b) {
+                    if (m[b] > mm) { second = fmax(second, mm); second = fmax(second, m2[b]); mm = m[b]; best = bi[b]; vsel = vbest[b]; asel = abest[b]; }
+                    else second = fmax(second, m[b]);
+                }
+                if (jv && t >= t0) {
+                    bp[(trow + t - 1) * N + j] = (unsigned char)best;
+                    if (mm > 0.0) minmargin = fmin(minmargin, (mm - fmax(second, 0.0)) / mm);
+                }
+                vn = __dmul_rn(__dmul_rn(p, vsel), asel);
+            }
+            if (jv) u[j] = vn;
+            __syncwarp();
+            double ssum = 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ssum = __dadd_rn(ssum, u[i]);
+            const double vnew = __ddiv_rn(vn, ssum);
+            __syncwarp();                                   // everybody has read u and v of this frame
+            if (jv) {
+                v[j] = vnew;
+                if (t == t0 - 1) a.hand_used[(long long)c * N + j] = vnew;
+                if (t == tend - 1) a.hand_end[(long long)c * N + j] = vnew;
+            }
+            __syncwarp();
+        }
+        if (tend == T) {                                    // path[T-1] = first maximum of the last row (_hidden.c:268)
+            int best = 0;
+            double m = v[0], second = -1.0;
+            for (int i = 1; i < N; ++i) {
+                if (v[i] > m) { second = m; m = v[i]; best = i; }
+                else if (v[i] > second) second = v[i];
+            }
+            if (jv) bp[(trow + T - 1) * N + j] = (unsigned char)best;
+            if (m > 0.0 && N > 1) minmargin = fmin(minmargin, (m - fmax(second, 0.0)) / m);
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) minmargin = fmin(minmargin, __shfl_xor_sync(FULL, minmargin, off));
+        if (lane == 0 && minmargin < a.margin_min) atomicAdd(a.flagged, 1);
+        __syncwarp();
+    }
+}
+
 #ifndef PANEL_HOST_EMU
 int panel_sms()
 {
@@ -1267,6 +1403,21 @@ int launch_viterbi_panel(const VitArgs& a, int em, cudaStream_t st)
         case EM_POBS: return launch_viterbi_regs_em<EM_POBS>(a, st);
         case EM_GAUSS: return launch_viterbi_regs_em<EM_GAUSS>(a, st);
         case EM_DISC: return launch_viterbi_regs_em<EM_DISC>(a, st);
+    }
+    return BHMM_ERR_INVALID;
+}
+
+bool panel_viterbi_chain_ok(int N) { return panel_mode() > 0 && N >= 1 && N <= 32; }
+
+int launch_viterbi_chain(const VitChainArgs& a, int em, cudaStream_t st)
+{
+    if (a.N < 1 || a.N > 32) return BHMM_ERR_UNSUPPORTED;
+    if (a.ch.n <= 0) return BHMM_OK;
+    const int grid = (int)std::max(1LL, std::min<long long>(((long long)a.ch.n + PW - 1) / PW, (long long)panel_sms() * 4));
+    switch (em) {
+        case EM_POBS: k_viterbi_chain32<EM_POBS><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
+        case EM_GAUSS: k_viterbi_chain32<EM_GAUSS><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
+        case EM_DISC: k_viterbi_chain32<EM_DISC><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
     }
     return BHMM_ERR_INVALID;
 }

@@ -194,6 +194,7 @@ inline void emu_dmma(double& d0, double& d1, double a, double b)
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 inline double atomicAdd(double* p, double v) { const double o = *p; *p = o + v; return o; }
 inline int __double2hiint(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(b >> 32); }
 inline int __double2loint(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(b & 0xffffffff); }

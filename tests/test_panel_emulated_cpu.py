@@ -417,3 +417,79 @@ def test_viterbi_regs_is_bit_exact(emu, oracle_port, N):
                                F.ctypes.data_as(C.POINTER(C.c_ubyte)))
     assert rc == 0
     assert np.array_equal(_resolve(F, T), oracle_port.viterbi(A, pobs, pi))
+
+
+# ------------------------------------------------------------------------------------------------ time-chunked Viterbi, N <= 32
+def _viterbi_chain(emu, N, em_kind, plan, A, pi, grid, warm, exact=0, chain_list=None, pobs=None, sym=None, Bt=None, M=0,
+                   F=None, hu=None, he=None, margin_min=1e-9, ignore_outliers=0):
+    row0, ln, t0, TT = plan
+    lst = None if chain_list is None else np.array(chain_list, dtype=np.int32)
+    flagged = np.zeros(1, dtype=np.int32)
+    rc = emu.panel_emu_viterbi_chain(C.c_int(N), C.c_int(em_kind), C.c_int(grid), ptr(row0, C.c_longlong), ptr(ln, C.c_int),
+                                     ptr(t0, C.c_int), ptr(TT, C.c_int), ptr(lst, C.c_int),
+                                     C.c_int(len(row0) if lst is None else len(lst)), C.c_int(warm), None, C.c_int(exact),
+                                     ptr(pobs), None, ptr(sym, C.c_int), None, None, ptr(Bt), C.c_int(M),
+                                     C.c_int(ignore_outliers), ptr(A), ptr(pi), F.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                     ptr(hu), ptr(he), flagged.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(margin_min))
+    assert rc == 0
+    return int(flagged[0])
+
+
+@pytest.mark.parametrize('N', [32, 10, 3])
+def test_time_chunked_viterbi_matches_sequential(emu, oracle_port, N):
+    """k_viterbi_chain32: two trajectories cut into 15 chains that run in parallel after a warm-up reproduce the oracle's
+    sequential Viterbi paths bit for bit, the hand-overs agree to rounding, and no decision is flagged as a near-tie."""
+    rng = np.random.default_rng(50 + N)
+    X = rng.random((N, N)) + 2.0 * np.eye(N)
+    A = np.ascontiguousarray(X / X.sum(axis=1)[:, None])
+    pi = rng.random(N)
+    pi /= pi.sum()
+    Ts = [400, 173]
+    pobs = [np.ascontiguousarray(rng.random((T, N)) ** 3 + 1e-6) for T in Ts]
+    cat = np.ascontiguousarray(np.vstack(pobs))
+    plan = make_plan(Ts, 40)
+    n = len(plan[0])
+    assert n == 15
+    F = np.full((cat.shape[0], N), 255, dtype=np.uint8)
+    hu, he = np.zeros((n, N)), np.zeros((n, N))
+    flagged = _viterbi_chain(emu, N, EM_POBS, plan, A, pi, grid=2, warm=80, pobs=cat, F=F, hu=hu, he=he)
+    assert flagged == 0
+    row = 0
+    for T, p in zip(Ts, pobs):
+        assert np.array_equal(_resolve(F[row:row + T], T), oracle_port.viterbi(A, p, pi))
+        row += T
+    t0 = plan[2]
+    for c in range(n):
+        if t0[c] > 0:
+            np.testing.assert_allclose(hu[c], he[c - 1], rtol=1e-11, atol=1e-300)
+
+
+def test_time_chunked_viterbi_fix_up_and_tie_flag(emu, oracle_port):
+    """(1) A warm-up that is too short on a slowly mixing model leaves wrong hand-overs; exact passes over the failing chains,
+    in order, repair the map.  (2) A model with structural ties is flagged (the caller then runs the sequential kernel)."""
+    N = 8
+    rng = np.random.default_rng(4)
+    X = rng.random((N, N)) + 60.0 * np.eye(N)
+    A = np.ascontiguousarray(X / X.sum(axis=1)[:, None])
+    pi = np.ones(N) / N
+    T = 240
+    pobs = np.ascontiguousarray(0.3 + 0.7 * rng.random((T, N)))         # weakly informative: the start matters for long
+    plan = make_plan([T], 30)
+    n = len(plan[0])
+    F = np.zeros((T, N), dtype=np.uint8)
+    hu, he = np.zeros((n, N)), np.zeros((n, N))
+    _viterbi_chain(emu, N, EM_POBS, plan, A, pi, grid=1, warm=1, pobs=pobs, F=F, hu=hu, he=he)
+    bad = [c for c in range(1, n) if np.max(np.abs(hu[c] - he[c - 1]) / np.maximum(hu[c], he[c - 1])) > 1e-11]
+    assert bad, 'the one-frame warm-up should have failed somewhere'
+    while bad:                                              # certification loop: earliest failing chain first
+        c = bad[0]
+        _viterbi_chain(emu, N, EM_POBS, plan, A, pi, grid=1, warm=1, exact=1, chain_list=[c], pobs=pobs, F=F, hu=hu, he=he)
+        bad = [k for k in range(1, n) if np.max(np.abs(hu[k] - he[k - 1]) / np.maximum(hu[k], he[k - 1])) > 1e-11]
+    assert np.array_equal(_resolve(F, T), oracle_port.viterbi(A, pobs, pi))
+    # (2) structural ties
+    A1 = np.full((N, N), 1.0 / N)
+    p1 = np.ascontiguousarray(np.tile(np.array([[0.5, 0.25] * (N // 2)]), (60, 1)))
+    plan1 = make_plan([60], 20)
+    F1 = np.zeros((60, N), dtype=np.uint8)
+    h1, h2 = np.zeros((3, N)), np.zeros((3, N))
+    assert _viterbi_chain(emu, N, EM_POBS, plan1, A1, pi, grid=1, warm=10, pobs=p1, F=F1, hu=h1, he=h2) > 0

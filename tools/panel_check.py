@@ -125,6 +125,17 @@ def parity_wide():
     b.close()
 
 
+def timing_viterbi_c5():
+    """C5 shape, reduced: ONE trajectory of 2e7 frames, 32 states (the sequential kernel walks it at ~0.5 us per frame)."""
+    N, T = 32, 20000000
+    pi, A, means, sigmas, O, S = ts.gaussian_observations(N, 1, T, seed=5)
+    b = TrajectoryBatch([O[0]], N)
+    ms = timeit(lambda: b.viterbi_gaussian(A, pi, means, sigmas), reps=1)
+    print('%s N=32 one trajectory of %d frames: Viterbi %.1f ms -> %.4f G frames/s; info %s'
+          % ('team ' if CHILD else 'panel', T, ms, T / ms / 1e6, b.info()), flush=True)
+    b.close()
+
+
 def timing():
     N, K, T = 32, 64, 100000
     pi, A, means, sigmas, O, S = ts.gaussian_observations(N, K, T, seed=5)
@@ -203,6 +214,16 @@ def parity():
     lp_ref, alpha_ref = orc.forward(A, pobs, pi)
     check('hidden.forward N=32: logprob', abs(lp - lp_ref) <= RTOL * abs(lp_ref))
     check('hidden.forward N=32: alpha', float(np.max(np.abs(alpha - alpha_ref))) <= 1e-10)
+    # ---- time-chunked Viterbi: one long trajectory cut into chains, against the sequential oracle
+    s = rng.integers(0, N, size=60000)
+    long_obs = [means[s] + sigmas[s] * rng.standard_normal(60000)]
+    for chunk in (0, 1500):
+        b = TrajectoryBatch(long_obs, N, chunk=chunk, warm=0)
+        got = b.viterbi_gaussian(A, pi, means, sigmas).cpu().numpy()
+        want = orc.viterbi(A, orc.gaussian_p_obs(long_obs[0], means, sigmas), pi)
+        check('chunked viterbi N=32, 60000 frames, chunk=%d: path' % chunk, np.array_equal(got, want),
+              '%d mismatches; info %s' % (int(np.sum(got != want)), b.info()))
+        b.close()
     b = TrajectoryBatch(obs, N, chunk=214, warm=0)
     path, counts, sums, ll = b.gibbs_gaussian(A, pi, means, sigmas, seed=7, sweep=0)
     check('gibbs sweep N=32: loglik of the filter', abs(ll - ref['loglik']) <= RTOL * abs(ref['loglik']))
@@ -214,6 +235,8 @@ if __name__ == '__main__':
     if CHILD:
         timing()
         timing_wide()
+        if '--with-sequential-c5' in sys.argv:
+            timing_viterbi_c5()                             # ~10 s of a single warp: only on request
         sys.exit(0)
     t0 = time.time()
     parity()
@@ -222,5 +245,6 @@ if __name__ == '__main__':
     if '--quick' not in sys.argv and not failures:
         timing()
         timing_wide()
+        timing_viterbi_c5()
         subprocess.run([sys.executable, os.path.abspath(__file__), '--team-child'], timeout=600)
     sys.exit(1 if failures else 0)
