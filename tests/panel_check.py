@@ -1,8 +1,8 @@
 """Parity and timing of the opt-in panel kernels (bhmm_b200/csrc/panel_kernels.cu: N = 32 and 32 < N <= 104) on a B200.
 
-    timeout 900 python tools/panel_check.py            # parity against the oracle, then timing next to the team kernels
-    timeout 600 python tools/panel_check.py --quick    # parity only (what tests/test_panel_cuda.py runs)
-    timeout 900 python tools/panel_check.py --mode=2   # N = 32 on the 4-warp wide kernels (BHMM_B200_PANEL=2)
+    timeout 900 python tests/panel_check.py            # parity against the oracle, then timing next to the team kernels
+    timeout 600 python tests/panel_check.py --quick    # parity only (what tests/test_panel_cuda.py runs)
+    timeout 900 python tests/panel_check.py --mode=2   # N = 32 on the 4-warp wide kernels (BHMM_B200_PANEL=2)
 
 The panel family is selected by BHMM_B200_PANEL=1, which the library reads once per process; this script sets it for
 itself and times the team kernels in a child process without it.  Every GPU call sits under the caller's `timeout`: the

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.skipif(os.environ.get('BHMM_B200_PANEL_TEST') != '1', reason='panel kernels are opt-in until verified on a B200')
 def test_panel_kernels_match_oracle():
-    r = subprocess.run(['timeout', '600', sys.executable, os.path.join(ROOT, 'tools', 'panel_check.py'), '--quick'],
+    r = subprocess.run(['timeout', '600', sys.executable, os.path.join(ROOT, 'tests', 'panel_check.py'), '--quick'],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-4000:]
