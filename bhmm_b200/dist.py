@@ -52,3 +52,17 @@ def allreduce_sum(tensor):
     if initialized() and world_size() > 1:
         _td().all_reduce(tensor, op=_td().ReduceOp.SUM)
     return tensor
+
+
+def broadcast_int(value, src=0):
+    """The integer `value` of rank `src` on every rank (identity without torch.distributed).  Used to agree on the seed of
+    the host-side parameter draws of the Gibbs sampler: every rank must draw the SAME model from the all-reduced
+    statistics, or the shards silently sample different chains."""
+    if not (initialized() and world_size() > 1):
+        return int(value)
+    import torch
+    td = _td()
+    dev = 'cuda' if td.get_backend() == 'nccl' else 'cpu'
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    td.broadcast(t, src=src)
+    return int(t.item())

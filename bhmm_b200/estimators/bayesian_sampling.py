@@ -34,7 +34,13 @@ class BayesianHMMSampler(object):
         if initial_model is None:
             raise NotImplementedError('bhmm_b200 needs initial_model= (bhmm.init_hmm is outside the hot path)')
         self.reversible = reversible
-        self._np_rng = np.random.default_rng(np.random.randint(0, 2 ** 31 - 1))
+        # Host-side parameter draws.  One process: numpy's global RNG, as in the reference (np.random.seed reproduces a
+        # run).  Sharded over several ranks: every rank must draw the SAME parameters from the all-reduced statistics, so
+        # the ranks agree on one seed (rank 0's next global draw) and use a private stream from it.
+        self._rng = np.random
+        if shard and dist.world_size() > 1:
+            self._rng = np.random.RandomState(dist.broadcast_int(np.random.randint(0, 2 ** 31 - 1)))
+        self._np_rng = np.random.default_rng(self._rng.randint(0, 2 ** 31 - 1))
         self.stationary = stationary
         self.nstates = nstates
         if shard and dist.world_size() > 1:
@@ -137,9 +143,9 @@ class BayesianHMMSampler(object):
         """Sample emission parameters from P(E | S, O) (:333-339)."""
         om = self.model.output_model
         if self._output == 'gaussian':
-            om.sample_from_statistics(st['count'], st['so'], st['soo'])
+            om.sample_from_statistics(st['count'], st['so'], st['soo'], rng=self._rng)
         else:
-            om.sample_from_histogram(st['hist'])
+            om.sample_from_histogram(st['hist'], rng=self._rng)
 
     def _updateTransitionMatrix(self, st):
         """Sample the transition matrix and the initial distribution (:341-373)."""
@@ -157,7 +163,7 @@ class BayesianHMMSampler(object):
                 if not np.any(positive):
                     Tij[i, i] = 1.0
                 else:
-                    Tij[i, positive] = np.random.dirichlet(Cm[i, positive])
+                    Tij[i, positive] = self._rng.dirichlet(Cm[i, positive])
         if self.stationary:
             p0 = _tmatrix.stationary_distribution(Tij, C=Cm)
         else:
@@ -165,5 +171,5 @@ class BayesianHMMSampler(object):
             first_timestep_counts_with_prior = n0 + self.prior_n0
             positive = first_timestep_counts_with_prior > 0
             p0 = np.zeros_like(n0)
-            p0[positive] = np.random.dirichlet(first_timestep_counts_with_prior[positive])
+            p0[positive] = self._rng.dirichlet(first_timestep_counts_with_prior[positive])
         self.model.update(p0, Tij)

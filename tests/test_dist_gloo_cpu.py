@@ -73,3 +73,49 @@ def test_sharded_estep_allreduce_world2():
     assert abs(r0['loglik'] - ref['loglik']) <= 1e-12 * abs(ref['loglik'])
     np.testing.assert_allclose(r0['C'], ref['C'], rtol=1e-12)
     np.testing.assert_allclose(r0['wsum'], ref['wsum'], rtol=1e-12)
+
+
+def _worker_param_draws(rank, world, port, out):
+    """Ranks whose global numpy RNGs are in DIFFERENT states must still draw identical Gibbs parameters."""
+    import torch.distributed as td
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    td.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from bhmm_b200 import dist
+        from bhmm_b200.estimators.bayesian_sampling import BayesianHMMSampler
+        from bhmm_b200.hmm.generic_hmm import HMM
+        from bhmm_b200.output_models.gaussian import GaussianOutputModel
+        np.random.seed(1000 + 17 * rank)                    # deliberately different per rank
+        seed = dist.broadcast_int(np.random.randint(0, 2 ** 31 - 1))
+        A = np.array([[0.9, 0.1], [0.2, 0.8]])
+        pi = np.array([2.0 / 3, 1.0 / 3])
+        st = {'C': np.array([[900, 100], [110, 390]], dtype=np.int64), 'n0': np.array([2, 1], dtype=np.int64),
+              'count': np.array([1000.0, 500.0]), 'so': np.array([-1000.0, 750.0]), 'soo': np.array([2000.0, 1700.0])}
+        draws = []
+        for reversible in (False, True):
+            s = BayesianHMMSampler.__new__(BayesianHMMSampler)
+            s.reversible, s.stationary, s.nstates, s._output = reversible, False, 2, 'gaussian'
+            s._rng = np.random.RandomState(seed)            # what __init__ sets up when the batch is sharded
+            s._np_rng = np.random.default_rng(s._rng.randint(0, 2 ** 31 - 1))
+            s.prior_C, s.prior_n0, s.transition_matrix_sampling_steps = A.copy(), pi.copy(), 1000
+            s.model = HMM(pi, A, GaussianOutputModel(2, means=[-1.0, 1.5], sigmas=[1.0, 1.0]))
+            s._updateEmissionProbabilities(st)
+            s._updateTransitionMatrix(st)
+            draws.append(np.concatenate([s.model.transition_matrix.ravel(), s.model.initial_distribution,
+                                         s.model.output_model.means, s.model.output_model.sigmas]))
+        out[rank] = dict(seed=seed, draws=np.concatenate(draws))
+    finally:
+        td.destroy_process_group()
+
+
+def test_gibbs_parameter_draws_agree_across_ranks_world2():
+    import torch.multiprocessing as mp
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_param_draws, args=(world, port, out), nprocs=world, join=True)
+    assert out[0]['seed'] == out[1]['seed']
+    assert np.array_equal(out[0]['draws'], out[1]['draws'])
+    assert np.all(np.isfinite(out[0]['draws']))

@@ -215,6 +215,7 @@ def test_gibbs_transition_matrix_update_reversible_and_not():
         s = BayesianHMMSampler.__new__(BayesianHMMSampler)
         s.reversible, s.stationary, s.nstates = reversible, False, 3
         s._np_rng = np.random.default_rng(11)
+        s._rng = np.random
         s.prior_C, s.prior_n0 = A.copy(), pi.copy()
         s.transition_matrix_sampling_steps = 1000
         s.model = HMM(pi, A, GaussianOutputModel(3, means=[-1.0, 0.0, 1.0], sigmas=[1.0, 1.0, 1.0]))
