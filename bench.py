@@ -38,6 +38,7 @@ WORKLOADS = {
     'c2': (3, 100, 10000, 'C2-shape: 3-state Gaussian HMM, 100 trajectories x 1e4 frames, Baum-Welch EM'),
     'small': (10, 64, 20000, 'reduced C3 shape for quick checks: 10 states, 64 x 2e4 frames'),
     'n3': (3, 4096, 100000, 'memory-bound regime: 3-state Gaussian HMM (C1/C2 model), 4096 trajectories x 1e5 frames per GPU, Baum-Welch EM'),
+    'n32': (32, 256, 100000, 'C5 model family, batched: 32-state Gaussian HMM, 256 trajectories x 1e5 frames per GPU, Baum-Welch EM (FP64-pipe bound; set BHMM_B200_PANEL=1|2 for the tensor-pipe kernels)'),
 }
 
 
@@ -372,7 +373,7 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
         ab = algorithmic_bytes_per_frame(N)
-        family = 'lane<N=%d,EM_GAUSS>' % N if lane_family else 'team<EM_GAUSS>'
+        family = 'lane<N=%d,EM_GAUSS>' % N if lane_family else ('panel<EM_GAUSS>' if (os.environ.get('BHMM_B200_PANEL') in ('1', '2') and 17 <= N <= 104) else 'team<EM_GAUSS>')
         dom = 'backward_stats' if kms['backward_stats'] >= kms['forward'] else 'forward'
         dom_ms = kms[dom] / args.steps
         # the dominant kernel also walks the warm-up frames; only the chain's own frames count as algorithmic bytes
