@@ -128,8 +128,8 @@ def parity_wide():
 def timing_viterbi_c5():
     """C5 shape, reduced: ONE trajectory of 2e7 frames, 32 states (the sequential kernel walks it at ~0.5 us per frame)."""
     N, T = 32, 20000000
-    pi, A, means, sigmas, O, S = ts.gaussian_observations(N, 1, T, seed=5)
-    b = TrajectoryBatch([O[0]], N)
+    pi, A, means, sigmas, O, S = ts.gaussian_observations(N, 1, T // 10, seed=5)     # the host generator walks frame by frame
+    b = TrajectoryBatch([np.tile(O[0], 10)], N)
     ms = timeit(lambda: b.viterbi_gaussian(A, pi, means, sigmas), reps=1)
     print('%s N=32 one trajectory of %d frames: Viterbi %.1f ms -> %.4f G frames/s; info %s'
           % ('team ' if CHILD else 'panel', T, ms, T / ms / 1e6, b.info()), flush=True)
