@@ -634,7 +634,7 @@ __device__ __forceinline__ void wide_table2(const Emission& em, long long row, i
 template <int EM, int NT>
 __global__ void WIDE_KERNEL_ATTR(NT) k_forward_wide(const FwdArgs a)
 {
-    constexpr int NP = WideGeom<NT>::NP, KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS;
+    constexpr int KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS;
     __shared__ __align__(16) double Sx[2][PCH * NPS];     // the frame's vector with the densities ...
     __shared__ __align__(16) double Sd[2][PCH * NPS];     // ... and with all densities set to one (outlier rule)
     __shared__ double red[2][3][NT][PCH];                 // per tile and chain: sum of Sx, sum of Sd, any density != 0
@@ -806,7 +806,7 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_forward_wide(const FwdArgs a)
 template <int EM, int NT>
 __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide(const BwdArgs a)
 {
-    constexpr int NP = WideGeom<NT>::NP, KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS;
+    constexpr int KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS;
     __shared__ __align__(16) double Sw[2][PCH * NPS];
     __shared__ __align__(16) double Sb[2][PCH * NPS];
     __shared__ __align__(16) double Su[PCH * NPS];
