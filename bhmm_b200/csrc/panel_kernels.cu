@@ -1268,7 +1268,7 @@ __global__ void __launch_bounds__(PW * 32) k_viterbi_chain32(const VitChainArgs 
     }
 }
 
-#ifndef PANEL_HOST_EMU
+#ifndef PANEL_HOST_NO_LAUNCHERS
 int panel_sms()
 {
     static int n = 0;
@@ -1347,11 +1347,11 @@ int launch_backward_wide_em(const BwdArgs& a, int NT, cudaStream_t st)
                   (k_backward_stats_wide<EM, 13><<<a.grid, 13 * 32, 0, st>>>(a)));
     return BHMM_OK;
 }
-#endif   // PANEL_HOST_EMU
+#endif   // PANEL_HOST_NO_LAUNCHERS
 
 }  // namespace
 
-#ifndef PANEL_HOST_EMU
+#ifndef PANEL_HOST_NO_LAUNCHERS
 // BHMM_B200_PANEL: unset / 0 = off; 1 = N = 32 on the one-warp-per-8-chains kernels, 17 <= N <= 104 otherwise on the wide
 // kernels; 2 = N = 32 on the wide kernels too (4 warps per 8 chains: a third of the registers, more resident warps)
 static int panel_mode()
@@ -1485,4 +1485,4 @@ int launch_backward_stats_panel(const BwdArgs& a, int em, cudaStream_t st)
     }
     return BHMM_ERR_INVALID;
 }
-#endif   // PANEL_HOST_EMU
+#endif   // PANEL_HOST_NO_LAUNCHERS

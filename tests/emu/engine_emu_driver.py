@@ -1,0 +1,130 @@
+"""Drives the CPU build of the library (tests/emu/engine_emu.so: host logic + hostified kernels on the warp emulator and a
+fake CUDA runtime) through the C ABI with numpy buffers as "device" memory, and compares an E-step, a discrete E-step
+and Viterbi paths with the CPU oracle.  Run by tests/test_engine_emulated_cpu.py in a fresh process per BHMM_B200_PANEL
+mode (the library reads the variable once).  Prints one line per check, exits non-zero on a failure."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle.oracle import Oracle   # noqa: E402
+
+lib = C.CDLL(os.path.join(HERE, 'engine_emu.so'))
+lib.bhmm_b200_last_error_string.restype = C.c_char_p
+dp = C.POINTER(C.c_double)
+failures = []
+
+
+def d(a):
+    return a.ctypes.data_as(dp)
+
+
+def check(name, ok, detail=''):
+    print('%-64s %s %s' % (name, 'ok' if ok else 'FAIL', detail), flush=True)
+    if not ok:
+        failures.append(name)
+
+
+def rc_ok(rc):
+    assert rc == 0, (rc, lib.bhmm_b200_last_error_string())
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-300)))
+
+
+class Batch(object):
+    def __init__(self, lengths, N, chunk, warm):
+        self.N = N
+        self.offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+        self.rows = int(self.offsets[-1])
+        self.h = C.c_void_p()
+        rc_ok(lib.bhmm_b200_batch_create(C.byref(self.h), self.offsets.ctypes.data_as(C.POINTER(C.c_longlong)), len(lengths),
+                                         N, chunk, warm))
+
+    def info(self):
+        v = np.zeros(8)
+        lib.bhmm_b200_batch_info(self.h, d(v))
+        return dict(chains=int(v[0]), chunk=int(v[1]), warm=int(v[2]), fix_f=v[3], fix_b=v[4], worst_f=v[5], worst_b=v[6])
+
+    def close(self):
+        lib.bhmm_b200_batch_destroy(self.h)
+
+
+def unpack(st, N):
+    o = 1
+    out = {'loglik': st[0]}
+    for key, n in (('gamma0', N), ('C', N * N), ('wsum', N), ('wd', N), ('wdd', N)):
+        out[key] = st[o:o + n]
+        o += n
+    out['C'] = out['C'].reshape(N, N)
+    return out
+
+
+def run(N, chunk, warm):
+    orc = Oracle('port')
+    rng = np.random.default_rng(N)
+    X = rng.random((N, N)) + 2.0 * np.eye(N)
+    A = np.ascontiguousarray(X / X.sum(axis=1)[:, None])
+    pi = rng.random(N)
+    pi /= pi.sum()
+    means, sigmas = np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
+    lengths = [150, 61, 1, 97]
+    obs = []
+    for T in lengths:
+        s = rng.integers(0, N, T)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    cat = np.ascontiguousarray(np.concatenate(obs))
+    ref = orc.estep_gaussian(obs, A, pi, means, sigmas)
+    wdd = sum((g * (o[:, None] - means) ** 2).sum(axis=0) for g, o in zip(ref['gammas'], obs))
+    tag = 'N=%d chunk=%d: ' % (N, chunk)
+    b = Batch(lengths, N, chunk, warm)
+    stats = np.zeros(lib.bhmm_b200_stats_len_gaussian(N))
+    gamma = np.zeros((b.rows, N))
+    rc_ok(lib.bhmm_b200_estep_gaussian(b.h, d(cat), d(A), d(pi), d(means), d(sigmas), 1, d(gamma), d(stats), None))
+    st = unpack(stats, N)
+    check(tag + 'E-step loglik', abs(st['loglik'] - ref['loglik']) <= 1e-10 * abs(ref['loglik']), '%.10e' % st['loglik'])
+    check(tag + 'E-step C', rel(st['C'], ref['C']) <= 1e-9, 'worst rel %.1e' % rel(st['C'], ref['C']))
+    check(tag + 'E-step gamma0', rel(st['gamma0'], ref['gamma0']) <= 1e-10)
+    check(tag + 'E-step sum gamma', rel(st['wsum'], ref['wsum']) <= 1e-10)
+    check(tag + 'E-step sum gamma d^2', rel(st['wdd'], wdd) <= 1e-9)
+    check(tag + 'E-step gamma rows', np.max(np.abs(gamma - np.vstack(ref['gammas']))) <= 1e-10)
+    info = b.info()
+    check(tag + 'plan cut the trajectories into chains', info['chains'] > len(lengths) if chunk else True, str(info))
+    path = np.zeros(b.rows, dtype=np.int32)
+    rc_ok(lib.bhmm_b200_viterbi_gaussian(b.h, d(cat), d(A), d(pi), d(means), d(sigmas), 1, path.ctypes.data_as(C.POINTER(C.c_int)), None))
+    ok = True
+    for k, o in enumerate(obs):
+        want = orc.viterbi(A, orc.gaussian_p_obs(o, means, sigmas), pi)
+        ok = ok and np.array_equal(path[b.offsets[k]:b.offsets[k + 1]], want)
+    check(tag + 'Viterbi paths', ok)
+    b.close()
+    # discrete
+    M = 11
+    B = rng.random((N, M)) ** 2 + 1e-3
+    B /= B.sum(axis=1)[:, None]
+    sym = [rng.integers(0, M, T).astype(np.int32) for T in lengths]
+    scat = np.ascontiguousarray(np.concatenate(sym))
+    rd = orc.estep_discrete(sym, A, pi, B)
+    b = Batch(lengths, N, chunk, warm)
+    dstats = np.zeros(lib.bhmm_b200_stats_len_discrete(N))
+    Bnum = np.zeros((N, M))
+    rc_ok(lib.bhmm_b200_estep_discrete(b.h, scat.ctypes.data_as(C.POINTER(C.c_int)), d(A), d(pi), d(np.ascontiguousarray(B)), M, 0,
+                                       None, d(dstats), d(Bnum), None))
+    check(tag + 'discrete loglik', abs(dstats[0] - rd['loglik']) <= 1e-10 * abs(rd['loglik']))
+    check(tag + 'discrete C', rel(dstats[1 + N:1 + N + N * N].reshape(N, N), rd['C']) <= 1e-9)
+    check(tag + 'discrete B numerator', np.max(np.abs(Bnum - rd['Bnum'])) <= 1e-9 * np.abs(rd['Bnum']).max())
+    b.close()
+
+
+if __name__ == '__main__':
+    print('BHMM_B200_PANEL =', os.environ.get('BHMM_B200_PANEL'), flush=True)
+    for spec in sys.argv[1:]:
+        N, chunk, warm = (int(x) for x in spec.split(','))
+        run(N, chunk, warm)
+    sys.exit(1 if failures else 0)

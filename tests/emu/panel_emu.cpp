@@ -1,7 +1,8 @@
 // tests/emu/panel_emu.cpp -- the panel kernels' SOURCE (bhmm_b200/csrc/panel_kernels.cu) compiled for the CPU on top of
 // warp_emu.h, exported with a flat C interface for tests/test_panel_emulated_cpu.py.  Test infrastructure only.
 //   g++ -O1 -std=c++17 -shared -fPIC -I/usr/local/cuda/include -o panel_emu.so panel_emu.cpp
-#define PANEL_HOST_EMU 1
+#define PANEL_HOST_EMU 1            // asm (DMMA, prefetch) -> emulator hooks
+#define PANEL_HOST_NO_LAUNCHERS 1   // no <<<>>> launchers, no CUDA runtime: the kernels are called directly below
 #include "warp_emu.h"
 
 #include "../../bhmm_b200/csrc/panel_kernels.cu"

@@ -1,0 +1,63 @@
+"""The WHOLE library on the CPU: its host logic (capi.cu, engine.cu: chain planning, workspace layout, certification loops,
+statistics reduction, Viterbi path resolution, the C ABI) and its general-N kernels are hostified (tests/emu/hostify.py)
+and run on the warp emulator with a fake CUDA runtime (tests/emu/cuda_fake.cpp), driven through the C ABI with numpy
+buffers as device memory and compared with the oracle (tests/emu/engine_emu_driver.py).
+
+Mode 0 (the default kernels, which ARE validated on the B200) calibrates the emulation itself.  Modes 1 and 2 select the
+opt-in panel family (BHMM_B200_PANEL), which had no GPU time in the round it was written: this is the check of its
+integration into the engine -- plan capacities, rows of partial statistics, hand-over certification, the time-chunked
+Viterbi with its fallback -- that the kernel-level emulation (test_panel_emulated_cpu.py) cannot give."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, 'emu')
+CSRC = os.path.join(HERE, '..', 'bhmm_b200', 'csrc')
+
+
+@pytest.fixture(scope='module')
+def engine_emu():
+    so = os.path.join(EMU, 'engine_emu.so')
+    deps = [os.path.join(EMU, f) for f in ('hostify.py', 'cuda_fake.h', 'cuda_fake.cpp', 'warp_emu.h', 'lane_stubs.cpp',
+                                           'build_engine_emu.sh')]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.h', '.cuh'))]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        if not os.path.exists(os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include', 'cuda_runtime.h')):
+            pytest.skip('CUDA headers not found')
+        subprocess.run(['bash', os.path.join(EMU, 'build_engine_emu.sh')], check=True, stdout=subprocess.DEVNULL)
+    return so
+
+
+def _drive(mode, specs, trace=False):
+    env = dict(os.environ, BHMM_B200_PANEL=str(mode))
+    if trace:
+        env['EMU_TRACE'] = '1'
+    r = subprocess.run([sys.executable, os.path.join(EMU, 'engine_emu_driver.py')] + specs, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert ' ok ' in r.stdout and 'FAIL' not in r.stdout
+    return r
+
+
+def test_default_kernels_on_the_emulator(engine_emu):
+    """Calibration: the GPU-validated team kernels, certification and path chase reproduce the oracle on the emulator."""
+    r = _drive(0, ['5,40,40', '32,40,40'], trace=True)
+    assert 'block 32 ' in r.stderr                      # the one-warp team kernels ran
+
+
+def test_panel_family_through_the_engine(engine_emu):
+    """BHMM_B200_PANEL=1: N = 32 on the one-warp panel kernels, N = 21 / 40 on the wide kernels, chunked Viterbi."""
+    r = _drive(1, ['32,40,40', '21,40,40', '40,0,0'], trace=True)
+    assert 'block 32 ' not in r.stderr                  # no team chain kernel was launched
+    assert 'block 256 ' in r.stderr                     # wide kernels, 8 warps (N = 40)
+
+
+def test_wide_kernels_at_n32_and_n100_through_the_engine(engine_emu):
+    """BHMM_B200_PANEL=2 (N = 32 on the 4-warp wide kernels) and the C4 state count: 13-warp wide kernels + Viterbi with the
+    matrix column in registers."""
+    _drive(2, ['32,40,40'])
+    r = _drive(1, ['100,40,40'], trace=True)
+    assert 'block 416 ' in r.stderr
