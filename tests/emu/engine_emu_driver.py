@@ -103,6 +103,25 @@ def run(N, chunk, warm):
         want = orc.viterbi(A, orc.gaussian_p_obs(o, means, sigmas), pi)
         ok = ok and np.array_equal(path[b.offsets[k]:b.offsets[k + 1]], want)
     check(tag + 'Viterbi paths', ok)
+    # Gibbs hidden-path sweep with given uniforms: forward filter (the family's forward kernel) + backward sampling
+    u_traj = [rng.random(T) for T in lengths]                     # draw order of _sample_path: first draw for t = T-1
+    u_rows = np.ascontiguousarray(np.concatenate([u[::-1] for u in u_traj]))
+    gpath = np.zeros(b.rows, dtype=np.int32)
+    counts = np.zeros(N * N + 2 * N, dtype=np.int64)
+    sums = np.zeros(2 * N)
+    ll = C.c_double(0.0)
+    rc_ok(lib.bhmm_b200_gibbs_gaussian(b.h, d(cat), d(A), d(pi), d(means), d(sigmas), 1, d(u_rows), C.c_ulonglong(0),
+                                       C.c_ulonglong(0), gpath.ctypes.data_as(C.POINTER(C.c_int)),
+                                       counts.ctypes.data_as(C.POINTER(C.c_longlong)), d(sums), C.byref(ll), None))
+    ok, Cint = True, np.zeros((N, N), dtype=np.int64)
+    for k, o in enumerate(obs):
+        alpha = orc.forward(A, orc.gaussian_p_obs(o, means, sigmas), pi)[1]
+        want = orc.sample_path(alpha, A, u=u_traj[k])
+        ok = ok and np.array_equal(gpath[b.offsets[k]:b.offsets[k + 1]], want)
+        np.add.at(Cint, (want[:-1], want[1:]), 1)
+    check(tag + 'Gibbs sweep: sampled paths (given uniforms)', ok)
+    check(tag + 'Gibbs sweep: integer transition counts', np.array_equal(counts[:N * N].reshape(N, N), Cint))
+    check(tag + 'Gibbs sweep: loglik of the filter', abs(ll.value - ref['loglik']) <= 1e-10 * abs(ref['loglik']))
     b.close()
     # discrete
     M = 11
