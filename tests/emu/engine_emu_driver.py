@@ -141,9 +141,58 @@ def run(N, chunk, warm):
     b.close()
 
 
+def run_time_sharded(N, world=3, halo=90, chunk=40, warm=40):
+    """C5 layout: each "rank" owns a third of every trajectory plus a halo (bhmm_b200_batch_create_ranges); the owned
+    statistics add up to the whole trajectories' (engine.TimeShardedTrajectories without torch)."""
+    orc = Oracle('port')
+    rng = np.random.default_rng(7 * N)
+    X = rng.random((N, N)) + 2.0 * np.eye(N)
+    A = np.ascontiguousarray(X / X.sum(axis=1)[:, None])
+    pi = rng.random(N)
+    pi /= pi.sum()
+    means, sigmas = np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
+    obs = []
+    for T in (400, 333):
+        s = rng.integers(0, N, T)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    ref = orc.estep_gaussian(obs, A, pi, means, sigmas)
+    total = np.zeros(lib.bhmm_b200_stats_len_gaussian(N))
+    llp = C.POINTER(C.c_longlong)
+    for r in range(world):
+        pieces, lengths, lo_l, hi_l = [], [], [], []
+        for o in obs:
+            T = len(o)
+            lo, hi = (T * r) // world, (T * (r + 1)) // world
+            a, b_ = max(0, lo - halo), min(T, hi + halo)
+            pieces.append(o[a:b_])
+            lengths.append(b_ - a)
+            lo_l.append(lo - a)
+            hi_l.append(hi - a)
+        cat = np.ascontiguousarray(np.concatenate(pieces))
+        offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+        lo_a, hi_a = np.array(lo_l, dtype=np.int64), np.array(hi_l, dtype=np.int64)
+        h = C.c_void_p()
+        rc_ok(lib.bhmm_b200_batch_create_ranges(C.byref(h), offsets.ctypes.data_as(llp), lo_a.ctypes.data_as(llp),
+                                                hi_a.ctypes.data_as(llp), len(obs), N, chunk, warm))
+        stats = np.zeros_like(total)
+        rc_ok(lib.bhmm_b200_estep_gaussian(h, d(cat), d(A), d(pi), d(means), d(sigmas), 1, None, d(stats), None))
+        total += stats
+        lib.bhmm_b200_batch_destroy(h)
+    st = unpack(total, N)
+    tag = 'time-sharded N=%d, %d shards: ' % (N, world)
+    check(tag + 'loglik', abs(st['loglik'] - ref['loglik']) <= 1e-10 * abs(ref['loglik']), '%.10e vs %.10e' % (st['loglik'], ref['loglik']))
+    check(tag + 'C', rel(st['C'], ref['C']) <= 1e-8, 'worst rel %.1e' % rel(st['C'], ref['C']))
+    check(tag + 'transitions counted', abs(st['C'].sum() - (sum(len(o) for o in obs) - len(obs))) < 1e-7)
+    check(tag + 'gamma0', rel(st['gamma0'], ref['gamma0']) <= 1e-10)
+    check(tag + 'sum gamma', rel(st['wsum'], ref['wsum']) <= 1e-9)
+
+
 if __name__ == '__main__':
     print('BHMM_B200_PANEL =', os.environ.get('BHMM_B200_PANEL'), flush=True)
     for spec in sys.argv[1:]:
+        if spec.startswith('s'):
+            run_time_sharded(int(spec[1:]))
+            continue
         N, chunk, warm = (int(x) for x in spec.split(','))
         run(N, chunk, warm)
     sys.exit(1 if failures else 0)
