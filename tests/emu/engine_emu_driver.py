@@ -66,10 +66,10 @@ def unpack(st, N):
     return out
 
 
-def run(N, chunk, warm):
+def run(N, chunk, warm, diag=2.0):
     orc = Oracle('port')
     rng = np.random.default_rng(N)
-    X = rng.random((N, N)) + 2.0 * np.eye(N)
+    X = rng.random((N, N)) + diag * np.eye(N)              # a heavy diagonal mixes slowly: short warm-ups fail
     A = np.ascontiguousarray(X / X.sum(axis=1)[:, None])
     pi = rng.random(N)
     pi /= pi.sum()
@@ -82,7 +82,7 @@ def run(N, chunk, warm):
     cat = np.ascontiguousarray(np.concatenate(obs))
     ref = orc.estep_gaussian(obs, A, pi, means, sigmas)
     wdd = sum((g * (o[:, None] - means) ** 2).sum(axis=0) for g, o in zip(ref['gammas'], obs))
-    tag = 'N=%d chunk=%d: ' % (N, chunk)
+    tag = 'N=%d chunk=%d warm=%d diag=%g: ' % (N, chunk, warm, diag)
     b = Batch(lengths, N, chunk, warm)
     stats = np.zeros(lib.bhmm_b200_stats_len_gaussian(N))
     gamma = np.zeros((b.rows, N))
@@ -96,6 +96,8 @@ def run(N, chunk, warm):
     check(tag + 'E-step gamma rows', np.max(np.abs(gamma - np.vstack(ref['gammas']))) <= 1e-10)
     info = b.info()
     check(tag + 'plan cut the trajectories into chains', info['chains'] > len(lengths) if chunk else True, str(info))
+    if diag > 10 and warm < 8:
+        check(tag + 'the short warm-up needed fix-ups', info['fix_f'] + info['fix_b'] > 0, str(info))
     path = np.zeros(b.rows, dtype=np.int32)
     rc_ok(lib.bhmm_b200_viterbi_gaussian(b.h, d(cat), d(A), d(pi), d(means), d(sigmas), 1, path.ctypes.data_as(C.POINTER(C.c_int)), None))
     ok = True
@@ -193,6 +195,6 @@ if __name__ == '__main__':
         if spec.startswith('s'):
             run_time_sharded(int(spec[1:]))
             continue
-        N, chunk, warm = (int(x) for x in spec.split(','))
-        run(N, chunk, warm)
+        parts = [float(x) for x in spec.split(',')]
+        run(int(parts[0]), int(parts[1]), int(parts[2]), *(parts[3:4]))
     sys.exit(1 if failures else 0)

@@ -44,14 +44,16 @@ def _drive(mode, specs, trace=False):
 
 def test_default_kernels_on_the_emulator(engine_emu):
     """Calibration: the GPU-validated team kernels, certification and path chase reproduce the oracle on the emulator."""
-    r = _drive(0, ['5,40,40', '32,40,40', 's32'], trace=True)
+    r = _drive(0, ['5,40,40', '32,40,40', 's32', '32,40,2,300'], trace=True)
     assert 'block 32 ' in r.stderr                      # the one-warp team kernels ran
 
 
 def test_panel_family_through_the_engine(engine_emu):
     """BHMM_B200_PANEL=1: N = 32 on the one-warp panel kernels, N = 21 / 40 on the wide kernels, chunked Viterbi, the Gibbs
-    sweep on the family's forward filter, and the time-sharded (C5) layout: owned ranges + halo, statistics add up."""
-    r = _drive(1, ['32,40,40', '21,40,40', '40,0,0', 's32'], trace=True)
+    sweep on the family's forward filter, and the time-sharded (C5) layout: owned ranges + halo, statistics add up; a slowly mixing model
+    with a two-frame warm-up exercises the failed-certification paths (exact forward fix-ups, backward retries with a longer
+    warm-up, Viterbi fix-ups)."""
+    r = _drive(1, ['32,40,40', '21,40,40', '40,0,0', 's32', '32,40,2,300'], trace=True)
     assert 'block 32 ' not in r.stderr                  # no team chain kernel was launched
     assert 'block 256 ' in r.stderr                     # wide kernels, 8 warps (N = 40)
 
@@ -59,6 +61,6 @@ def test_panel_family_through_the_engine(engine_emu):
 def test_wide_kernels_at_n32_and_n100_through_the_engine(engine_emu):
     """BHMM_B200_PANEL=2 (N = 32 on the 4-warp wide kernels) and the C4 state count: 13-warp wide kernels + Viterbi with the
     matrix column in registers."""
-    _drive(2, ['32,40,40'])
+    _drive(2, ['32,40,40', '32,40,2,300'])
     r = _drive(1, ['100,40,40'], trace=True)
     assert 'block 416 ' in r.stderr
