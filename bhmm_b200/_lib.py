@@ -81,6 +81,7 @@ _proto('bhmm_b200_adapt_warm', C.c_int, C.c_int, C.c_double, C.c_double, C.c_int
 _proto('bhmm_b200_batch_destroy', None, _vp)
 _proto('bhmm_b200_batch_replan', C.c_int, _vp, C.c_int, C.c_int)
 _proto('bhmm_b200_batch_uses_lane_kernels', C.c_int, _vp)
+_proto('bhmm_b200_batch_set_viterbi_only', C.c_int, _vp, C.c_int)
 _proto('bhmm_b200_batch_workspace_bytes', C.c_size_t, _vp)
 _proto('bhmm_b200_batch_attach_workspace', C.c_int, _vp, _vp, C.c_size_t)
 _proto('bhmm_b200_batch_info', None, _vp, _dp)

@@ -17,6 +17,7 @@ struct bhmm_b200_batch {
     std::vector<long long> offsets;
     int chunk = 0, warm_f = 0, warm_b = 0, warm_min = 32;
     bool lane = false;          // small-N fast path (lane_kernels.cuh) instead of the team family
+    bool no_alpha = false;      // Viterbi-only batch: no (rows, N) forward variables in the workspace
     double* d_g0buf = nullptr;
     int partial_rows = 0;
     HostPlan plan, segplan;
@@ -72,6 +73,7 @@ size_t batch_layout(bhmm_b200_batch* b, char* base)
     // forward variables: row-major (rows,N), or interleaved [chain/32][frame][state/2][chain%32] double2 (lane family)
     size_t alpha_doubles = (size_t)b->rows * N;
     if (b->lane) alpha_doubles = std::max(alpha_doubles, (size_t)((n + 31) / 32) * b->chunk * ((N + 1) / 2) * 64);
+    if (b->no_alpha) alpha_doubles = 32;      // Viterbi needs the observations, the back-pointer map and the path only
     const size_t o_alpha = cv.add<double>(alpha_doubles);
     const size_t o_F = cv.add<unsigned char>((size_t)b->rows * N * (N > 256 ? 2 : 1));
     if (base) {
@@ -181,6 +183,7 @@ int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
                  const double* sigma, double* d_gamma, double* d_stats, double* d_Bnum, cudaStream_t st)
 {
     const int N = b->N;
+    if (b->no_alpha) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "Viterbi-only batch: no forward variables"); return BHMM_ERR_UNSUPPORTED; }
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     b->w.ch.warm = b->warm_f;
@@ -273,6 +276,7 @@ int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
 {
     const int N = b->N;
     if (!b->own_lo.empty()) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "hidden-path sampling needs whole trajectories (batch has owned ranges)"); return BHMM_ERR_UNSUPPORTED; }
+    if (b->no_alpha) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "Viterbi-only batch: no forward variables"); return BHMM_ERR_UNSUPPORTED; }
     if (N > 256) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "sampling supports N <= 256"); return BHMM_ERR_UNSUPPORTED; }
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
@@ -416,6 +420,14 @@ extern "C" int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm)
 }
 
 extern "C" int bhmm_b200_batch_uses_lane_kernels(const bhmm_b200_batch* b) { return b && b->lane ? 1 : 0; }
+
+extern "C" int bhmm_b200_batch_set_viterbi_only(bhmm_b200_batch* b, int on)
+{
+    if (!b) return BHMM_ERR_INVALID;
+    b->no_alpha = on != 0;
+    b->carved = false;          // the workspace is laid out again (query bhmm_b200_batch_workspace_bytes after this call)
+    return BHMM_OK;
+}
 
 extern "C" size_t bhmm_b200_batch_workspace_bytes(const bhmm_b200_batch* b)
 {

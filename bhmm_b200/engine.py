@@ -58,7 +58,8 @@ class TrajectoryBatch(object):
     _shared = None      # a SubBatchedTrajectories owner lends its workspace to its groups
     _own_ranges = None  # owned (lo, hi) frame range per trajectory, None: whole trajectories
 
-    def __init__(self, observations, nstates, device=None, chunk=0, warm=0):
+    def __init__(self, observations, nstates, device=None, chunk=0, warm=0, viterbi_only=False):
+        self._viterbi_only = bool(viterbi_only)
         first = np.asarray(observations[0])
         host_dtype = np.int32 if np.issubdtype(first.dtype, np.integer) else np.float64
         lengths = [len(o) for o in observations]
@@ -111,6 +112,9 @@ class TrajectoryBatch(object):
                                                        lo.ctypes.data_as(llp), hi.ctypes.data_as(llp), self.K, self.N,
                                                        int(chunk), int(warm))
             check(rc)
+            if getattr(self, '_viterbi_only', False):
+                # no (rows, N) forward variables in the workspace: one very long trajectory fits a GPU for Viterbi (C5)
+                check(lib.bhmm_b200_batch_set_viterbi_only(self._handle, 1))
             self._attach()
         self._stats = torch.zeros(lib.bhmm_b200_stats_len_gaussian(self.N), dtype=torch.float64, device=self.device)
         self._path = None

@@ -142,6 +142,12 @@ int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm);
 /* 1 when the batch runs the small-N one-thread-per-chain kernels (N <= 16), 0 for the general-N team kernels.
  * The environment variable BHMM_B200_FAMILY=team forces the latter at creation time. */
 int bhmm_b200_batch_uses_lane_kernels(const bhmm_b200_batch* b);
+/* Viterbi-only batch: the workspace holds no (rows, N) forward variables -- observations, uint8 back-pointer map and path
+ * only (N + 4 + 8 bytes per frame instead of 9 N + 12) -- so that one very long trajectory (C5: 1e9 frames x 32 states = 44 GB)
+ * fits one GPU for bhmm_b200_viterbi_*; E-step and sampling calls on such a batch return BHMM_B200_ERR_UNSUPPORTED.  Call
+ * it right after bhmm_b200_batch_create, before bhmm_b200_batch_workspace_bytes / attach_workspace.  (The reference has no
+ * counterpart: compute_viterbi_paths, maximum_likelihood.py:332-352, keeps every trajectory's (T, N) table in host memory.) */
+int bhmm_b200_batch_set_viterbi_only(bhmm_b200_batch* b, int on);
 size_t bhmm_b200_batch_workspace_bytes(const bhmm_b200_batch* b);
 int bhmm_b200_batch_attach_workspace(bhmm_b200_batch* b, void* d_workspace, size_t bytes);
 /* info[0]=chains, [1]=chunk, [2]=warm, [3]=fwd fix-up sweeps, [4]=bwd fix-up sweeps, [5]=worst fwd mismatch,

@@ -143,6 +143,33 @@ def run(N, chunk, warm, diag=2.0):
     b.close()
 
 
+def run_viterbi_only(N):
+    """A Viterbi-only batch has no forward-variable workspace: Viterbi works, the E-step is refused."""
+    orc = Oracle('port')
+    rng = np.random.default_rng(11 * N)
+    X = rng.random((N, N)) + 2.0 * np.eye(N)
+    A = np.ascontiguousarray(X / X.sum(axis=1)[:, None])
+    pi = np.ones(N) / N
+    means, sigmas = np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
+    T = 500
+    s = rng.integers(0, N, T)
+    o = means[s] + sigmas[s] * rng.standard_normal(T)
+    lib.bhmm_b200_batch_workspace_bytes.restype = C.c_size_t
+    b = Batch([T], N, 50, 40)
+    full = lib.bhmm_b200_batch_workspace_bytes(b.h)
+    rc_ok(lib.bhmm_b200_batch_set_viterbi_only(b.h, 1))
+    lean = lib.bhmm_b200_batch_workspace_bytes(b.h)
+    tag = 'viterbi-only N=%d: ' % N
+    check(tag + 'workspace without the forward variables', full - lean >= T * N * 8 - 4096, '%d -> %d bytes' % (full, lean))
+    path = np.zeros(T, dtype=np.int32)
+    rc_ok(lib.bhmm_b200_viterbi_gaussian(b.h, d(o), d(A), d(pi), d(means), d(sigmas), 1, path.ctypes.data_as(C.POINTER(C.c_int)), None))
+    check(tag + 'path', np.array_equal(path, orc.viterbi(A, orc.gaussian_p_obs(o, means, sigmas), pi)), str(b.info()))
+    stats = np.zeros(lib.bhmm_b200_stats_len_gaussian(N))
+    rc = lib.bhmm_b200_estep_gaussian(b.h, d(o), d(A), d(pi), d(means), d(sigmas), 1, None, d(stats), None)
+    check(tag + 'E-step refused', rc == 5, 'rc %d' % rc)
+    b.close()
+
+
 def run_time_sharded(N, world=3, halo=90, chunk=40, warm=40):
     """C5 layout: each "rank" owns a third of every trajectory plus a halo (bhmm_b200_batch_create_ranges); the owned
     statistics add up to the whole trajectories' (engine.TimeShardedTrajectories without torch)."""
@@ -194,6 +221,9 @@ if __name__ == '__main__':
     for spec in sys.argv[1:]:
         if spec.startswith('s'):
             run_time_sharded(int(spec[1:]))
+            continue
+        if spec.startswith('v'):
+            run_viterbi_only(int(spec[1:]))
             continue
         parts = [float(x) for x in spec.split(',')]
         run(int(parts[0]), int(parts[1]), int(parts[2]), *(parts[3:4]))

@@ -450,3 +450,30 @@ def test_time_sharded_trajectories(eng, oracle_port, N, world):
         eng.TimeShardedTrajectories.combine(short, [s.estep_gaussian_local(A, pi, means, sigmas) for s in short])
     for s in short:
         s.close()
+
+
+def test_viterbi_only_batch(eng, oracle_port):
+    """A Viterbi-only batch (no forward-variable workspace: how one C5-sized trajectory fits a GPU for Viterbi) returns the
+    same paths as a full batch and refuses the E-step."""
+    rng = np.random.default_rng(77)
+    N = 5
+    X = rng.random((N, N)) + 2.0 * np.eye(N)
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    means, sigmas = np.linspace(-4, 4, N), np.linspace(0.6, 1.5, N)
+    obs = []
+    for T in (3000, 1200):
+        s = rng.integers(0, N, size=T)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    full = eng.TrajectoryBatch(obs, N, chunk=400, warm=0)
+    lean = eng.TrajectoryBatch(obs, N, chunk=400, warm=0, viterbi_only=True)
+    assert lean.workspace_bytes < full.workspace_bytes
+    p_full = full.viterbi_gaussian(A, pi, means, sigmas).cpu().numpy()
+    p_lean = lean.viterbi_gaussian(A, pi, means, sigmas).cpu().numpy()
+    assert np.array_equal(p_full, p_lean)
+    for o, p in zip(obs, lean.split(p_lean)):
+        assert np.array_equal(p, oracle_port.viterbi(A, oracle_port.gaussian_p_obs(o, means, sigmas), pi))
+    with pytest.raises(NotImplementedError):
+        lean.estep_gaussian(A, pi, means, sigmas)
+    full.close()
+    lean.close()

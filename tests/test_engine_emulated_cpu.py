@@ -44,7 +44,7 @@ def _drive(mode, specs, trace=False):
 
 def test_default_kernels_on_the_emulator(engine_emu):
     """Calibration: the GPU-validated team kernels, certification and path chase reproduce the oracle on the emulator."""
-    r = _drive(0, ['5,40,40', '32,40,40', 's32', '32,40,2,300'], trace=True)
+    r = _drive(0, ['5,40,40', '32,40,40', 's32', '32,40,2,300', 'v10'], trace=True)
     assert 'block 32 ' in r.stderr                      # the one-warp team kernels ran
 
 
@@ -61,6 +61,6 @@ def test_panel_family_through_the_engine(engine_emu):
 def test_wide_kernels_at_n32_and_n100_through_the_engine(engine_emu):
     """BHMM_B200_PANEL=2 (N = 32 on the 4-warp wide kernels) and the C4 state count: 13-warp wide kernels + Viterbi with the
     matrix column in registers."""
-    _drive(2, ['32,40,40', '32,40,2,300'])
+    _drive(2, ['32,40,40', '32,40,2,300', 'v32'])
     r = _drive(1, ['100,40,40'], trace=True)
     assert 'block 416 ' in r.stderr
