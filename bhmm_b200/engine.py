@@ -69,13 +69,15 @@ class TrajectoryBatch(object):
         self._setup(cat, lengths, nstates, device, chunk, warm)
 
     @classmethod
-    def from_concatenated(cls, rows, lengths, nstates, device=None, chunk=0, warm=0, _shared=None, own_ranges=None):
+    def from_concatenated(cls, rows, lengths, nstates, device=None, chunk=0, warm=0, _shared=None, own_ranges=None,
+                          viterbi_only=False):
         """Build from one concatenated per-frame array (numpy, or a torch tensor that may already live on the GPU)
         and the list of trajectory lengths.  ``own_ranges``: optional list of (lo, hi) per trajectory -- only those
         frames are owned (statistics, likelihood), the rest is halo (see ``TimeShardedTrajectories``)."""
         self = cls.__new__(cls)
         self._shared = _shared
         self._own_ranges = own_ranges
+        self._viterbi_only = bool(viterbi_only)   # no forward-variable workspace (Viterbi of one very long trajectory)
         self._setup(rows, lengths, nstates, device, chunk, warm)
         return self
 
