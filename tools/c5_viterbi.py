@@ -5,8 +5,8 @@
 
 The batch is Viterbi-only (no forward-variable workspace: N + 12 bytes per frame), the observations are generated on the
 device in blocks.  Prints one JSON line: frames per second, the plan (chains, chunk, warm-up, fix-up sweeps) and a
-checksum of the path; `--check K` additionally compares the first K frames... of a SHORT run with the sequential kernel
-(run it without BHMM_B200_PANEL and compare the checksums of the two JSON lines: the paths must be identical).
+checksum of the path: run a SHORT trajectory with and without BHMM_B200_PANEL and compare the checksums of the two lines
+-- the paths must be identical.
 """
 import argparse
 import json

@@ -16,6 +16,10 @@ for mode in 0 1 2; do
         > gpurun_out/bench_n32_panel$mode.json 2> gpurun_out/bench_n32_panel$mode.err
     echo "bench n32 panel=$mode: $?" | tee -a gpurun_out/first_call.log
 done
+for mode in 0 1; do
+    BHMM_B200_PANEL=$mode timeout 240 python tools/c5_viterbi.py --frames 2e7 > gpurun_out/c5_viterbi_2e7_panel$mode.json 2>> gpurun_out/first_call.log
+done
+BHMM_B200_PANEL=1 timeout 300 python tools/c5_viterbi.py --frames 1e9 > gpurun_out/c5_viterbi_1e9_panel1.json 2>> gpurun_out/first_call.log
 BHMM_B200_PANEL=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
     --log-file gpurun_out/launches_n32_panel1.csv python bench.py --workload n32 --trajectories 64 --steps 2 --warmup 1 --no-cpu-baseline \
     > gpurun_out/ncu_n32_panel1.log 2>&1
