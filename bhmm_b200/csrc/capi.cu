@@ -500,19 +500,58 @@ extern "C" int bhmm_b200_viterbi_dev(int* d_path, const double* d_A, const doubl
     const size_t o_off = cv.add<long long>(2);
     const size_t o_bp = cv.add<unsigned short>((size_t)T * N);
     const size_t o_chase = cv.add<char>(chase_scratch_bytes(N, T));
-    RC_TRY(g_lit_arena.ensure(cv.off + 256));
-    long long* d_offs = (long long*)(g_lit_arena.base + o_off);
+    const size_t o_flag = cv.add<int>(4);
+    // Opt-in (BHMM_B200_PANEL): a long trajectory is cut into chains whose max-product recursions run in parallel with
+    // certified hand-overs (panel_kernels.cu:k_viterbi_chain32); the strictly sequential kernel walks it at ~0.5 us per
+    // frame, slower than one CPU core.  Any decision too close to call, or an uncertifiable hand-over: sequential kernel.
+    const bool chunked = panel_viterbi_chain_ok(N) && T >= 4096;
+    LitScratch s;
+    char* base = nullptr;
+    if (chunked) {
+        RC_TRY(lit_prepare(s, N, T, cv.off + 256, true, st));
+        base = s.extra;
+    } else {
+        RC_TRY(g_lit_arena.ensure(cv.off + 256));
+        base = g_lit_arena.base;
+    }
+    long long* d_offs = (long long*)(base + o_off);
     const long long offs[2] = {0, T};
     CUDA_TRY(cudaMemcpyAsync(d_offs, offs, sizeof(offs), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     VitArgs a{};
     a.em.pobs = d_pobs;
     a.N = N; a.K = 1; a.offsets = d_offs; a.A = d_A; a.pi = d_pi;
-    a.backptr = g_lit_arena.base + o_bp; a.path = d_path;
-    RC_TRY(launch_viterbi_team(a, EM_POBS, st));
-    LAUNCHED(1);
+    a.backptr = base + o_bp; a.path = d_path;
+    bool map_done = false;
+    if (chunked && s.w.chunked) {
+        int* d_flag = (int*)(base + o_flag);
+        CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+        VitChainArgs va{};
+        va.em.pobs = d_pobs;
+        va.N = N; va.A = d_A; va.pi = d_pi; va.backptr = a.backptr;
+        va.hand_used = s.w.hu_f; va.hand_end = s.w.he_f; va.flagged = d_flag; va.margin_min = 1e-9;
+        const int rc = run_chains_certified(s.w, N, +1, [&](const Chains& ch, cudaStream_t s2) {
+            VitChainArgs x = va;
+            x.ch = ch;
+            return launch_viterbi_chain(x, EM_POBS, s2);
+        }, g_last_info, st);
+        if (rc == BHMM_OK) {
+            int flagged = 0;
+            CUDA_TRY(cudaMemcpyAsync(&flagged, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            map_done = (flagged == 0);
+        } else if (rc != BHMM_ERR_NOT_CERTIFIED) {
+            return rc;
+        } else {
+            clear_error();
+        }
+    }
+    if (!map_done) {
+        RC_TRY(launch_viterbi_team(a, EM_POBS, st));
+        LAUNCHED(1);
+    }
     if (N <= 256)       // uint8 maps: the path is resolved in parallel; wider back-pointers were backtraced in the kernel
-        RC_TRY(chase_single((const unsigned char*)a.backptr, N, T, g_lit_arena.base + o_chase, d_path, st));
+        RC_TRY(chase_single((const unsigned char*)a.backptr, N, T, base + o_chase, d_path, st));
     return finish(st);
 }
 

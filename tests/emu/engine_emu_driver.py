@@ -143,6 +143,25 @@ def run(N, chunk, warm, diag=2.0):
     b.close()
 
 
+def run_literal_viterbi(N, T=4500):
+    """bhmm.hidden.viterbi(A, pobs, pi) on one long trajectory through the host-pointer C ABI (bhmm_b200_viterbi): with the
+    panel family enabled the trajectory is cut into chains (T >= 4096), otherwise one team walks it."""
+    orc = Oracle('port')
+    rng = np.random.default_rng(3 * N)
+    X = rng.random((N, N)) + 2.0 * np.eye(N)
+    A = np.ascontiguousarray(X / X.sum(axis=1)[:, None])
+    pi = rng.random(N)
+    pi /= pi.sum()
+    pobs = np.ascontiguousarray(rng.random((T, N)) ** 3 + 1e-6)
+    path = np.zeros(T, dtype=np.int32)
+    rc_ok(lib.bhmm_b200_viterbi(path.ctypes.data_as(C.POINTER(C.c_int)), d(A), d(pobs), d(pi), N, T))
+    info = np.zeros(8)
+    lib.bhmm_b200_last_info(d(info))
+    check('literal viterbi N=%d T=%d: path' % (N, T), np.array_equal(path, orc.viterbi(A, pobs, pi)),
+          'chains %d chunk %d warm %d fix-ups %g' % (info[0], info[1], info[2], info[3]))
+    return int(info[0])
+
+
 def run_viterbi_only(N):
     """A Viterbi-only batch has no forward-variable workspace: Viterbi works, the E-step is refused."""
     orc = Oracle('port')
@@ -221,6 +240,11 @@ if __name__ == '__main__':
     for spec in sys.argv[1:]:
         if spec.startswith('s'):
             run_time_sharded(int(spec[1:]))
+            continue
+        if spec.startswith('l'):
+            chains = run_literal_viterbi(int(spec[1:]))
+            if os.environ.get('BHMM_B200_PANEL') in ('1', '2'):
+                check('literal viterbi: the trajectory was cut into chains', chains > 1, str(chains))
             continue
         if spec.startswith('v'):
             run_viterbi_only(int(spec[1:]))

@@ -224,6 +224,18 @@ def parity():
         check('chunked viterbi N=32, 60000 frames, chunk=%d: path' % chunk, np.array_equal(got, want),
               '%d mismatches; info %s' % (int(np.sum(got != want)), b.info()))
         b.close()
+    # ---- literal hidden.viterbi on one long trajectory (the case where the sequential kernel loses to a CPU core)
+    N3 = 3
+    A3 = np.array([[0.97, 0.02, 0.01], [0.03, 0.94, 0.03], [0.01, 0.04, 0.95]])
+    pobs3 = np.ascontiguousarray(rng.random((1000000, N3)) ** 2 + 1e-3)
+    pi3 = np.ones(N3) / N3
+    t0 = time.time()
+    got = hidden.viterbi(A3, pobs3, pi3)
+    t1 = time.time()
+    want = orc.viterbi(A3, pobs3, pi3)
+    t2 = time.time()
+    check('literal hidden.viterbi N=3, T=1e6 (chunked): path', np.array_equal(got, want),
+          'GPU call %.1f ms (incl. copies), oracle C %.1f ms' % (1e3 * (t1 - t0), 1e3 * (t2 - t1)))
     b = TrajectoryBatch(obs, N, chunk=214, warm=0)
     path, counts, sums, ll = b.gibbs_gaussian(A, pi, means, sigmas, seed=7, sweep=0)
     check('gibbs sweep N=32: loglik of the filter', abs(ll - ref['loglik']) <= RTOL * abs(ref['loglik']))
