@@ -529,7 +529,7 @@ extern "C" int bhmm_b200_viterbi_dev(int* d_path, const double* d_A, const doubl
         VitChainArgs va{};
         va.em.pobs = d_pobs;
         va.N = N; va.A = d_A; va.pi = d_pi; va.backptr = a.backptr;
-        va.hand_used = s.w.hu_f; va.hand_end = s.w.he_f; va.flagged = d_flag; va.margin_min = 1e-9;
+        va.hand_used = s.w.hu_f; va.hand_end = s.w.he_f; va.flagged = d_flag; va.margin_min = std::max(1e-9, 1e4 * g_cert_tol);
         const int rc = run_chains_certified(s.w, N, +1, [&](const Chains& ch, cudaStream_t s2) {
             VitChainArgs x = va;
             x.ch = ch;

@@ -517,7 +517,7 @@ static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const do
         VitChainArgs va{};
         va.em = em; va.N = N; va.A = b->d_A; va.pi = b->d_pi; va.backptr = b->d_F;
         va.hand_used = b->w.hu_f; va.hand_end = b->w.he_f; va.flagged = b->d_err + 1;
-        va.margin_min = 1e-9;                               // four orders above the certification tolerance (1e-13)
+        va.margin_min = std::max(1e-9, 1e4 * g_cert_tol);   // four orders above the certification tolerance (default 1e-13)
         b->w.ch.warm = b->warm_f;
         const int rc = run_chains_certified(b->w, N, +1, [&](const Chains& ch, cudaStream_t s2) {
             VitChainArgs x = va;
