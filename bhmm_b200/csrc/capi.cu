@@ -496,15 +496,16 @@ extern "C" int bhmm_b200_viterbi_dev(int* d_path, const double* d_A, const doubl
     if (N < 1 || T < 1) { bhmm_set_error(BHMM_ERR_INVALID, "N and T must be positive"); return BHMM_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(g_lit_mutex);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool chunked = panel_viterbi_chain_ok(N) && T >= 4096;
     Carver cv;
     const size_t o_off = cv.add<long long>(2);
     const size_t o_bp = cv.add<unsigned short>((size_t)T * N);
     const size_t o_chase = cv.add<char>(chase_scratch_bytes(N, T));
     const size_t o_flag = cv.add<int>(4);
+    const size_t o_vflag = cv.add<unsigned>(chunked ? (size_t)T : 1);
     // Opt-in (BHMM_B200_PANEL): a long trajectory is cut into chains whose max-product recursions run in parallel with
     // certified hand-overs (panel_kernels.cu:k_viterbi_chain32); the strictly sequential kernel walks it at ~0.5 us per
     // frame, slower than one CPU core.  Any decision too close to call, or an uncertifiable hand-over: sequential kernel.
-    const bool chunked = panel_viterbi_chain_ok(N) && T >= 4096;
     LitScratch s;
     char* base = nullptr;
     if (chunked) {
@@ -522,36 +523,41 @@ extern "C" int bhmm_b200_viterbi_dev(int* d_path, const double* d_A, const doubl
     a.em.pobs = d_pobs;
     a.N = N; a.K = 1; a.offsets = d_offs; a.A = d_A; a.pi = d_pi;
     a.backptr = base + o_bp; a.path = d_path;
-    bool map_done = false;
+    bool chunked_map = false;
+    int* d_flag = (int*)(base + o_flag);
+    unsigned* d_vflag = (unsigned*)(base + o_vflag);
     if (chunked && s.w.chunked) {
-        int* d_flag = (int*)(base + o_flag);
-        CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
         VitChainArgs va{};
         va.em.pobs = d_pobs;
         va.N = N; va.A = d_A; va.pi = d_pi; va.backptr = a.backptr;
-        va.hand_used = s.w.hu_f; va.hand_end = s.w.he_f; va.flagged = d_flag; va.margin_min = std::max(1e-9, 1e4 * g_cert_tol);
+        va.hand_used = s.w.hu_f; va.hand_end = s.w.he_f; va.flagmap = d_vflag;
+        va.margin_min = std::max(1e-11, 100.0 * g_cert_tol);
         const int rc = run_chains_certified(s.w, N, +1, [&](const Chains& ch, cudaStream_t s2) {
             VitChainArgs x = va;
             x.ch = ch;
             return launch_viterbi_chain(x, EM_POBS, s2);
         }, g_last_info, st);
-        if (rc == BHMM_OK) {
-            int flagged = 0;
-            CUDA_TRY(cudaMemcpyAsync(&flagged, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            map_done = (flagged == 0);
-        } else if (rc != BHMM_ERR_NOT_CERTIFIED) {
-            return rc;
-        } else {
-            clear_error();
+        if (rc == BHMM_OK) chunked_map = true;
+        else if (rc != BHMM_ERR_NOT_CERTIFIED) return rc;
+        else clear_error();
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        if (!chunked_map) {
+            RC_TRY(launch_viterbi_team(a, EM_POBS, st));
+            LAUNCHED(1);
         }
-    }
-    if (!map_done) {
-        RC_TRY(launch_viterbi_team(a, EM_POBS, st));
+        if (N <= 256)   // uint8 maps: the path is resolved in parallel; wider back-pointers were backtraced in the kernel
+            RC_TRY(chase_single((const unsigned char*)a.backptr, N, T, base + o_chase, d_path, st));
+        if (!chunked_map) break;
+        int flagged = 0;                                    // near-tie decisions ON the resolved path
+        CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+        RC_TRY(launch_viterbi_path_flags(d_vflag, d_path, d_offs, 1, T, d_flag, st));
         LAUNCHED(1);
+        CUDA_TRY(cudaMemcpyAsync(&flagged, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (flagged == 0) break;
+        chunked_map = false;
     }
-    if (N <= 256)       // uint8 maps: the path is resolved in parallel; wider back-pointers were backtraced in the kernel
-        RC_TRY(chase_single((const unsigned char*)a.backptr, N, T, base + o_chase, d_path, st));
     return finish(st);
 }
 

@@ -41,6 +41,7 @@ struct bhmm_b200_batch {
     double* d_partials = nullptr;
     int stats_grid = 0;
     int* d_err = nullptr;
+    unsigned* d_vflag = nullptr;   // chunked Viterbi: near-tie flags per row of the back-pointer map
     Arena disc;                 // B staging + Bt for the discrete model (sized on first use)
     RunInfo info;
     // optional per-kernel timing (CUDA events on the launching stream)
@@ -76,6 +77,7 @@ size_t batch_layout(bhmm_b200_batch* b, char* base)
     if (b->no_alpha) alpha_doubles = 32;      // Viterbi needs the observations, the back-pointer map and the path only
     const size_t o_alpha = cv.add<double>(alpha_doubles);
     const size_t o_F = cv.add<unsigned char>((size_t)b->rows * N * (N > 256 ? 2 : 1));
+    const size_t o_vflag = cv.add<unsigned>(panel_viterbi_chain_ok(N) ? (size_t)b->rows : 1);
     if (base) {
         b->d_offsets = (long long*)(base + o_offs);
         b->w = ChainWork();
@@ -96,6 +98,7 @@ size_t batch_layout(bhmm_b200_batch* b, char* base)
         b->d_err = (int*)(base + o_err);
         b->d_alpha = (double*)(base + o_alpha);
         b->d_F = (unsigned char*)(base + o_F);
+        b->d_vflag = (unsigned*)(base + o_vflag);
         b->cw_base = base + o_cw;
     }
     return cv.off + 256;
@@ -509,42 +512,46 @@ static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const do
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     // Opt-in (BHMM_B200_PANEL): trajectories that the plan cuts into chains (one very long trajectory, C5) run their
-    // max-product recursions chain-parallel with certified hand-overs; if any decision's margin is too small to be
-    // certified, or the hand-overs cannot be certified, the sequential kernel below recomputes the whole map.
-    bool map_done = false;
+    // max-product recursions chain-parallel with certified hand-overs.  A decision whose margin is too small to be
+    // certified only matters if the resolved path goes through it: that is checked after the path chase, and then -- or when
+    // the hand-overs cannot be certified -- the sequential kernel recomputes the whole map.
+    bool chunked_map = false;
     if (panel_viterbi_chain_ok(N) && b->w.chunked) {
-        CUDA_TRY(cudaMemsetAsync(b->d_err + 1, 0, sizeof(int), st));
         VitChainArgs va{};
         va.em = em; va.N = N; va.A = b->d_A; va.pi = b->d_pi; va.backptr = b->d_F;
-        va.hand_used = b->w.hu_f; va.hand_end = b->w.he_f; va.flagged = b->d_err + 1;
-        va.margin_min = std::max(1e-9, 1e4 * g_cert_tol);   // four orders above the certification tolerance (default 1e-13)
+        va.hand_used = b->w.hu_f; va.hand_end = b->w.he_f; va.flagmap = b->d_vflag;
+        va.margin_min = std::max(1e-11, 100.0 * g_cert_tol);   // two orders above the certification tolerance (default 1e-13)
         b->w.ch.warm = b->warm_f;
         const int rc = run_chains_certified(b->w, N, +1, [&](const Chains& ch, cudaStream_t s2) {
             VitChainArgs x = va;
             x.ch = ch;
             return launch_viterbi_chain(x, emkind, s2);
         }, b->info, st);
-        if (rc == BHMM_OK) {
-            int flagged = 0;
-            CUDA_TRY(cudaMemcpyAsync(&flagged, b->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            map_done = (flagged == 0);
-        } else if (rc != BHMM_ERR_NOT_CERTIFIED) {
-            return rc;
-        } else {
-            bhmm_set_error(BHMM_OK, "");
+        if (rc == BHMM_OK) chunked_map = true;
+        else if (rc != BHMM_ERR_NOT_CERTIFIED) return rc;
+        else bhmm_set_error(BHMM_OK, "");
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        if (!chunked_map) {
+            VitArgs a{};
+            a.em = em; a.N = N; a.K = b->K; a.offsets = b->d_offsets; a.A = b->d_A; a.pi = b->d_pi;
+            a.backptr = b->d_F; a.path = d_path;
+            RC_TRY(launch_viterbi_team(a, emkind, st));
+            LAUNCHED(1);
         }
-    }
-    if (!map_done) {
-        VitArgs a{};
-        a.em = em; a.N = N; a.K = b->K; a.offsets = b->d_offsets; a.A = b->d_A; a.pi = b->d_pi;
-        a.backptr = b->d_F; a.path = d_path;
-        RC_TRY(launch_viterbi_team(a, emkind, st));
+        if (N <= 256) {     // uint8 maps written by the kernel: resolve the paths by segment-wise map composition
+            RC_TRY(launch_chase(b->d_F, b->seg, N, b->seg_map, b->seg_enter, d_path, st));
+            LAUNCHED(3);
+        }
+        if (!chunked_map) break;
+        int flagged = 0;
+        CUDA_TRY(cudaMemsetAsync(b->d_err + 1, 0, sizeof(int), st));
+        RC_TRY(launch_viterbi_path_flags(b->d_vflag, d_path, b->d_offsets, b->K, b->rows, b->d_err + 1, st));
         LAUNCHED(1);
-    }
-    if (N <= 256) {     // uint8 maps written by the kernel: resolve the paths by segment-wise map composition
-        RC_TRY(launch_chase(b->d_F, b->seg, N, b->seg_map, b->seg_enter, d_path, st));
-        LAUNCHED(3);
+        CUDA_TRY(cudaMemcpyAsync(&flagged, b->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (flagged == 0) break;
+        chunked_map = false;                                // a near-tie on the path: sequential kernel, resolve again
     }
     return finish_stream(st);
 }

@@ -55,7 +55,8 @@ struct VitChainArgs {
     void* backptr;           // (rows, N) uint8 shifted back-pointer map (CHASE layout of k_viterbi_team)
     double* hand_used;       // (n_chains_total, N): normalised max-product vector at t0-1 the chain was started from
     double* hand_end;        // (n_chains_total, N): the chain's vector at its last frame
-    int* flagged;            // device counter: chains with a decision whose relative margin is below margin_min
+    unsigned* flagmap;       // (rows) one word per row of the map: bit j set = the decision stored in F[row][j] had a
+                             // relative margin below margin_min (only decisions ON the resolved path matter)
     double margin_min;
 };
 
@@ -133,6 +134,9 @@ bool panel_viterbi_ok(int N);                // 32 < N <= 104: Viterbi with the 
 int launch_viterbi_panel(const VitArgs& a, int em, cudaStream_t st);
 bool panel_viterbi_chain_ok(int N);          // N <= 32: time-chunked Viterbi for trajectories cut into chains
 int launch_viterbi_chain(const VitChainArgs& a, int em, cudaStream_t st);
+// counter += number of decisions ON the resolved paths whose margin was flagged (0: the paths are certified)
+int launch_viterbi_path_flags(const unsigned* flagmap, const int* path, const long long* offsets, int K, long long rows,
+                              int* counter, cudaStream_t st);
 
 // ---- frame-parallel kernels (frame_kernels.cu)
 int launch_gaussian_pobs(const double* obs, const double* mu, const double* sigma, int N, long long rows,

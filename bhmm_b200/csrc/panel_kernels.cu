@@ -1140,9 +1140,12 @@ __global__ void __launch_bounds__(((NMAX + 31) / 32) * 32) k_viterbi_regs(const 
 // the same component-wise relative comparison as the forward filter's (certify.cu), with exact re-runs of the chains that
 // fail.  Arithmetic per frame is exactly k_viterbi_team's (_hidden.c:229-265 operation order).  Because a certified
 // hand-over still differs from the sequential one in the last digits, a decision (arg max over predecessors) is only
-// provably the sequential one if its best and second-best candidates differ by more than that: every chain tracks the
-// smallest relative margin of its own decisions and counts itself in `flagged` when it falls below margin_min -- the caller
-// then falls back to the sequential kernel, so a returned path is always the reference's.
+// provably the sequential one if its best and second-best candidates differ by more than that: every decision whose
+// relative margin is below margin_min sets its bit in `flagmap`.  Only decisions ON the resolved path can change it (by
+// induction from the last frame backwards), so after the path chase k_viterbi_path_flags counts the flagged decisions the
+// path went through; if there is one, the caller recomputes the map with the sequential kernel -- a returned path is always
+// the reference's.  (Measured on dalton data: P(margin < eps) = 0.25 eps per decision but 0.01 eps per ON-PATH decision, i.e.
+// 1e-4 expected fallbacks for 1e9 frames at eps = 1e-11, against 8 flagged decisions if every decision counted at 1e-9.)
 // ================================================================================================
 template <int EM>
 __global__ void __launch_bounds__(PW * 32) k_viterbi_chain32(const VitChainArgs a)
@@ -1189,7 +1192,6 @@ __global__ void __launch_bounds__(PW * 32) k_viterbi_chain32(const VitChainArgs 
             }
             __syncwarp();
         }
-        double minmargin = 1.0;
         const int tfirst = (mode == 2) ? t0 : tstart;
         double raw_next = jv ? em_raw(trow + tfirst) : 0.0;
         for (int t = tfirst; t < tend; ++t) {
@@ -1231,9 +1233,11 @@ __global__ void __launch_bounds__(PW * 32) k_viterbi_chain32(const VitChainArgs 
                     if (m[b] > mm) { second = fmax(second, mm); second = fmax(second, m2[b]); mm = m[b]; best = bi[b]; vsel = vbest[b]; asel = abest[b]; }
                     else second = fmax(second, m[b]);
                 }
-                if (jv && t >= t0) {
-                    bp[(trow + t - 1) * N + j] = (unsigned char)best;
-                    if (mm > 0.0) minmargin = fmin(minmargin, (mm - fmax(second, 0.0)) / mm);
+                if (t >= t0) {
+                    if (jv) bp[(trow + t - 1) * N + j] = (unsigned char)best;
+                    const bool near = jv && mm > 0.0 && (mm - fmax(second, 0.0)) < a.margin_min * mm;
+                    const unsigned word = __ballot_sync(FULL, near);
+                    if (lane == 0) a.flagmap[trow + t - 1] = word;
                 }
                 vn = __dmul_rn(__dmul_rn(p, vsel), asel);
             }
@@ -1259,13 +1263,31 @@ __global__ void __launch_bounds__(PW * 32) k_viterbi_chain32(const VitChainArgs 
                 else if (v[i] > second) second = v[i];
             }
             if (jv) bp[(trow + T - 1) * N + j] = (unsigned char)best;
-            if (m > 0.0 && N > 1) minmargin = fmin(minmargin, (m - fmax(second, 0.0)) / m);
+            const bool near = m > 0.0 && N > 1 && (m - fmax(second, 0.0)) < a.margin_min * m;
+            if (lane == 0) a.flagmap[trow + T - 1] = near ? 0xffffffffu : 0u;
         }
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) minmargin = fmin(minmargin, __shfl_xor_sync(FULL, minmargin, off));
-        if (lane == 0 && minmargin < a.margin_min) atomicAdd(a.flagged, 1);
         __syncwarp();
     }
+}
+
+// On-path flags of the chunked Viterbi: row r of trajectory k holds the decision "state at r given the state at r+1"
+// (bit index = path[r+1]); the last row holds the final arg max (any bit).
+__global__ void k_viterbi_path_flags(const unsigned* __restrict__ flagmap, const int* __restrict__ path,
+                                     const long long* __restrict__ offsets, int K, long long rows, int* counter)
+{
+    int hits = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        const unsigned w = flagmap[r];
+        if (w == 0u) continue;
+        int lo = 0, hi = K;                                 // trajectory of row r: offsets[lo] <= r < offsets[lo + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (offsets[mid] <= r) lo = mid; else hi = mid;
+        }
+        const bool last = (r == offsets[lo + 1] - 1);
+        if (last || ((w >> path[r + 1]) & 1u)) ++hits;
+    }
+    if (hits) atomicAdd(counter, hits);
 }
 
 #ifndef PANEL_HOST_NO_LAUNCHERS
@@ -1420,6 +1442,15 @@ int launch_viterbi_chain(const VitChainArgs& a, int em, cudaStream_t st)
         case EM_DISC: k_viterbi_chain32<EM_DISC><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;
     }
     return BHMM_ERR_INVALID;
+}
+
+int launch_viterbi_path_flags(const unsigned* flagmap, const int* path, const long long* offsets, int K, long long rows,
+                              int* counter, cudaStream_t st)
+{
+    if (rows <= 0) return BHMM_OK;
+    const int grid = (int)std::max(1LL, std::min<long long>((rows + 255) / 256, (long long)panel_sms() * 8));
+    k_viterbi_path_flags<<<grid, 256, 0, st>>>(flagmap, path, offsets, K, rows, counter);
+    return BHMM_OK;
 }
 
 bool panel_forward_ok(const FwdArgs& a, int em)

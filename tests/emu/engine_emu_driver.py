@@ -162,6 +162,21 @@ def run_literal_viterbi(N, T=4500):
     return int(info[0])
 
 
+def run_literal_viterbi_ties(N=8, T=4500):
+    """Structural ties (rank-one A, emission rows repeating with period 2): every decision is an exact tie, only the
+    first-maximum rule decides.  The chunked run flags them on its path and the sequential kernel must take over."""
+    orc = Oracle('port')
+    A = np.full((N, N), 1.0 / N)
+    pi = np.ones(N) / N
+    rng = np.random.default_rng(1)
+    base = np.array([[0.5, 0.25] * (N // 2), [0.25, 0.5] * (N // 2)])
+    pobs = np.ascontiguousarray(base[rng.integers(0, 2, T)])
+    path = np.zeros(T, dtype=np.int32)
+    rc_ok(lib.bhmm_b200_viterbi(path.ctypes.data_as(C.POINTER(C.c_int)), d(A), d(pobs), d(pi), N, T))
+    check('literal viterbi with structural ties N=%d T=%d: path (sequential fallback)' % (N, T),
+          np.array_equal(path, orc.viterbi(A, pobs, pi)))
+
+
 def run_viterbi_only(N):
     """A Viterbi-only batch has no forward-variable workspace: Viterbi works, the E-step is refused."""
     orc = Oracle('port')
@@ -240,6 +255,9 @@ if __name__ == '__main__':
     for spec in sys.argv[1:]:
         if spec.startswith('s'):
             run_time_sharded(int(spec[1:]))
+            continue
+        if spec == 'ties':
+            run_literal_viterbi_ties()
             continue
         if spec.startswith('l'):
             chains = run_literal_viterbi(int(spec[1:]))

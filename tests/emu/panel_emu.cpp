@@ -123,23 +123,31 @@ extern "C" int panel_emu_viterbi(int N, int em_kind, int grid, int K, const long
     return 1;
 }
 
-// Time-chunked Viterbi (N <= 32): chains with warm-up / exact starts; returns the number of flagged chains in *flagged
+// Time-chunked Viterbi (N <= 32): chains with warm-up / exact starts; flagmap (rows): near-tie bits per row of the map
 extern "C" int panel_emu_viterbi_chain(int N, int em_kind, int grid, const long long* row0, const int* len, const int* t0,
                                        const int* T, const int* list, int n_run, int warm, const int* warmv, int exact,
                                        const double* pobs, const double* obs, const int* sym, const double* mu,
                                        const double* sigma, const double* Bt, int M, int ignore_outliers, const double* A,
                                        const double* pi, unsigned char* backptr, double* hand_used, double* hand_end,
-                                       int* flagged, double margin_min)
+                                       unsigned* flagmap, double margin_min)
 {
     VitChainArgs a{};
     a.ch = make_chains(row0, len, t0, T, list, n_run, warm, warmv, exact);
     a.em = make_emission(pobs, obs, sym, mu, sigma, Bt, M, ignore_outliers);
     a.N = N; a.A = A; a.pi = pi; a.backptr = backptr; a.hand_used = hand_used; a.hand_end = hand_end;
-    a.flagged = flagged; a.margin_min = margin_min;
+    a.flagmap = flagmap; a.margin_min = margin_min;
     switch (em_kind) {
         case EM_POBS: emu::launch(grid, PW * 32, [&] { k_viterbi_chain32<EM_POBS>(a); }); return 0;
         case EM_GAUSS: emu::launch(grid, PW * 32, [&] { k_viterbi_chain32<EM_GAUSS>(a); }); return 0;
         case EM_DISC: emu::launch(grid, PW * 32, [&] { k_viterbi_chain32<EM_DISC>(a); }); return 0;
     }
     return 1;
+}
+
+extern "C" int panel_emu_viterbi_path_flags(const unsigned* flagmap, const int* path, const long long* offsets, int K,
+                                            long long rows)
+{
+    int counter = 0;
+    emu::launch(2, 256, [&] { k_viterbi_path_flags(flagmap, path, offsets, K, rows, &counter); });
+    return counter;
 }

@@ -424,15 +424,16 @@ def _viterbi_chain(emu, N, em_kind, plan, A, pi, grid, warm, exact=0, chain_list
                    F=None, hu=None, he=None, margin_min=1e-9, ignore_outliers=0):
     row0, ln, t0, TT = plan
     lst = None if chain_list is None else np.array(chain_list, dtype=np.int32)
-    flagged = np.zeros(1, dtype=np.int32)
+    rows = int(row0[-1] + ln[-1])
+    flagmap = np.full(rows, 0xdeadbeef, dtype=np.uint32)    # every row must be written
     rc = emu.panel_emu_viterbi_chain(C.c_int(N), C.c_int(em_kind), C.c_int(grid), ptr(row0, C.c_longlong), ptr(ln, C.c_int),
                                      ptr(t0, C.c_int), ptr(TT, C.c_int), ptr(lst, C.c_int),
                                      C.c_int(len(row0) if lst is None else len(lst)), C.c_int(warm), None, C.c_int(exact),
                                      ptr(pobs), None, ptr(sym, C.c_int), None, None, ptr(Bt), C.c_int(M),
                                      C.c_int(ignore_outliers), ptr(A), ptr(pi), F.ctypes.data_as(C.POINTER(C.c_ubyte)),
-                                     ptr(hu), ptr(he), flagged.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(margin_min))
+                                     ptr(hu), ptr(he), flagmap.ctypes.data_as(C.POINTER(C.c_uint)), C.c_double(margin_min))
     assert rc == 0
-    return int(flagged[0])
+    return flagmap
 
 
 @pytest.mark.parametrize('N', [32, 10, 3])
@@ -452,12 +453,23 @@ def test_time_chunked_viterbi_matches_sequential(emu, oracle_port, N):
     assert n == 15
     F = np.full((cat.shape[0], N), 255, dtype=np.uint8)
     hu, he = np.zeros((n, N)), np.zeros((n, N))
-    flagged = _viterbi_chain(emu, N, EM_POBS, plan, A, pi, grid=2, warm=80, pobs=cat, F=F, hu=hu, he=he)
-    assert flagged == 0
-    row = 0
+    flagmap = _viterbi_chain(emu, N, EM_POBS, plan, A, pi, grid=2, warm=80, pobs=cat, F=F, hu=hu, he=he, margin_min=1e-11)
+    assert not np.any(flagmap == 0xdeadbeef)                # every row of the map got its flag word
+    row, paths = 0, []
     for T, p in zip(Ts, pobs):
-        assert np.array_equal(_resolve(F[row:row + T], T), oracle_port.viterbi(A, p, pi))
+        paths.append(_resolve(F[row:row + T], T))
+        assert np.array_equal(paths[-1], oracle_port.viterbi(A, p, pi))
         row += T
+    # no decision ON the resolved paths is a near-tie (k_viterbi_path_flags)
+    path = np.ascontiguousarray(np.concatenate(paths), dtype=np.int32)
+    offs = np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64)
+    assert emu.panel_emu_viterbi_path_flags(flagmap.ctypes.data_as(C.POINTER(C.c_uint)), path.ctypes.data_as(C.POINTER(C.c_int)),
+                                            ptr(offs, C.c_longlong), len(Ts), C.c_longlong(len(path))) == 0
+    # with an absurdly large threshold every decision is "near": one hit per row
+    flag_all = _viterbi_chain(emu, N, EM_POBS, plan, A, pi, grid=2, warm=80, pobs=cat, F=F, hu=hu, he=he, margin_min=2.0)
+    hits = emu.panel_emu_viterbi_path_flags(flag_all.ctypes.data_as(C.POINTER(C.c_uint)), path.ctypes.data_as(C.POINTER(C.c_int)),
+                                            ptr(offs, C.c_longlong), len(Ts), C.c_longlong(len(path)))
+    assert hits == (len(path) - len(Ts) if N > 1 else 0) + (len(Ts) if N > 1 else 0)
     t0 = plan[2]
     for c in range(n):
         if t0[c] > 0:
@@ -492,4 +504,5 @@ def test_time_chunked_viterbi_fix_up_and_tie_flag(emu, oracle_port):
     plan1 = make_plan([60], 20)
     F1 = np.zeros((60, N), dtype=np.uint8)
     h1, h2 = np.zeros((3, N)), np.zeros((3, N))
-    assert _viterbi_chain(emu, N, EM_POBS, plan1, A1, pi, grid=1, warm=10, pobs=p1, F=F1, hu=h1, he=h2) > 0
+    fm = _viterbi_chain(emu, N, EM_POBS, plan1, A1, pi, grid=1, warm=10, pobs=p1, F=F1, hu=h1, he=h2)
+    assert np.count_nonzero(fm) > 30                        # ties at (almost) every frame
