@@ -53,9 +53,12 @@ def test_panel_family_through_the_engine(engine_emu):
     sweep on the family's forward filter, and the time-sharded (C5) layout: owned ranges + halo, statistics add up; a slowly mixing model
     with a two-frame warm-up exercises the failed-certification paths (exact forward fix-ups, backward retries with a longer
     warm-up, Viterbi fix-ups)."""
-    r = _drive(1, ['32,40,40', '21,40,40', '40,0,0', 's32', '32,40,2,300', 'l8', 'ties'], trace=True)
+    r = _drive(1, ['32,40,40', '21,40,40', '40,0,0', 's32', '32,40,2,300', 'l8'], trace=True)
     assert 'block 32 ' not in r.stderr                  # no team chain kernel was launched
     assert 'block 256 ' in r.stderr                     # wide kernels, 8 warps (N = 40)
+    # structural ties: the chunked Viterbi flags decisions on its path and the sequential team kernel takes over
+    r = _drive(1, ['ties'], trace=True)
+    assert 'block 32 ' in r.stderr
 
 
 def test_wide_kernels_at_n32_and_n100_through_the_engine(engine_emu):
