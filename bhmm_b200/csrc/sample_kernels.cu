@@ -13,6 +13,8 @@
 //        k_chase_path  per segment, follows the maps from the now-known entering state and writes the path.
 // Device Philox4x32-10 supplies the uniforms in production; an explicit uniform array reproduces the
 // reference's glibc stream for parity.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -107,6 +109,51 @@ __global__ void k_chase_link(Chains seg, int N, const unsigned char* __restrict_
         s = map[(long long)cur * N + s];
         if (seg.t0[cur] == 0) break;
         --cur;
+    }
+}
+
+// The same link step for batches with very many segments (one 1e9-frame trajectory has 3.9e6 of them: the walk above is
+// that many DEPENDENT global loads, of the order of seconds).  One warp per trajectory end: the map rows of the next 32
+// segments are contiguous, the warp copies them into shared memory with coalesced loads whose addresses do not depend on
+// the walk, lane 0 walks the 32 rows there (one shared-memory round trip per segment), the lanes store the 32 entering
+// states.  Chosen by the launchers when the batch has at least chase_tiled_threshold() segments.
+__global__ void k_chase_link_tiled(Chains seg, int N, const unsigned char* __restrict__ map, int* __restrict__ enter)
+{
+    __shared__ unsigned char tile[32 * 256];
+    __shared__ int states[32];
+    const int lane = threadIdx.x;
+    const int sidx = blockIdx.x * 32 + lane;
+    const bool is_last = sidx < seg.n && (seg.t0[sidx] + seg.len[sidx] >= seg.T[sidx]);
+    unsigned todo = __ballot_sync(0xffffffffu, is_last);
+    while (todo) {
+        const int l0 = __ffs(todo) - 1;
+        todo &= todo - 1;
+        int cur = blockIdx.x * 32 + l0;                       // the last segment of one trajectory
+        int s = 0;                                            // F at the last frame ignores the entering state
+        for (;;) {
+            const int lo = max(cur - 31, 0);
+            const int nrows = cur - lo + 1;
+            for (int k = lane; k < nrows * N; k += 32) {      // tile row l = segment cur - l
+                const int r = k / N, c = k - r * N;
+                tile[(cur - lo - r) * N + c] = map[(long long)lo * N + k];
+            }
+            const int idx = cur - lane;
+            const unsigned fm = __ballot_sync(0xffffffffu, idx >= 0 && seg.t0[idx] == 0);
+            const int stop = fm ? (__ffs(fm) - 1) : 31;       // the trajectory's first segment, if it lies in this tile
+            __syncwarp();
+            if (lane == 0) {
+                for (int l = 0; l <= stop; ++l) {
+                    states[l] = s;
+                    s = tile[l * N + s];
+                }
+            }
+            __syncwarp();
+            if (lane <= stop) enter[cur - lane] = states[lane];
+            s = __shfl_sync(0xffffffffu, s, 0);
+            if (fm) break;
+            cur -= 32;
+            __syncwarp();
+        }
     }
 }
 
@@ -205,12 +252,30 @@ int launch_sample_table_philox(const double* alpha, const double* A, unsigned lo
     return BHMM_OK;
 }
 
+// segments from which the tiled link kernel is used: 65536 (16.8 M frames in the batch) unless BHMM_B200_CHASE_TILED says
+// otherwise (the CPU emulation tests force it with 1)
+static int chase_tiled_threshold()
+{
+    static int t = -1;
+    if (t < 0) {
+        const char* e = getenv("BHMM_B200_CHASE_TILED");
+        t = (e && atoi(e) > 0) ? atoi(e) : (1 << 16);
+    }
+    return t;
+}
+
+static void link_segments(const Chains& seg, int N, const unsigned char* seg_map, int* seg_enter, cudaStream_t st)
+{
+    if (seg.n >= chase_tiled_threshold() && N <= 256) k_chase_link_tiled<<<nblk(seg.n, 32), 32, 0, st>>>(seg, N, seg_map, seg_enter);
+    else k_chase_link<<<nblk(seg.n, 128), 128, 0, st>>>(seg, N, seg_map, seg_enter);
+}
+
 int launch_chase(const unsigned char* F, const Chains& seg, int N, unsigned char* seg_map, int* seg_enter, int* path,
                  cudaStream_t st)
 {
     if (seg.n <= 0) return BHMM_OK;
     k_chase_map<<<nblk((long long)seg.n * N, 128), 128, 0, st>>>(F, seg, N, seg_map);
-    k_chase_link<<<nblk(seg.n, 128), 128, 0, st>>>(seg, N, seg_map, seg_enter);
+    link_segments(seg, N, seg_map, seg_enter, st);
     k_chase_path<<<nblk(seg.n, 128), 128, 0, st>>>(F, seg, N, seg_enter, path);
     return BHMM_OK;
 }
@@ -218,7 +283,7 @@ int launch_chase(const unsigned char* F, const Chains& seg, int N, unsigned char
 int launch_chase_link(const Chains& seg, int N, const unsigned char* seg_map, int* seg_enter, cudaStream_t st)
 {
     if (seg.n <= 0) return BHMM_OK;
-    k_chase_link<<<nblk(seg.n, 128), 128, 0, st>>>(seg, N, seg_map, seg_enter);
+    link_segments(seg, N, seg_map, seg_enter, st);
     return BHMM_OK;
 }
 

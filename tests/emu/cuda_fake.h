@@ -29,5 +29,15 @@ inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v)
 inline int atomicMax(int* p, int v) { const int o = *p; if (v > o) *p = v; return o; }
 inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
 inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((unsigned long long)a * b) >> 32); }
+inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+inline int __shfl_sync(unsigned, int v, int src)
+{
+    emu::Warp& w = emu::my_warp();
+    w.si[emu::lane_id()] = v;
+    emu::rendezvous(w.g);
+    const int r = w.si[src & 31];
+    emu::rendezvous(w.g);
+    return r;
+}
 inline void __threadfence_block() {}
 inline void __threadfence() {}

@@ -260,7 +260,8 @@ if __name__ == '__main__':
             run_literal_viterbi_ties()
             continue
         if spec.startswith('l'):
-            chains = run_literal_viterbi(int(spec[1:]))
+            nt = spec[1:].split('x')
+            chains = run_literal_viterbi(int(nt[0]), *(int(x) for x in nt[1:2]))
             if os.environ.get('BHMM_B200_PANEL') in ('1', '2'):
                 check('literal viterbi: the trajectory was cut into chains', chains > 1, str(chains))
             continue

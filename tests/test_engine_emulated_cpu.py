@@ -31,8 +31,10 @@ def engine_emu():
     return so
 
 
-def _drive(mode, specs, trace=False):
+def _drive(mode, specs, trace=False, tiled_chase=False):
     env = dict(os.environ, BHMM_B200_PANEL=str(mode))
+    if tiled_chase:
+        env['BHMM_B200_CHASE_TILED'] = '1'              # the link kernel for batches with very many segments, forced
     if trace:
         env['EMU_TRACE'] = '1'
     r = subprocess.run([sys.executable, os.path.join(EMU, 'engine_emu_driver.py')] + specs, env=env, stdout=subprocess.PIPE,
@@ -67,3 +69,11 @@ def test_wide_kernels_at_n32_and_n100_through_the_engine(engine_emu):
     _drive(2, ['32,40,40', '32,40,2,300', 'v32'])
     r = _drive(1, ['100,40,40'], trace=True)
     assert 'block 416 ' in r.stderr
+
+
+def test_tiled_chase_link_forced(engine_emu):
+    """k_chase_link_tiled (chosen on its own only from 65536 segments, i.e. for C5-sized trajectories) forced for every
+    batch: batched Viterbi and Gibbs paths with several ragged trajectories, and a literal Viterbi over 36 segments (two
+    tiles), in default and panel mode."""
+    _drive(0, ['5,40,40', 'l8x9000'], tiled_chase=True)
+    _drive(1, ['32,40,40', 'l8x9000'], tiled_chase=True)
