@@ -177,6 +177,39 @@ def run_literal_viterbi_ties(N=8, T=4500):
           np.array_equal(path, orc.viterbi(A, pobs, pi)))
 
 
+def run_attached_workspace(N):
+    """The caller lends the workspace (how engine.py runs it: a torch tensor of bhmm_b200_batch_workspace_bytes bytes): the
+    advertised size must cover everything the library carves from it (checked for real under AddressSanitizer)."""
+    orc = Oracle('port')
+    rng = np.random.default_rng(5 * N)
+    X = rng.random((N, N)) + 2.0 * np.eye(N)
+    A = np.ascontiguousarray(X / X.sum(axis=1)[:, None])
+    pi = np.ones(N) / N
+    means, sigmas = np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
+    lengths = [130, 77]
+    obs = []
+    for T in lengths:
+        s = rng.integers(0, N, T)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    cat = np.ascontiguousarray(np.concatenate(obs))
+    lib.bhmm_b200_batch_workspace_bytes.restype = C.c_size_t
+    b = Batch(lengths, N, 30, 40)
+    need = lib.bhmm_b200_batch_workspace_bytes(b.h)
+    ws = np.zeros(need + 256, dtype=np.uint8)
+    base = (ws.ctypes.data + 255) & ~255
+    rc_ok(lib.bhmm_b200_batch_attach_workspace(b.h, C.c_void_p(base), C.c_size_t(need)))
+    stats = np.zeros(lib.bhmm_b200_stats_len_gaussian(N))
+    rc_ok(lib.bhmm_b200_estep_gaussian(b.h, d(cat), d(A), d(pi), d(means), d(sigmas), 1, None, d(stats), None))
+    ref = orc.estep_gaussian(obs, A, pi, means, sigmas)
+    check('attached workspace N=%d (%d bytes): E-step loglik' % (N, need), abs(stats[0] - ref['loglik']) <= 1e-10 * abs(ref['loglik']))
+    path = np.zeros(b.rows, dtype=np.int32)
+    rc_ok(lib.bhmm_b200_viterbi_gaussian(b.h, d(cat), d(A), d(pi), d(means), d(sigmas), 1, path.ctypes.data_as(C.POINTER(C.c_int)), None))
+    ok = all(np.array_equal(path[b.offsets[k]:b.offsets[k + 1]], orc.viterbi(A, orc.gaussian_p_obs(o, means, sigmas), pi))
+             for k, o in enumerate(obs))
+    check('attached workspace N=%d: Viterbi paths' % N, ok)
+    b.close()
+
+
 def run_viterbi_only(N):
     """A Viterbi-only batch has no forward-variable workspace: Viterbi works, the E-step is refused."""
     orc = Oracle('port')
@@ -264,6 +297,9 @@ if __name__ == '__main__':
             chains = run_literal_viterbi(int(nt[0]), *(int(x) for x in nt[1:2]))
             if os.environ.get('BHMM_B200_PANEL') in ('1', '2'):
                 check('literal viterbi: the trajectory was cut into chains', chains > 1, str(chains))
+            continue
+        if spec.startswith('w'):
+            run_attached_workspace(int(spec[1:]))
             continue
         if spec.startswith('v'):
             run_viterbi_only(int(spec[1:]))

@@ -36,6 +36,6 @@ sed -i "s|ROOT = os.path.dirname(os.path.dirname(HERE))|ROOT = '$ROOT'|" "$E/emu
 cd "$E/emu"
 for mode in 0 1 2; do
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 \
-        BHMM_B200_PANEL=$mode BHMM_B200_CHASE_TILED=1 python engine_emu_driver.py 32,40,40 21,40,40 s32 l8 v10 | grep -v " ok " || true
+        BHMM_B200_PANEL=$mode BHMM_B200_CHASE_TILED=1 python engine_emu_driver.py 32,40,40 21,40,40 s32 l8 v10 w32 w40 | grep -v " ok " || true
 done
 echo "engine under ASan: done (no AddressSanitizer report above = clean)"

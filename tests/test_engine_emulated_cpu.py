@@ -66,7 +66,7 @@ def test_panel_family_through_the_engine(engine_emu):
 def test_wide_kernels_at_n32_and_n100_through_the_engine(engine_emu):
     """BHMM_B200_PANEL=2 (N = 32 on the 4-warp wide kernels) and the C4 state count: 13-warp wide kernels + Viterbi with the
     matrix column in registers."""
-    _drive(2, ['32,40,40', '32,40,2,300', 'v32'])
+    _drive(2, ['32,40,40', '32,40,2,300', 'v32', 'w32'])
     r = _drive(1, ['100,40,40'], trace=True)
     assert 'block 416 ' in r.stderr
 
