@@ -527,7 +527,11 @@ static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const do
             x.ch = ch;
             return launch_viterbi_chain(x, emkind, s2);
         }, b->info, st);
-        if (rc == BHMM_OK) chunked_map = true;
+        if (rc == BHMM_OK) {
+            chunked_map = true;
+            // the warm-up length learns from this pass like the forward filter's (estep_common)
+            b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT, b->edge_f);
+        }
         else if (rc != BHMM_ERR_NOT_CERTIFIED) return rc;
         else bhmm_set_error(BHMM_OK, "");
     }
