@@ -135,31 +135,85 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
+def _testsystems():
+    """bhmm_b200/util/testsystems.py loaded BY PATH (numpy only): the reference arm and the cpu_baseline leg draw the
+    same synthetic data as the CUDA arm without importing the bhmm_b200 package (which would map libbhmm_b200.so)."""
+    import importlib.util
+    name = '_bench_testsystems'
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, 'bhmm_b200', 'util', 'testsystems.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules[name] = mod
+    return mod
+
+
+_THREAD_VARS = ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMEXPR_NUM_THREADS')
+
+
+def _single_threaded_blas():
+    """Every CPU worker is ONE core: numpy's BLAS (gamma.T.dot(obs), np.dot in the M-step) must not spawn a thread
+    team per worker (round 1 ran cores x cores threads and under-reported the reference about 50-fold)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=1)
+    except Exception:                                   # pragma: no cover
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def _ref_worker(args):
-    """One host core: the reference's per-trajectory E-step call sequence (maximum_likelihood.py:249-265) through the
-    reference's own C functions, then its two-pass Gaussian M-step (gaussian.py:214-272) on that core's share."""
-    obs_list, A, pi, means, sigmas, kind = args
+    """One host core, one leg of the reference's call sequence through the reference's own C functions:
+    'em'      maximum_likelihood.py:249-265 per trajectory (p_obs, forward, backward, state_probabilities,
+              transition_counts) + the two-pass Gaussian M-step gaussian.py:214-272 on this core's share;
+    'gibbs'   bayesian_sampling.py:325-329 per trajectory (p_obs, forward, sample_path) + the path statistics of
+              generic_hmm.py:297-334,398-431;
+    'viterbi' maximum_likelihood.py:347-349 per trajectory (p_obs, viterbi)."""
+    obs_list, A, pi, means, sigmas, kind, leg = args
     from oracle import oracle as orc
-    o = orc.Oracle(kind)
-    t0 = time.perf_counter()
-    st = o.estep_gaussian(obs_list, A, pi, means, sigmas, ignore_outliers=True)
-    orc.mstep_gaussian(obs_list, st['gammas'])
-    return time.perf_counter() - t0, sum(len(x) for x in obs_list)
+    with _single_threaded_blas():
+        o = orc.Oracle(kind)
+        t0 = time.perf_counter()
+        if leg == 'em':
+            st = o.estep_gaussian(obs_list, A, pi, means, sigmas, ignore_outliers=True)
+            orc.mstep_gaussian(obs_list, st['gammas'])
+        elif leg == 'gibbs':
+            paths = []
+            for k, obs in enumerate(obs_list):
+                pobs = o.gaussian_p_obs(obs, means, sigmas, True)
+                lp, alpha = o.forward(A, pobs, pi)
+                paths.append(o.sample_path(alpha, A, seed=1 + k))
+            o.path_stats(paths, obs_list, A.shape[0])
+        elif leg == 'viterbi':
+            for obs in obs_list:
+                o.viterbi(A, o.gaussian_p_obs(obs, means, sigmas, True), pi)
+        else:
+            raise ValueError(leg)
+        return time.perf_counter() - t0, sum(len(x) for x in obs_list)
 
 
-def cpu_reference_iteration(obs, A, pi, means, sigmas, cores, kind):
-    """One EM iteration over the sample `obs` (list of arrays) spread over `cores` forked workers.
+def cpu_reference_iteration(obs, A, pi, means, sigmas, cores, kind, leg='em'):
+    """One step of `leg` over the sample `obs` (list of arrays) spread over `cores` spawned single-threaded workers.
     Returns (seconds = slowest worker, frames)."""
     import multiprocessing as mp
     shares = [obs[i::cores] for i in range(cores)]
     shares = [s for s in shares if s]
-    jobs = [(s, A, pi, means, sigmas, kind) for s in shares]
-    if len(jobs) == 1:
-        res = [_ref_worker(jobs[0])]
-    else:
-        ctx = mp.get_context('fork')
+    jobs = [(s, A, pi, means, sigmas, kind, leg) for s in shares]
+    # fresh interpreters (spawn) whose numpy/BLAS start with one thread: a forked child of a process that already runs a
+    # BLAS thread team keeps paying for it even under threadpoolctl (measured here: 5.3 M vs 7.8 M frames*iters/s on 8 cores)
+    saved = {k: os.environ.get(k) for k in _THREAD_VARS}
+    os.environ.update({k: '1' for k in _THREAD_VARS})
+    try:
+        ctx = mp.get_context('spawn')
         with ctx.Pool(len(jobs)) as pool:
             res = pool.map(_ref_worker, jobs)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     return max(r[0] for r in res), sum(r[1] for r in res)
 
 
@@ -170,6 +224,16 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return 'unknown'
+
+
 def reference_kind():
     from oracle import oracle as orc
     orc.build(ref=os.path.isdir('/root/reference'))
@@ -177,11 +241,31 @@ def reference_kind():
 
 
 def cpu_sample(N, K, T, seed, cores, per_core):
-    from bhmm_b200.util import testsystems as ts
+    ts = _testsystems()
     ntraj = max(1, min(K, cores * per_core))
     pi, A, means, sigmas, O, S = ts.gaussian_observations(N, ntraj, T, seed=seed)
     pi0, A0, m0, s0 = ts.perturbed_initial_model(A, means, N)
     return [O[k] for k in range(ntraj)], A0, pi0, m0, s0
+
+
+def cpu_baseline_block(N, K, T, cores, per_core, kind, legs=('em', 'gibbs', 'viterbi')):
+    """The reported CPU baseline: (1) ONE core, as shipped -- the reference has no parallelism of its
+    own; (2) all host cores, one spawned single-threaded worker per core over disjoint trajectory subsets.  The headline
+    `value` is the all-cores Baum-Welch figure; the Gibbs and Viterbi legs and the one-core figures ride beside it."""
+    obs, A0, pi0, m0, s0 = cpu_sample(N, K, T, 3, cores, per_core)
+    workers = min(cores, len(obs))
+    out = {'unit': 'frames*iters/s', 'cores': workers, 'kind': kind, 'cpu_model': cpu_model(),
+           'sample': '%d trajectories x %d frames per leg (of %d x %d per GPU): %d spawned single-threaded workers, '
+                     'BLAS capped at 1 thread per worker; the one-core figures time the first %d trajectories'
+                     % (len(obs), T, K, T, workers, min(len(obs), max(1, per_core // 2)))}
+    one = obs[:max(1, per_core // 2)]
+    for leg in legs:
+        t, f = cpu_reference_iteration(obs, A0, pi0, m0, s0, cores, kind, leg)
+        t1, f1 = cpu_reference_iteration(one, A0, pi0, m0, s0, 1, kind, leg)
+        out[leg] = {'all_cores': f / t, 'single_core_as_shipped': f1 / t1, 'per_core_efficiency': (f / t) / workers / (f1 / t1)}
+    out['value'] = out['em']['all_cores']
+    out['single_core_as_shipped'] = out['em']['single_core_as_shipped']
+    return out
 
 
 def run_reference_arm(args):
@@ -201,15 +285,19 @@ def run_reference_arm(args):
         t_tot += t
         frames += f
     value = frames / t_tot
-    sample = '%d trajectories x %d frames per step (of %d x %d per GPU), %d forked workers' % (len(obs), T, K, T, min(cores, len(obs)))
+    workers = min(cores, len(obs))
+    t1, f1 = cpu_reference_iteration(obs[:1], A0, pi0, m0, s0, 1, kind)
+    sample = ('%d trajectories x %d frames per step (of %d x %d per GPU), %d spawned single-threaded workers (BLAS capped '
+              'at 1 thread each)' % (len(obs), T, K, T, workers))
     line = {
         'impl': 'reference', 'metric': 'Baum-Welch EM throughput (frames x iterations per second)', 'value': value,
         'unit': 'frames*iters/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': desc, 'nstates': N, 'sample': sample},
-        'cpu_baseline': {'value': value, 'unit': 'frames*iters/s', 'cores': min(cores, len(obs)), 'kind': kind,
-                         'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'frames*iters/s', 'cores': workers, 'kind': kind,
+                         'sample': sample, 'cpu_model': cpu_model(), 'single_core_as_shipped': f1 / t1,
+                         'per_core_efficiency': value / workers / (f1 / t1)},
         'e2e': {'value': value, 'unit': 'frames*iters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -389,13 +477,7 @@ def run_ours(args):
         # CPU baseline: reference C implementation on the host cores, bounded sample
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = host_cores()
-            kind = reference_kind()
-            cobs, cA, cpi, cm, cs = cpu_sample(N, K, T, 3, cores, args.cpu_traj_per_core)
-            ct, cf = cpu_reference_iteration(cobs, cA, cpi, cm, cs, cores, kind)
-            cpu_baseline = {'value': cf / ct, 'unit': 'frames*iters/s', 'cores': min(cores, len(cobs)), 'kind': kind,
-                            'sample': '%d trajectories x %d frames, one EM iteration (E-step call sequence + '
-                                      'two-pass M-step), %d forked workers' % (len(cobs), T, min(cores, len(cobs)))}
+            cpu_baseline = cpu_baseline_block(N, K, T, host_cores(), args.cpu_traj_per_core, reference_kind())
         line = {
             'metric': 'Baum-Welch EM throughput (frames x iterations per second)',
             'value': value, 'unit': 'frames*iters/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -449,6 +531,7 @@ def main():
     ap.add_argument('--warm', type=int, default=0)
     ap.add_argument('--cpu-traj-per-core', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

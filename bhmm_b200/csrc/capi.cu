@@ -27,6 +27,17 @@ void bhmm_set_error(int code, const char* msg)
     snprintf(t_msg, sizeof(t_msg), "%s", msg ? msg : "");
 }
 
+// RC_TRY: keep the innermost message (e.g. the CUDA error string) and append the call site
+void bhmm_note_error(int code, const char* where)
+{
+    if (t_err == code && t_msg[0]) {
+        const size_t n = strlen(t_msg);
+        if (n + 8 < sizeof(t_msg) && !strstr(t_msg, " <- ")) snprintf(t_msg + n, sizeof(t_msg) - n, " <- %s", where ? where : "");
+        return;
+    }
+    bhmm_set_error(code, where);
+}
+
 static inline void clear_error() { t_err = BHMM_OK; t_msg[0] = 0; }
 
 // ------------------------------------------------------------------------------------------------

@@ -80,3 +80,4 @@ __device__ __forceinline__ double rel_mismatch(double a, double b)
     } while (0)
 
 void bhmm_set_error(int code, const char* msg);
+void bhmm_note_error(int code, const char* where);

@@ -16,7 +16,7 @@ extern double g_cert_tol;
 #define RC_TRY(expr)                        \
     do {                                    \
         int rc_ = (expr);                   \
-        if (rc_ != BHMM_OK) { bhmm_set_error(rc_, #expr); return rc_; } \
+        if (rc_ != BHMM_OK) { bhmm_note_error(rc_, #expr); return rc_; } \
     } while (0)
 
 // Grow-only device buffer carved into aligned pieces.  Either owned (cudaMalloc) or attached (caller memory).

@@ -600,9 +600,11 @@ struct WideGeom {
     static constexpr int NP = 8 * NT;
     static constexpr int KS = 2 * NT;
     static constexpr int NPS = NP + ((4 - NP % 16 + 16) % 16);   // row stride = 4 mod 16 doubles: conflict-free operand loads
-    // one block per SM: 64 K registers / (32 NT threads), in the allocation unit of 8 (ptxas stops at 128 for 13 warps
-    // when it is only given __launch_bounds__)
-    static constexpr int MAXREG = ((65536 / (32 * NT)) / 8 * 8) > 255 ? 255 : ((65536 / (32 * NT)) / 8 * 8);
+    // one block per SM: 64 K registers / (32 threads x warps), where the hardware allocates registers to a block in units of
+    // FOUR warps -- 13 warps cost 16 (first B200 run of the family: __maxnreg__(152) with 416 threads failed to launch,
+    // "too many resources requested"; ptxas itself stops at 128 when it is only given __launch_bounds__(416))
+    static constexpr int WALLOC = (NT + 3) / 4 * 4;
+    static constexpr int MAXREG = ((65536 / (32 * WALLOC)) / 8 * 8) > 255 ? 255 : ((65536 / (32 * WALLOC)) / 8 * 8);
 };
 #ifdef PANEL_HOST_EMU
 #define WIDE_KERNEL_ATTR(NT)
