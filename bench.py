@@ -461,7 +461,7 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
         ab = algorithmic_bytes_per_frame(N)
-        family = 'lane<N=%d,EM_GAUSS>' % N if lane_family else ('panel<EM_GAUSS>' if (os.environ.get('BHMM_B200_PANEL') in ('1', '2') and 17 <= N <= 104) else 'team<EM_GAUSS>')
+        family = 'lane<N=%d,EM_GAUSS>' % N if lane_family else ('panel<EM_GAUSS>' if (os.environ.get('BHMM_B200_PANEL', '1') in ('1', '2') and 17 <= N <= 104) else 'team<EM_GAUSS>')
         dom = 'backward_stats' if kms['backward_stats'] >= kms['forward'] else 'forward'
         dom_ms = kms[dom] / args.steps
         # the dominant kernel also walks the warm-up frames; only the chain's own frames count as algorithmic bytes

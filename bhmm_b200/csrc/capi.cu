@@ -514,7 +514,7 @@ extern "C" int bhmm_b200_viterbi_dev(int* d_path, const double* d_A, const doubl
     const size_t o_chase = cv.add<char>(chase_scratch_bytes(N, T));
     const size_t o_flag = cv.add<int>(4);
     const size_t o_vflag = cv.add<unsigned>(chunked ? (size_t)T : 1);
-    // Opt-in (BHMM_B200_PANEL): a long trajectory is cut into chains whose max-product recursions run in parallel with
+    // Default (BHMM_B200_PANEL=0 turns it off): a long trajectory is cut into chains whose max-product recursions run in parallel with
     // certified hand-overs (panel_kernels.cu:k_viterbi_chain32); the strictly sequential kernel walks it at ~0.5 us per
     // frame, slower than one CPU core.  Any decision too close to call, or an uncertifiable hand-over: sequential kernel.
     LitScratch s;

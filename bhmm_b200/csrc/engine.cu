@@ -511,7 +511,7 @@ static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const do
     if (!b->own_lo.empty()) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "Viterbi needs whole trajectories (batch has owned ranges)"); return BHMM_ERR_UNSUPPORTED; }
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
-    // Opt-in (BHMM_B200_PANEL): trajectories that the plan cuts into chains (one very long trajectory, C5) run their
+    // Default (BHMM_B200_PANEL=0 turns it off): trajectories that the plan cuts into chains (one very long trajectory, C5) run their
     // max-product recursions chain-parallel with certified hand-overs.  A decision whose margin is too small to be
     // certified only matters if the resolved path goes through it: that is checked after the path chase, and then -- or when
     // the hand-overs cannot be certified -- the sequential kernel recomputes the whole map.

@@ -122,7 +122,7 @@ int backward_stats_grid(int N, int n_chains);
 int launch_viterbi_team(const VitArgs& a, int em, cudaStream_t st);
 
 // ---- panel family (panel_kernels.cu): FP64 tensor pipe, 8 chains per warp (N = 32) or per block (32 < N <= 104);
-// opt-in (BHMM_B200_PANEL=1)
+// the default for 17 <= N <= 104 (BHMM_B200_PANEL=0 turns it off)
 bool panel_enabled(int N);
 void panel_shape(int N, int* threads, int* chains_per_row);
 int panel_stats_rows(int N, int n_chains);   // rows of `partials` a statistics launch over n_chains writes

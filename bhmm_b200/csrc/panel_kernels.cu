@@ -1,9 +1,9 @@
 // bhmm_b200/csrc/panel_kernels.cu -- N = 32 chain kernels on the FP64 tensor pipe ("panel" family).
 //
-// STATUS: written at the end of round 1 without GPU time left to run it -- compiled for sm_100a only.  The family is
-// therefore OPT-IN (environment variable BHMM_B200_PANEL=1, read once per process); without it nothing here is launched
-// and N = 32 runs on the team kernels.  tests/test_panel_cuda.py (skipped unless the variable is set) is its parity
-// test; the fragment/index algebra below is checked on the CPU by tests/test_panel_layout_cpu.py.
+// STATUS: the default for 17 <= N <= 104 since round 2 (first B200 runs: parity against the oracle for N = 21, 32, 37, 64, 100,
+// compute-sanitizer memcheck + racecheck clean); BHMM_B200_PANEL=0 (read once per process) falls back to the team kernels,
+// =2 runs N = 32 on the 4-warp wide kernels.  tests/test_panel_cuda.py is the parity test; the fragment/index algebra below
+// is also checked on the CPU by tests/test_panel_layout_cpu.py and tests/emu.
 //
 // One WARP walks 8 chains at once.  The 8 x 32 panel of the chains' vectors times the 32 x 32 transition matrix is
 // 32 mma.sync.m8n8k4.f64 (DMMA) per frame, with the matrix resident in registers as B fragments.  Lane (g, q),
@@ -1376,14 +1376,15 @@ int launch_backward_wide_em(const BwdArgs& a, int NT, cudaStream_t st)
 }  // namespace
 
 #ifndef PANEL_HOST_NO_LAUNCHERS
-// BHMM_B200_PANEL: unset / 0 = off; 1 = N = 32 on the one-warp-per-8-chains kernels, 17 <= N <= 104 otherwise on the wide
+// BHMM_B200_PANEL: 0 = off (team kernels); unset / 1 (the default since the family's first B200 runs in round 2: parity,
+// memcheck and racecheck green, gpurun_out/c2_*.log) = N = 32 on the one-warp-per-8-chains kernels, 17 <= N <= 104 otherwise on the wide
 // kernels; 2 = N = 32 on the wide kernels too (4 warps per 8 chains: a third of the registers, more resident warps)
 static int panel_mode()
 {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("BHMM_B200_PANEL");
-        mode = (e && strcmp(e, "1") == 0) ? 1 : ((e && strcmp(e, "2") == 0) ? 2 : 0);
+        mode = (e && strcmp(e, "0") == 0) ? 0 : ((e && strcmp(e, "2") == 0) ? 2 : 1);
     }
     return mode;
 }

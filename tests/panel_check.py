@@ -16,11 +16,9 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 CHILD = '--team-child' in sys.argv
+TEAM_PARITY = '--team-parity' in sys.argv          # the same parity cases on the team kernels (BHMM_B200_PANEL=0)
 MODE = '2' if '--mode=2' in sys.argv else '1'      # 2: N = 32 on the 4-warp wide kernels instead of the one-warp kernels
-if not CHILD:
-    os.environ['BHMM_B200_PANEL'] = MODE
-else:
-    os.environ.pop('BHMM_B200_PANEL', None)
+os.environ['BHMM_B200_PANEL'] = '0' if (CHILD or TEAM_PARITY) else MODE
 
 import numpy as np   # noqa: E402
 import torch         # noqa: E402
@@ -103,14 +101,16 @@ def parity_wide():
             ok, worst = close(gam.cpu().numpy(), np.vstack(ref['gammas']), 1e-9, 1e-14)
             check(tag + 'gamma rows', ok, 'worst rel %.2e' % worst)
             b.close()
-    # discrete, the C4 model family
-    N, M = 100, 200
+    # discrete, the C4 model family at its own shape ("discrete N=100/M=1000")
+    N, M = 100, 1000
     X = rng.random((N, N)) ** 2 + 1e-3
     A = X / X.sum(axis=1)[:, None]
     pi = np.ones(N) / N
     B = rng.random((N, M)) ** 3 + 1e-4
     B /= B.sum(axis=1)[:, None]
-    sym = [rng.integers(0, M, size=Tk).astype(np.int32) for Tk in (1500, 801, 60)]
+    sym = [rng.integers(0, M, size=Tk).astype(np.int32) for Tk in (1500, 801, 60, 1, 2500)]
+    sym[1][::7] = M - 1                                    # the last symbol column
+    sym[1][3::7] = 0
     b = TrajectoryBatch(sym, N, chunk=200, warm=0)
     stats, Bnum = b.estep_discrete(A, pi, B)
     st = unpack_stats(stats.cpu().numpy(), N)
