@@ -38,7 +38,9 @@ WORKLOADS = {
     'c2': (3, 100, 10000, 'C2-shape: 3-state Gaussian HMM, 100 trajectories x 1e4 frames, Baum-Welch EM'),
     'small': (10, 64, 20000, 'reduced C3 shape for quick checks: 10 states, 64 x 2e4 frames'),
     'n3': (3, 4096, 100000, 'memory-bound regime: 3-state Gaussian HMM (C1/C2 model), 4096 trajectories x 1e5 frames per GPU, Baum-Welch EM'),
-    'n32': (32, 256, 100000, 'C5 model family, batched: 32-state Gaussian HMM, 256 trajectories x 1e5 frames per GPU, Baum-Welch EM (FP64-pipe bound; set BHMM_B200_PANEL=1|2 for the tensor-pipe kernels)'),
+    'c4': (100, 4096, 100000, 'C4: 100-state discrete HMM (1000 symbols), 4096 trajectories x 1e5 frames per GPU, Baum-Welch EM + Viterbi'),
+    'c5': (32, 1, 1000000000, 'C5: ONE trajectory, 32-state Gaussian HMM, time-sharded forward-backward + time-chunked Viterbi'),
+    'n32': (32, 256, 100000, 'C5 model family, batched: 32-state Gaussian HMM, 256 trajectories x 1e5 frames per GPU, Baum-Welch EM (FP64-pipe bound; panel kernels on the FP64 tensor pipe, BHMM_B200_PANEL=0 for the team kernels)'),
 }
 
 
@@ -305,28 +307,442 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------- our arm
+def synth_discrete_gpu(N, M, K, T, seed, device):
+    """C4-style symbol stream on the GPU (setup): metastable-looking state sequence (dwell 50 frames), symbols drawn from the
+    state's own block of M / N symbols; the model is the matching block-structured B with a floor, A diagonally dominant."""
+    import torch
+    rng = np.random.default_rng(seed)
+    X = rng.random((N, N)) + 0.05
+    X += np.eye(N) * N * 0.4
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    w = max(1, M // N)
+    B = np.full((N, M), 0.2 / M)
+    for i in range(N):
+        B[i, w * i:w * i + w] += 0.8 / w
+    B /= B.sum(axis=1)[:, None]
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    rows = K * T
+    st = torch.randint(0, N, (rows // 50 + 1,), generator=g, device=device).repeat_interleave(50)[:rows]
+    sym = (w * st + torch.randint(0, w, (rows,), generator=g, device=device)).clamp_(max=M - 1).to(torch.int32)
+    return pi, A, B, sym
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+FP64_DFMA_TFLOPS = 34.2     # vector DFMA, measured on this pool's B200 with tools/micro/fp64_peak.cu (DESIGN.md 5.4)
+FP64_DMMA_TFLOPS = 37.1     # mma.sync.m8n8k4.f64, same tool; the two do not overlap
+
+
+class Timer(object):
+    """CUDA events on the current stream, bracketed by barrier + synchronize; max over ranks."""
+
+    def __init__(self, dev, world):
+        import torch
+        self.torch, self.dev, self.world = torch, dev, world
+        self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as td
+            td.barrier()
+        self.torch.cuda.synchronize()
+
+    def start(self):
+        self.barrier()
+        self.e0.record()
+
+    def stop(self):
+        self.e1.record()
+        self.barrier()
+        t = self.torch.tensor([self.e0.elapsed_time(self.e1)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as td
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+
 def em_step(batch, model, dist, N):
-    """One Baum-Welch iteration through the public pieces: engine E-step, all-reduce, host M-step."""
-    from bhmm_b200.engine import unpack_stats
-    from bhmm_b200.util import tmatrix
+    """One Baum-Welch iteration through the public pieces: fused E-step, all-reduce of the packed statistics, M-step ON THE
+    GPU (engine.mstep_device), one small device-to-host copy of the updated parameters + log-likelihood."""
+    from bhmm_b200.engine import mstep_device, unpack_mstep
     A, pi, means, sigmas = model
     stats = batch.estep_gaussian(A, pi, means, sigmas)
     stats = dist.allreduce_sum(stats)
+    res = unpack_mstep(mstep_device(stats, N, means_old=means).cpu().numpy(), N)
+    if res['flags']:
+        raise RuntimeError('M-step flagged an empty count or a collapsed sigma (flags=%d)' % res['flags'])
+    return (res['A'], res['pi'], res['means'], res['sigmas']), res['loglik']
+
+
+def em_step_discrete(batch, model, dist, N):
+    from bhmm_b200.engine import mstep_device, mstep_discrete_device, unpack_mstep
+    A, pi, B = model
+    stats, Bnum = batch.estep_discrete(A, pi, B)
+    stats = dist.allreduce_sum(stats)
+    Bnum = dist.allreduce_sum(Bnum)
+    Bdev = mstep_discrete_device(Bnum)
+    res = unpack_mstep(mstep_device(stats, N, means_old=None, mincount=-1.0).cpu().numpy(), N)
+    return (res['A'], res['pi'], Bdev.cpu().numpy()), res['loglik']
+
+
+def base_line(args, world, desc, value, ms, unit='frames*iters/s', metric='Baum-Welch EM throughput (frames x iterations per second)'):
+    return {'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic'}
+
+
+def run_gaussian_em(args, torch, td, dev, world, rank, local):
+    """c1 / c2 / c3 / n3 / n32 / small: Gaussian Baum-Welch (+ the Gibbs half of the metric)."""
+    from bhmm_b200 import _lib, dist
+    from bhmm_b200.engine import TrajectoryBatch
+    from bhmm_b200.util import testsystems as ts
+
+    N, K, T, desc = WORKLOADS[args.workload]
+    if args.trajectories:
+        K = args.trajectories
+    Ktotal = K * world if args.scaling == 'weak' else K
+    if args.scaling == 'strong':
+        K = max(1, K // world)             # BASELINE config 3: 1024 trajectories in total, sharded over the GPUs
+    pi, A, means, sigmas, O = synth_gaussian_gpu(N, K, T, 3 + rank, dev)
+    host_obs = O.cpu().numpy()             # (K, T) host copy: what a user of the public API holds
+    rows = K * T
+    batch = TrajectoryBatch.from_concatenated(O.reshape(-1), [T] * K, N, chunk=args.chunk, warm=args.warm)
+    del O
+    batch.set_profiling(True)
+    lane_family = batch.uses_lane_kernels
+    pi0, A0, m0, s0 = ts.perturbed_initial_model(A, means, N)
+    model = (A0, pi0, m0, s0)
+    tm = Timer(dev, world)
+
+    # ---- device-resident Baum-Welch (the clock sampler starts before the warm-up; only samples under load are summarised)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
+    for _ in range(args.warmup):
+        model, ll = em_step(batch, model, dist, N)
+    tm.barrier()
+    launches0 = _lib.lib.bhmm_b200_launch_count()
+    kms = {'forward': 0.0, 'backward_stats': 0.0}
+    tm.start()
+    for _ in range(args.steps):
+        model, ll = em_step(batch, model, dist, N)
+        k = batch.kernel_ms()
+        kms['forward'] += k['forward']
+        kms['backward_stats'] += k['backward_stats']
+    ms = tm.stop()
+    launches = _lib.lib.bhmm_b200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * rows * args.steps / (ms * 1e-3)
+    info = batch.info()
+    rk = torch.tensor([float(launches), kms['forward'] + kms['backward_stats']], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(rk, op=td.ReduceOp.MAX)
+    max_rank_launches, max_rank_kernel_ms = int(rk[0].item()), float(rk[1].item()) / args.steps
+
+    # ---- Gibbs sweeps (second half of the metric), device resident, through the public sampler: forward + backward
+    # sampling + path statistics on the GPU, all-reduce, read-back, and the HOST parameter draw (SURVEY 8d (ii))
+    from bhmm_b200.estimators import BayesianHMMSampler
+    from bhmm_b200.hmm import HMM
+    from bhmm_b200.output_models import GaussianOutputModel
+    A_, pi_, m_, s_ = model
+    gsteps = max(1, min(args.steps, 10))
+    np.random.seed(11)
+    smp_init = HMM(pi_, A_, GaussianOutputModel(N, means=m_, sigmas=s_))
+    # the sampler runs on the resident batch (batch=: no second upload of the observations)
+    smp = BayesianHMMSampler([host_obs[k] for k in range(K)], N, initial_model=smp_init, reversible=False, shard=False,
+                             batch=batch)
+    smp._update()
+    tm.start()
+    for _ in range(gsteps):
+        smp._update()
+    gms = tm.stop()
+    gibbs_value = world * rows * gsteps / (gms * 1e-3)
+    smp._batch = None
+    del smp
+
+    # ---- end to end through the public estimator: host numpy lists in, fitted model + Viterbi paths out.  The upload of the
+    # observations happens ONCE, inside the timed region, exactly as a user's fit does; 20 EM iterations (SURVEY 8d, C3).
+    from bhmm_b200.estimators import MaximumLikelihoodEstimator
+    e2e_iters = args.e2e_iters
+    batch.close()
+    del batch
+    torch.cuda.empty_cache()
+    host_list = [host_obs[k] for k in range(K)]
+    init = HMM(pi0, A0, GaussianOutputModel(N, means=m0, sigmas=s0))
+    l0 = _lib.lib.bhmm_b200_launch_count()
+    tm.barrier()
+    w0 = time.perf_counter()
+    tm.start()
+    est = MaximumLikelihoodEstimator(host_list, N, initial_model=init, reversible=False, stationary=False, accuracy=-np.inf,
+                                     maxit=e2e_iters, shard=False, chunk=args.chunk, warm=args.warm)
+    fitted = est.fit()
+    e2e_ms = tm.stop()
+    e2e_wall = time.perf_counter() - w0
+    e2e_launches = _lib.lib.bhmm_b200_launch_count() - l0
+    e2e_value = world * rows * e2e_iters / (max(e2e_ms * 1e-3, e2e_wall))
+    e2e_ll = float(est.likelihoods[-1])
+    est._batch.close()
+
+    if rank != 0:
+        return None
+    peak, peak_src = hbm_peak()
+    ab = algorithmic_bytes_per_frame(N)
+    panel = os.environ.get('BHMM_B200_PANEL', '1') in ('1', '2') and 17 <= N <= 104
+    family = 'lane<N=%d,EM_GAUSS>' % N if lane_family else ('panel<EM_GAUSS>' if panel else 'team<EM_GAUSS>')
+    dom = 'backward_stats' if kms['backward_stats'] >= kms['forward'] else 'forward'
+    dom_ms = kms[dom] / args.steps
+    achieved = ab[dom] * rows / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom, {}).get('dram_bytes_per_frame')
+            traffic = traffic * rows if traffic is not None else None
+        except Exception:
+            traffic = None
+    flops = 6 * N * N + 40 * N
+    per_gpu = value / max(world, 1)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_block(N, K, T, host_cores(), args.cpu_traj_per_core, reference_kind())
+    gibbs_bytes = 20 + 16 * N
+    line = base_line(args, world, desc, value, ms)
+    line.update({
+        'config': {'workload': desc, 'nstates': N, 'trajectories_per_gpu': K, 'trajectories_total': K * world,
+                   'frames_per_trajectory': T, 'chunk': info['chunk'], 'warm': info['warm'], 'chains_per_gpu': info['chains'],
+                   'redundant_warmup_frames_frac': info['warm'] * max(0, info['chains'] - K) / float(rows),
+                   'l2': 'inputs larger than L2: %.2f GB observations + %.2f GB forward variables streamed per step'
+                         % (rows * 8 / 1e9, rows * N * 8 / 1e9),
+                   'mstep': 'on the GPU (engine.mstep_device); per step one D2H of %d doubles' % (N * N + 3 * N + 2),
+                   'certification': {'fixups_fwd': info['fixups_fwd'], 'fixups_bwd': info['fixups_bwd'],
+                                     'worst_fwd': info['worst_fwd'], 'worst_bwd': info['worst_bwd'],
+                                     'max_rank_launches': max_rank_launches,
+                                     'max_rank_kernel_ms_per_step': max_rank_kernel_ms}},
+        'roofline': {'bound': 'hbm', 'kernel': ('k_backward_stats_%s' if dom == 'backward_stats' else 'k_forward_%s') % family,
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': traffic, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_frame': ab[dom], 'kernel_ms': dom_ms,
+                     'all_kernels_ms': {k2: v / args.steps for k2, v in kms.items()},
+                     'iteration_frac': (ab['iteration'] * per_gpu / 1e9) / peak,
+                     # companion FP64 roofline (DESIGN.md 5.4): algorithmic flops 6N^2+40N per frame and iteration
+                     # (SURVEY.md 8d) against the vector-DFMA peak measured with tools/micro/fp64_peak.cu
+                     'fp64': {'flops_per_frame': flops, 'achieved_tflops': flops * per_gpu / 1e12,
+                              'peak_tflops': FP64_DFMA_TFLOPS, 'frac': flops * per_gpu / (FP64_DFMA_TFLOPS * 1e12)}},
+        'cpu_baseline': cpu_baseline,
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'frames*iters/s', 'h2d_bytes_per_step': rows * 8 // e2e_iters,
+                'd2h_bytes_per_step': (rows * 4) // e2e_iters + 8 * (N * N + 3 * N + 2), 'steps': e2e_iters,
+                'seconds': max(e2e_ms * 1e-3, e2e_wall), 'gpu_launches': int(e2e_launches), 'loglik': e2e_ll,
+                'device_msteps': int(est.device_msteps),
+                'note': 'MaximumLikelihoodEstimator(list of host numpy arrays).fit() with maxit=%d: ONE upload of the '
+                        'observations (pageable host memory, %d bytes) inside the timed region, %d EM iterations, then the '
+                        'Viterbi paths of all trajectories copied back (%d bytes) as fit() does (maximum_likelihood.py:439)'
+                        % (e2e_iters, rows * 8, e2e_iters, rows * 4)},
+        'gpu_launches': int(launches),
+        'gibbs': {'value': gibbs_value, 'unit': 'frames*sweeps/s', 'steps': gsteps, 'ms_per_step': gms / gsteps,
+                  'roofline_frac': (gibbs_bytes * gibbs_value / max(world, 1) / 1e9) / peak,
+                  'algorithmic_bytes_per_frame': gibbs_bytes,
+                  'note': 'BayesianHMMSampler._update(): forward + time-parallel backward sampling + path statistics on the '
+                          'GPU (Philox uniforms), all-reduce, read-back, HOST parameter draw (non-reversible Dirichlet rows)'},
+        'loglik': ll,
+    })
+    if cpu_baseline is not None:
+        line['gibbs']['cpu_all_cores'] = cpu_baseline['gibbs']['all_cores']
+    return line
+
+
+def run_c4(args, torch, td, dev, world, rank, local):
+    """C4: 100-state discrete HMM, 1000 symbols, 4096 trajectories x 1e5 frames (total; weak: per GPU), EM + Viterbi.  The
+    forward variables (80 MB per trajectory) exceed one GPU: groups of trajectories share one workspace (engine.make_batch)."""
+    from bhmm_b200 import _lib, dist
+    from bhmm_b200.engine import SubBatchedTrajectories, TrajectoryBatch
+    N, M = 100, 1000
+    _, K, T, desc = WORKLOADS['c4']
+    if args.trajectories:
+        K = args.trajectories
+    if args.scaling == 'strong':
+        K = max(1, K // world)
+    pi, A, B, sym = synth_discrete_gpu(N, M, K, T, 4 + rank, dev)
+    rows = K * T
+    free = torch.cuda.mem_get_info()[0]
+    batch = SubBatchedTrajectories.from_concatenated(sym, [T] * K, N, int(min(args.budget_gb * 1e9, 0.85 * free)), device=dev)
+    batch.set_profiling(True)
+    model = (A, pi, B)
+    tm = Timer(dev, world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
+    for _ in range(args.warmup):
+        model, ll = em_step_discrete(batch, model, dist, N)
+    launches0 = _lib.lib.bhmm_b200_launch_count()
+    kms = {'forward': 0.0, 'backward_stats': 0.0}
+    tm.start()
+    for _ in range(args.steps):
+        model, ll = em_step_discrete(batch, model, dist, N)
+        k = batch.kernel_ms()
+        kms['forward'] += k['forward']
+        kms['backward_stats'] += k['backward_stats']
+    ms = tm.stop()
+    launches = _lib.lib.bhmm_b200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * rows * args.steps / (ms * 1e-3)
+    A_, pi_, B_ = model
+    batch.viterbi_discrete(A_, pi_, B_)
+    tm.start()
+    path = batch.viterbi_discrete(A_, pi_, B_)
+    vms = tm.stop()
+    info = batch.info()
+    if rank != 0:
+        return None
+    per_gpu = value / world
+    flops = 6 * N * N + 40 * N
+    dom = 'backward_stats' if kms['backward_stats'] >= kms['forward'] else 'forward'
+    dom_ms = kms[dom] / args.steps
+    dom_flops = (4 * N * N if dom == 'backward_stats' else 2 * N * N) * rows      # DMMA work of that kernel per launch
+    peak, peak_src = hbm_peak()
+    line = base_line(args, world, desc, value, ms)
+    line.update({
+        'config': {'workload': desc, 'nstates': N, 'nsymbols': M, 'trajectories_per_gpu': K, 'frames_per_trajectory': T,
+                   'groups': info.get('groups'), 'chains_per_gpu': info['chains'], 'chunk': info['chunk'], 'warm': info['warm'],
+                   'l2': 'inputs larger than L2: %.1f GB of forward variables streamed per step' % (rows * N * 8 / 1e9)},
+        'roofline': {'bound': 'tensor', 'kernel': 'k_%s_wide<EM_DISC,13> (mma.sync.m8n8k4.f64)' % ('backward_stats' if dom == 'backward_stats' else 'forward'),
+                     'achieved': dom_flops / (dom_ms * 1e-3) / 1e12, 'peak': FP64_DMMA_TFLOPS, 'unit': 'TFLOP/s',
+                     'frac': dom_flops / (dom_ms * 1e-3) / 1e12 / FP64_DMMA_TFLOPS, 'traffic': None,
+                     'peak_source': 'FP64 DMMA peak measured with tools/micro/fp64_peak.cu on this pool (MEASURED_PEAKS.json has no FP64 figure)',
+                     'kernel_ms': dom_ms, 'all_kernels_ms': {k2: v / args.steps for k2, v in kms.items()},
+                     'iteration_frac_fp64': flops * per_gpu / (FP64_DMMA_TFLOPS * 1e12),
+                     'iteration_frac_hbm': ((8 + 16 * N) * per_gpu / 1e9) / peak},
+        'cpu_baseline': None, 'clocks': clocks,
+        'e2e': {'value': None, 'unit': 'frames*iters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                'note': 'not measured for this workload (see the c3 line)'},
+        'gpu_launches': int(launches),
+        'viterbi': {'ms': vms, 'frames_per_s': world * rows / (vms * 1e-3), 'path_checksum': int(path.to(torch.int64).sum().item())},
+        'loglik': ll,
+    })
+    return line
+
+
+def run_c5(args, torch, td, dev, world, rank, local):
+    """C5: ONE trajectory, 32 states, cut in TIME over the GPUs (engine.TimeShardedTrajectories): forward-backward statistics
+    of the whole trajectory, then (one GPU holds the 1e9 observations: 8 GB) the time-chunked Viterbi path."""
+    from bhmm_b200 import _lib
+    from bhmm_b200.engine import TimeShardedTrajectories, TrajectoryBatch, unpack_stats
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import c5_time_sharded as c5
+    N = 32
+    T = int(args.frames) if args.frames else int(1e9 if world >= 4 else 2.5e8 * world)
+    desc = WORKLOADS['c5'][3] + ' (%d frames on %d GPU%s)' % (T, world, 's' if world > 1 else '')
+    rng = np.random.default_rng(7)
+    X = rng.random((N, N)) + 0.2
+    X += np.eye(N) * N * 0.5
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    means, sigmas = np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
+    halo = 8 * max(128, 48 * N)
+    lo, hi = (T * rank) // world, (T * (rank + 1)) // world
+    a, b = max(0, lo - halo), min(T, hi + halo)
+    x = c5.frames(a, b, means, sigmas, dev)
+    batch = TrajectoryBatch.from_concatenated(x, [b - a], N, device=dev, own_ranges=[(lo - a, hi - a)])
+    batch.set_profiling(True)
+    tm = Timer(dev, world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
+
+    def step():
+        stats = batch.estep_gaussian(A, pi, means, sigmas).clone()
+        borders = torch.from_numpy(batch.border_handovers(0)).to(dev)
+        if world > 1:
+            td.all_reduce(stats, op=td.ReduceOp.SUM)
+            gathered = [torch.empty_like(borders) for _ in range(world)]
+            td.all_gather(gathered, borders)
+        else:
+            gathered = [borders]
+        ranges = [[((T * r) // world, (T * (r + 1)) // world, T)] for r in range(world)]
+        worst = TimeShardedTrajectories.certify([g.cpu().numpy()[None] for g in gathered], ranges, 1e-11)
+        return stats, worst
+    for _ in range(args.warmup):
+        step()
+    launches0 = _lib.lib.bhmm_b200_launch_count()
+    kms = {'forward': 0.0, 'backward_stats': 0.0}
+    tm.start()
+    for _ in range(args.steps):
+        stats, worst = step()
+        k = batch.kernel_ms()
+        kms['forward'] += k['forward']
+        kms['backward_stats'] += k['backward_stats']
+    ms = tm.stop()
+    launches = _lib.lib.bhmm_b200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
     st = unpack_stats(stats.cpu().numpy(), N)
-    A = tmatrix.estimate_P(st['C'], reversible=False, mincount_connectivity=1e-16)
-    pi = st['gamma0'] / st['gamma0'].sum()
-    shift = st['wd'] / st['wsum']
-    means = means + shift
-    sigmas = np.sqrt(np.maximum(st['wdd'] / st['wsum'] - shift * shift, 1e-300))
-    return (A, pi, means, sigmas), st['loglik']
+    info = batch.info()
+    batch.close()
+    del batch, x
+    torch.cuda.empty_cache()
+    vit = None
+    if rank == 0:
+        # Viterbi of the WHOLE trajectory on one GPU (observations 8 T bytes, back-pointer map T N bytes)
+        Tv = T if T * (8 + N + 8) < 0.8 * torch.cuda.mem_get_info()[0] else int(0.8 * torch.cuda.mem_get_info()[0] / (16 + N))
+        xv = c5.frames(0, Tv, means, sigmas, dev)
+        vb = TrajectoryBatch.from_concatenated(xv, [Tv], N, device=dev, viterbi_only=True)
+        vb.viterbi_gaussian(A, pi, means, sigmas)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        path = vb.viterbi_gaussian(A, pi, means, sigmas)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        vit = {'frames': Tv, 'seconds': dt, 'frames_per_s': Tv / dt, 'path_checksum': int(path.to(torch.int64).sum().item()),
+               'info': vb.info()}
+        vb.close()
+    if world > 1:
+        td.barrier()
+    if rank != 0:
+        return None
+    value = T * args.steps / (ms * 1e-3)
+    per_gpu = value / world
+    flops = 6 * N * N + 40 * N
+    dom = 'backward_stats' if kms['backward_stats'] >= kms['forward'] else 'forward'
+    dom_ms = kms[dom] / args.steps
+    own = hi - lo
+    dom_flops = (4 * N * N if dom == 'backward_stats' else 2 * N * N) * own
+    peak, peak_src = hbm_peak()
+    line = base_line(args, world, desc, value, ms, metric='forward-backward throughput of one long trajectory (frames x iterations per second)')
+    line['scaling'] = 'strong'
+    line.update({
+        'config': {'workload': desc, 'nstates': N, 'frames': T, 'frames_per_gpu': own, 'halo': halo, 'chains_per_gpu': info['chains'],
+                   'chunk': info['chunk'], 'warm': info['warm'], 'worst_border_mismatch': worst,
+                   'certification': {'fixups_fwd': info['fixups_fwd'], 'fixups_bwd': info['fixups_bwd'],
+                                     'worst_fwd': info['worst_fwd'], 'worst_bwd': info['worst_bwd']},
+                   'transitions_counted': float(st['C'].sum()),
+                   'l2': 'inputs larger than L2: %.1f GB of forward variables per GPU and step' % (own * N * 8 / 1e9)},
+        'roofline': {'bound': 'tensor', 'kernel': 'k_%s_panel32<EM_GAUSS> (mma.sync.m8n8k4.f64)' % dom,
+                     'achieved': dom_flops / (dom_ms * 1e-3) / 1e12, 'peak': FP64_DMMA_TFLOPS, 'unit': 'TFLOP/s',
+                     'frac': dom_flops / (dom_ms * 1e-3) / 1e12 / FP64_DMMA_TFLOPS, 'traffic': None,
+                     'peak_source': 'FP64 DMMA peak measured with tools/micro/fp64_peak.cu on this pool (MEASURED_PEAKS.json has no FP64 figure)',
+                     'kernel_ms': dom_ms, 'all_kernels_ms': {k2: v / args.steps for k2, v in kms.items()},
+                     'iteration_frac_fp64': flops * per_gpu / (FP64_DMMA_TFLOPS * 1e12),
+                     'iteration_frac_hbm': ((16 + 16 * N) * per_gpu / 1e9) / peak},
+        'cpu_baseline': None, 'clocks': clocks,
+        'e2e': {'value': None, 'unit': 'frames*iters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                'note': 'not measured for this workload (see the c3 line)'},
+        'gpu_launches': int(launches), 'viterbi': vit, 'loglik': st['loglik'],
+    })
+    return line
 
 
 def run_ours(args):
     import torch
     import torch.distributed as td
-    from bhmm_b200 import _lib, dist
-    from bhmm_b200.engine import TrajectoryBatch
-    from bhmm_b200.util import testsystems as ts
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -337,184 +753,10 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         td.init_process_group('nccl', device_id=dev)
-
-    N, K, T, desc = WORKLOADS[args.workload]
-    if args.trajectories:
-        K = args.trajectories
-    pi, A, means, sigmas, O = synth_gaussian_gpu(N, K, T, 3 + rank, dev)
-    host_obs = torch.empty((K * T,), dtype=torch.float64, pin_memory=True)
-    host_obs.copy_(O.reshape(-1))
-    rows = K * T
-
-    batch = TrajectoryBatch.from_concatenated(O.reshape(-1), [T] * K, N, chunk=args.chunk, warm=args.warm)
-    del O
-    batch.set_profiling(True)
-    lane_family = batch.uses_lane_kernels
-    pi0, A0, m0, s0 = ts.perturbed_initial_model(A, means, N)
-    model = (A0, pi0, m0, s0)
-
-    def barrier():
-        if world > 1:
-            td.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident measurement (the clock sampler starts before the warm-up so that nvidia-smi is up and
-    # sampling every 100 ms by the time the timed region runs; only samples under load are summarised)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.5)
-    for _ in range(args.warmup):
-        model, ll = em_step(batch, model, dist, N)
-    barrier()
-    launches0 = _lib.lib.bhmm_b200_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = {'forward': 0.0, 'backward_stats': 0.0}
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        model, ll = em_step(batch, model, dist, N)
-        k = batch.kernel_ms()
-        kms['forward'] += k['forward']
-        kms['backward_stats'] += k['backward_stats']
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.lib.bhmm_b200_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * rows * args.steps / (ms * 1e-3)
-    info = batch.info()
-    # what the slowest rank looked like: launches of the timed region (fix-up sweeps and redone passes show up here) and
-    # kernel time, maximum over ranks
-    rk = torch.tensor([float(launches), kms['forward'] + kms['backward_stats']], dtype=torch.float64, device=dev)
-    if world > 1:
-        td.all_reduce(rk, op=td.ReduceOp.MAX)
-    max_rank_launches, max_rank_kernel_ms = int(rk[0].item()), float(rk[1].item()) / args.steps
-
-    # ---- end-to-end: observations start in pinned host memory every step.  Every step's inputs are copied host ->
-    # device inside the timed region and its statistics are read back; the copy of step k+1 runs on a second stream
-    # while step k computes (double-buffered device input), as a serving loop would do it.
-    e2e_steps = max(1, min(args.steps, 5))
-    obs_a = batch.obs
-    obs_b = torch.empty_like(obs_a)
-    copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    bufs = [obs_a, obs_b]
-    barrier()
-    e0.record()
-    with torch.cuda.stream(copy_stream):
-        bufs[0].copy_(host_obs, non_blocking=True)
-        ready[0].record(copy_stream)
-    for k in range(e2e_steps):
-        if k + 1 < e2e_steps:
-            with torch.cuda.stream(copy_stream):
-                bufs[(k + 1) & 1].copy_(host_obs, non_blocking=True)
-                ready[(k + 1) & 1].record(copy_stream)
-        torch.cuda.current_stream(dev).wait_event(ready[k & 1])
-        batch.obs = bufs[k & 1]
-        model, ll = em_step(batch, model, dist, N)
-    e1.record()
-    barrier()
-    batch.obs = obs_a
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    e2e_value = world * rows * e2e_steps / (float(t.item()) * 1e-3)
-    # the same without overlap (copy, then compute), for reference
-    barrier()
-    e0.record()
-    for _ in range(e2e_steps):
-        batch.set_observations(host_obs, non_blocking=True)
-        model, ll = em_step(batch, model, dist, N)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    e2e_serial = world * rows * e2e_steps / (float(t.item()) * 1e-3)
-    stats_bytes = 8 * (1 + N + N * N + 3 * N)
-
-    # ---- Gibbs sweep (second half of the metric), device resident
-    gsteps = max(1, min(args.steps, 5))
-    A_, pi_, m_, s_ = model
-    batch.gibbs_gaussian(A_, pi_, m_, s_, seed=1, sweep=0)
-    barrier()
-    e0.record()
-    for sidx in range(gsteps):
-        path, counts, sums, gll = batch.gibbs_gaussian(A_, pi_, m_, s_, seed=1, sweep=1 + sidx)
-        c = dist.allreduce_sum(counts.clone()).cpu()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    gibbs_value = world * rows * gsteps / (float(t.item()) * 1e-3)
-
-    if rank == 0:
-        peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
-        else:
-            peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-        ab = algorithmic_bytes_per_frame(N)
-        family = 'lane<N=%d,EM_GAUSS>' % N if lane_family else ('panel<EM_GAUSS>' if (os.environ.get('BHMM_B200_PANEL', '1') in ('1', '2') and 17 <= N <= 104) else 'team<EM_GAUSS>')
-        dom = 'backward_stats' if kms['backward_stats'] >= kms['forward'] else 'forward'
-        dom_ms = kms[dom] / args.steps
-        # the dominant kernel also walks the warm-up frames; only the chain's own frames count as algorithmic bytes
-        achieved = ab[dom] * rows / (dom_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(dom, {}).get('dram_bytes_per_frame')
-                traffic = traffic * rows if traffic is not None else None
-            except Exception:
-                traffic = None
-        # CPU baseline: reference C implementation on the host cores, bounded sample
-        cpu_baseline = None
-        if world == 1 and not args.no_cpu_baseline:
-            cpu_baseline = cpu_baseline_block(N, K, T, host_cores(), args.cpu_traj_per_core, reference_kind())
-        line = {
-            'metric': 'Baum-Welch EM throughput (frames x iterations per second)',
-            'value': value, 'unit': 'frames*iters/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': desc, 'nstates': N, 'trajectories_per_gpu': K, 'frames_per_trajectory': T,
-                       'chunk': info['chunk'], 'warm': info['warm'], 'chains_per_gpu': info['chains'],
-                       'l2': 'inputs larger than L2: %.1f GB observations + %.1f GB forward variables streamed per step'
-                             % (rows * 8 / 1e9, rows * N * 8 / 1e9),
-                       'certification': {'fixups_fwd': info['fixups_fwd'], 'fixups_bwd': info['fixups_bwd'],
-                                         'worst_fwd': info['worst_fwd'], 'worst_bwd': info['worst_bwd'],
-                                         'max_rank_launches': max_rank_launches,
-                                         'max_rank_kernel_ms_per_step': max_rank_kernel_ms}},
-            'roofline': {'bound': 'hbm', 'kernel': ('k_backward_stats_%s' if dom == 'backward_stats' else 'k_forward_%s') % family,
-                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'peak_source': peak_src,
-                         'algorithmic_bytes_per_frame': ab[dom], 'kernel_ms': dom_ms,
-                         'all_kernels_ms': {k2: v / args.steps for k2, v in kms.items()},
-                         'iteration_frac': (ab['iteration'] * rows / (ms / args.steps * 1e-3) / 1e9) / peak,
-                         # companion FP64 roofline: algorithmic flops 6N^2+40N per frame and iteration
-                         #  against the vector-DFMA peak measured with tools/micro/fp64_peak.cu
-                         'fp64': {'flops_per_frame': 6 * N * N + 40 * N,
-                                  'achieved_tflops': (6 * N * N + 40 * N) * value / max(world, 1) / 1e12,
-                                  'peak_tflops': 34.2, 'frac': (6 * N * N + 40 * N) * value / max(world, 1) / 34.2e12}},
-            'cpu_baseline': cpu_baseline,
-            'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': 'frames*iters/s', 'h2d_bytes_per_step': rows * 8,
-                    'd2h_bytes_per_step': stats_bytes, 'steps': e2e_steps,
-                    'note': 'input copy of step k+1 overlaps the compute of step k (double-buffered device input)',
-                    'value_without_overlap': e2e_serial},
-            'gpu_launches': int(launches),
-            'gibbs': {'value': gibbs_value, 'unit': 'frames*sweeps/s', 'steps': gsteps,
-                      'note': 'forward + time-parallel backward sampling + path statistics, Philox uniforms'},
-            'loglik': ll,
-        }
+    runner = {'c4': run_c4, 'c5': run_c5}.get(args.workload, run_gaussian_em)
+    line = runner(args, torch, td, dev, world, rank, local)
+    if rank == 0 and line is not None:
         print(json.dumps(line))
-    batch.close()
     if world > 1:
         td.destroy_process_group()
 
@@ -531,7 +773,11 @@ def main():
     ap.add_argument('--warm', type=int, default=0)
     ap.add_argument('--cpu-traj-per-core', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: the workload\'s trajectories PER GPU; strong: in total (BASELINE config 3: 1024 over 8 GPUs)')
+    ap.add_argument('--e2e-iters', type=int, default=20, help='EM iterations of the end-to-end fit (SURVEY 8d: 20 for C3)')
+    ap.add_argument('--frames', type=float, default=0, help='c5: frames of the trajectory')
+    ap.add_argument('--budget-gb', type=float, default=140.0, help='c4: workspace budget per GPU')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

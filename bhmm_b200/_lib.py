@@ -81,6 +81,7 @@ _proto('bhmm_b200_adapt_warm', C.c_int, C.c_int, C.c_double, C.c_double, C.c_int
 _proto('bhmm_b200_batch_destroy', None, _vp)
 _proto('bhmm_b200_batch_replan', C.c_int, _vp, C.c_int, C.c_int)
 _proto('bhmm_b200_batch_uses_lane_kernels', C.c_int, _vp)
+_proto('bhmm_b200_wave_chains', C.c_int, C.c_int)
 _proto('bhmm_b200_batch_set_viterbi_only', C.c_int, _vp, C.c_int)
 _proto('bhmm_b200_batch_workspace_bytes', C.c_size_t, _vp)
 _proto('bhmm_b200_batch_attach_workspace', C.c_int, _vp, _vp, C.c_size_t)
@@ -97,6 +98,8 @@ _proto('bhmm_b200_gibbs_gaussian', C.c_int, _vp, _vp, _dp, _dp, _dp, _dp, C.c_in
        C.c_ulonglong, _vp, _vp, _vp, _dp, _vp)
 _proto('bhmm_b200_gibbs_discrete', C.c_int, _vp, _vp, _dp, _dp, _dp, C.c_int, C.c_int, _vp, C.c_ulonglong,
        C.c_ulonglong, _vp, _vp, _dp, _vp)
+_proto('bhmm_b200_mstep_dev', C.c_int, _vp, _vp, C.c_int, C.c_double, _vp, _vp)
+_proto('bhmm_b200_mstep_discrete_dev', C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp)
 _proto('bhmm_b200_path_symbol_histogram', C.c_int, _vp, _vp, C.c_longlong, C.c_int, C.c_int, _vp, _vp)
 
 #: every symbol include/bhmm_b200.h declares (tests check that the library exports all of them)

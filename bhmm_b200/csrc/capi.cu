@@ -901,3 +901,29 @@ extern "C" void bhmm_b200_discrete_update_pout(const int* obs, const double* wei
     if (finish(nullptr)) return;
     if (d2h(pout, s.ptr<double>(kp), nm)) bhmm_set_error(BHMM_ERR_CUDA, "D2H copy failed");
 }
+
+// ------------------------------------------------------------------------------------------------
+// M-step on the device: the reduced statistics never leave the GPU except as the updated parameters.
+// ------------------------------------------------------------------------------------------------
+extern "C" int bhmm_b200_mstep_dev(const double* d_stats, const double* d_means_old, int N, double mincount, double* d_out,
+                                   void* stream)
+{
+    clear_error();
+    if (!d_stats || !d_out || N < 1) { bhmm_set_error(BHMM_ERR_INVALID, "mstep: null pointer or N < 1"); return BHMM_ERR_INVALID; }
+    RC_TRY(require_device());
+    RC_TRY(launch_mstep_hmm(d_stats, d_means_old, N, d_means_old != nullptr, mincount, d_out, (cudaStream_t)stream));
+    LAUNCHED(1);
+    CUDA_TRY(cudaGetLastError());
+    return BHMM_OK;
+}
+
+extern "C" int bhmm_b200_mstep_discrete_dev(const double* d_Bnum, int N, int M, double* d_B, double* d_Bt, void* stream)
+{
+    clear_error();
+    if (!d_Bnum || !d_B || N < 1 || M < 1) { bhmm_set_error(BHMM_ERR_INVALID, "mstep_discrete: null pointer or empty shape"); return BHMM_ERR_INVALID; }
+    RC_TRY(require_device());
+    RC_TRY(launch_mstep_rows(d_Bnum, N, M, d_B, d_Bt, (cudaStream_t)stream));
+    LAUNCHED(1);
+    CUDA_TRY(cudaGetLastError());
+    return BHMM_OK;
+}

@@ -135,14 +135,40 @@ void batch_plan(bhmm_b200_batch* b, int chunk, int warm)
         team_shape(b->N, &tthreads, &tcpb);
         const long long cap = b->lane ? (long long)sms * lane_blocks_per_sm(b->N, EM_GAUSS) * lane_threads()
                                       : (long long)backward_stats_grid(b->N, 1 << 28) * tcpb;
-        for (int it = 0; it < 200; ++it) {
+        auto count = [&](long long c) {
             long long n = 0;
             for (int k = 0; k < b->K; ++k) {
                 const long long own = b->own_lo.empty() ? b->offsets[k + 1] - b->offsets[k] : b->own_hi[k] - b->own_lo[k];
-                n += (own + b->chunk - 1) / b->chunk;
+                n += (own + c - 1) / c;
             }
-            if (n <= cap || b->chunk >= (1 << 30)) break;
-            b->chunk = (int)std::min<long long>((long long)b->chunk + std::max(1, b->chunk / 100), 1 << 30);
+            return n;
+        };
+        if (b->lane) {
+            for (int it = 0; it < 200; ++it) {
+                if (count(b->chunk) <= cap || b->chunk >= (1 << 30)) break;
+                b->chunk = (int)std::min<long long>((long long)b->chunk + std::max(1, b->chunk / 100), 1 << 30);
+            }
+        } else {
+            // Persistent blocks walk their chain groups in rounds, and a round that is mostly empty costs as much as a full
+            // one (C4 on one GPU, first B200 run of the wide kernels: groups of 1365 whole trajectories on a wave of 1184
+            // chains took two rounds, 42 % of the machine idle).  Choose the number of rounds m and the chunk together:
+            // the smallest chunk c with at most m x wave chains, cost m x (c + warm-up), cheapest m wins.
+            long long maxT = 1;
+            for (int k = 0; k < b->K; ++k) maxT = std::max(maxT, b->offsets[k + 1] - b->offsets[k]);
+            const long long lo_c = std::max<long long>(64, 2LL * w);
+            double best_cost = 1e300;
+            long long best_c = std::max<long long>(maxT, 1);
+            for (int m = 1; m <= 32; ++m) {
+                if (count(maxT) > (long long)m * cap) continue;            // even whole trajectories do not fit m rounds
+                long long lo = std::min(lo_c, maxT), hi = maxT;          // smallest c in [lo, hi] with count(c) <= m cap
+                while (lo < hi) {
+                    const long long mid = (lo + hi) / 2;
+                    if (count(mid) <= (long long)m * cap) hi = mid; else lo = mid + 1;
+                }
+                const double cost = (double)m * ((double)lo + (lo < maxT ? (double)w : 0.0));
+                if (cost < best_cost * 0.98) { best_cost = cost; best_c = lo; }   // more rounds only for a real gain
+            }
+            b->chunk = (int)std::min<long long>(best_c, 1 << 30);
         }
     }
     b->warm_f = b->warm_b = w;
@@ -423,6 +449,22 @@ extern "C" int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm)
 }
 
 extern "C" int bhmm_b200_batch_uses_lane_kernels(const bhmm_b200_batch* b) { return b && b->lane ? 1 : 0; }
+
+extern "C" int bhmm_b200_wave_chains(int N)
+{
+    if (N < 1 || N > 1024) return 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return 0; }
+    const char* fam = getenv("BHMM_B200_FAMILY");
+    if (lane_supported(N, EM_GAUSS) && !(fam && strcmp(fam, "team") == 0)) {
+        int sms = 148, dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return sms * lane_blocks_per_sm(N, EM_GAUSS) * lane_threads();
+    }
+    int tthreads = 32, tcpb = 1;
+    team_shape(N, &tthreads, &tcpb);
+    return backward_stats_grid(N, 1 << 28) * tcpb;
+}
 
 extern "C" int bhmm_b200_batch_set_viterbi_only(bhmm_b200_batch* b, int on)
 {

@@ -8,6 +8,10 @@
 //   k_colsum_*                          state_counts, hidden/api.py:191-211
 //   k_xi_norm / k_xi_accumulate         _compute_transition_counts, _hidden.c:148-183
 //   k_update_pout                       _update_pout, output_models/impl_c/_discrete.c:1-32
+//   k_mstep_hmm / k_mstep_rows          the M-step from the reduced statistics, on the device:
+//                                       maximum_likelihood.py:284-330 with estimate_P -> C / rowsum
+//                                       (_tmatrix_disconnected.py:110-115, non-reversible), GaussianOutputModel.estimate
+//                                       gaussian.py:214-272, DiscreteOutputModel.estimate discrete.py:214-215
 #include "common.cuh"
 #include "kernels.h"
 
@@ -171,6 +175,77 @@ __global__ void k_transpose(const double* __restrict__ in, int R, int Cc, double
     out[(long long)c * R + r] = in[k];
 }
 
+// M-step from the packed (all-reduced) E-step statistics [loglik | gamma0 (N) | C (N*N) | sum gamma | sum gamma d | sum gamma d^2]
+// (d = o - mu_old).  Thread i owns row i: A[i,:] = C[i,:] / sum_j C[i,j] with the row sum taken left to right like numpy's
+// C.sum(axis=1) on a short row; pi = gamma0 / sum gamma0 (maximum_likelihood.py:318-320); with `gauss`: mu = mu_old + wd / w,
+// sigma = sqrt(wdd / w - (wd / w)^2), which equals the reference's two-pass estimate about the NEW mean (gaussian.py:244-270).
+// out = [A (N*N) | pi (N) | mu (N) | sigma (N) | flags (1) | loglik (1)]; flags (a double holding small integers) counts what the host
+// must look at: +1 per count C[i,j] <= mincount (the general-connectivity estimator applies, _tmatrix_disconnected.py:68-123),
+// +1024 per sigma below machine epsilon or NaN (gaussian.py:271-272 raises).
+__global__ void k_mstep_hmm(const double* __restrict__ stats, const double* __restrict__ mu_old, int N, int gauss,
+                            double mincount, double* __restrict__ out)
+{
+    __shared__ double g0sum;
+    __shared__ int flags;
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int j = 0; j < N; ++j) s += stats[1 + j];
+        g0sum = s;
+        flags = 0;
+    }
+    __syncthreads();
+    const double* Cm = stats + 1 + N;
+    double* A = out;
+    double* pi = out + (long long)N * N;
+    double* mu = pi + N;
+    double* sg = mu + N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double rs = 0.0;
+        int low = 0;
+        for (int j = 0; j < N; ++j) {
+            const double c = Cm[(long long)i * N + j];
+            rs += c;
+            low += !(c > mincount);
+        }
+        for (int j = 0; j < N; ++j) A[(long long)i * N + j] = Cm[(long long)i * N + j] / rs;
+        pi[i] = stats[1 + i] / g0sum;
+        int f = low;
+        if (gauss) {
+            const double* w = stats + 1 + N + (long long)N * N;
+            const double shift = w[N + i] / w[i];
+            const double var = w[2 * N + i] / w[i] - shift * shift;
+            const double s = sqrt(var > 0.0 ? var : 0.0);
+            mu[i] = mu_old[i] + shift;
+            sg[i] = s;
+            if (!(s >= 2.220446049250313e-16)) f += 1024;
+        } else {
+            mu[i] = 0.0;
+            sg[i] = 0.0;
+        }
+        if (f) atomicAdd(&flags, f);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { sg[N] = (double)flags; sg[N + 1] = stats[0]; }
+}
+
+// Row normalisation of the B numerators (discrete.py:214-215): one warp per state, fixed-order partial sums per lane and a
+// fixed shuffle tree (deterministic).  Also writes the transposed table Bt (M,N) the discrete emission kernels gather from.
+__global__ void k_mstep_rows(const double* __restrict__ Bnum, int N, int M, double* __restrict__ B, double* __restrict__ Bt)
+{
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= N) return;
+    const double* row = Bnum + (long long)i * M;
+    double s = 0.0;
+    for (int k = lane; k < M; k += 32) s += row[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    for (int k = lane; k < M; k += 32) {
+        const double b = row[k] / s;
+        B[(long long)i * M + k] = b;
+        if (Bt) Bt[(long long)k * N + i] = b;
+    }
+}
+
 inline unsigned nblk(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace
@@ -238,6 +313,19 @@ int launch_update_pout(const int* sym, const double* w, long long rows, int N, i
 {
     if (rows <= 0) return BHMM_OK;
     k_update_pout<<<nblk(rows * N, 256), 256, 0, st>>>(sym, w, rows, N, M, pout);
+    return BHMM_OK;
+}
+
+int launch_mstep_hmm(const double* stats, const double* mu_old, int N, int gauss, double mincount, double* out, cudaStream_t st)
+{
+    k_mstep_hmm<<<1, 256, 0, st>>>(stats, mu_old, N, gauss, mincount, out);
+    return BHMM_OK;
+}
+
+int launch_mstep_rows(const double* Bnum, int N, int M, double* B, double* Bt, cudaStream_t st)
+{
+    if (N <= 0 || M <= 0) return BHMM_OK;
+    k_mstep_rows<<<(N + 3) / 4, 128, 0, st>>>(Bnum, N, M, B, Bt);
     return BHMM_OK;
 }
 

@@ -154,6 +154,8 @@ int launch_transition_counts(const double* alpha, const double* beta, const doub
                              int T, double* C, double* scratch, cudaStream_t st);
 int transition_counts_blocks(int T);
 int launch_update_pout(const int* sym, const double* w, long long rows, int N, int M, double* pout, cudaStream_t st);
+int launch_mstep_hmm(const double* stats, const double* mu_old, int N, int gauss, double mincount, double* out, cudaStream_t st);
+int launch_mstep_rows(const double* Bnum, int N, int M, double* B, double* Bt, cudaStream_t st);
 int launch_transpose(const double* in, int R, int Cc, double* out, cudaStream_t st);
 
 // ---- certification of chain hand-overs (certify.cu)

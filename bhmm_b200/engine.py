@@ -42,6 +42,45 @@ def unpack_stats(stats, N):
     return out
 
 
+def mstep_device(stats, N, means_old=None, mincount=1e-16, out=None):
+    """M-step on the GPU from the packed (all-reduced) E-step statistics (include/bhmm_b200.h: bhmm_b200_mstep_dev).
+
+    ``stats``: device tensor from ``estep_*``; ``means_old``: the means the E-step ran with (host array or device tensor;
+    None for a discrete model).  Returns the packed DEVICE tensor [A (N*N) | pi | means | sigmas | flags | loglik]; see
+    ``unpack_mstep``.  Nothing is copied to the host here."""
+    torch = _torch()
+    if out is None:
+        out = torch.empty(N * N + 3 * N + 2, dtype=torch.float64, device=stats.device)
+    m = None
+    if means_old is not None:
+        m = means_old if torch.is_tensor(means_old) else torch.as_tensor(f64(means_old)).to(stats.device)
+    with torch.cuda.device(stats.device):
+        check(lib.bhmm_b200_mstep_dev(C.c_void_p(stats.data_ptr()), C.c_void_p(m.data_ptr()) if m is not None else None,
+                                      int(N), float(mincount), C.c_void_p(out.data_ptr()),
+                                      C.c_void_p(torch.cuda.current_stream(stats.device).cuda_stream)))
+    return out
+
+
+def unpack_mstep(packed, N):
+    """Host view of ``mstep_device``'s result: dict(A, pi, means, sigmas, flags, loglik)."""
+    p = np.asarray(packed, dtype=np.float64)
+    o = N * N
+    return dict(A=p[:o].reshape(N, N).copy(), pi=p[o:o + N].copy(), means=p[o + N:o + 2 * N].copy(),
+                sigmas=p[o + 2 * N:o + 3 * N].copy(), flags=int(p[o + 3 * N]), loglik=float(p[o + 3 * N + 1]))
+
+
+def mstep_discrete_device(Bnum, out=None):
+    """Row-normalised output matrix on the GPU (discrete.py:214-215; bhmm_b200_mstep_discrete_dev); device tensor (N,M)."""
+    torch = _torch()
+    N, M = Bnum.shape
+    if out is None:
+        out = torch.empty_like(Bnum)
+    with torch.cuda.device(Bnum.device):
+        check(lib.bhmm_b200_mstep_discrete_dev(C.c_void_p(Bnum.data_ptr()), int(N), int(M), C.c_void_p(out.data_ptr()), None,
+                                               C.c_void_p(torch.cuda.current_stream(Bnum.device).cuda_stream)))
+    return out
+
+
 class TrajectoryBatch(object):
     """All trajectories of one data set (or of one rank's shard of it), resident on one GPU.
 
@@ -65,7 +104,21 @@ class TrajectoryBatch(object):
         lengths = [len(o) for o in observations]
         if len(lengths) == 0 or min(lengths) <= 0:
             raise ValueError('every trajectory needs at least one frame')
-        cat = np.concatenate([np.asarray(o, dtype=host_dtype) for o in observations])
+        rows = int(np.sum(lengths))
+        if len(lengths) <= 8192 and rows // len(lengths) >= 16384:
+            # long trajectories: copy each one straight into its slice of the device array (no concatenated host copy:
+            # for C3 that is 0.8 GB of host traffic saved in MaximumLikelihoodEstimator(...).fit()'s one-off upload)
+            torch = _torch()
+            dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+            cat = torch.empty(rows, dtype=torch.int32 if host_dtype == np.int32 else torch.float64, device=dev)
+            off = 0
+            for o in observations:
+                a = np.ascontiguousarray(o, dtype=host_dtype)
+                cat[off:off + a.shape[0]].copy_(torch.from_numpy(a), non_blocking=False)
+                off += a.shape[0]
+            self._adopt = True
+        else:
+            cat = np.concatenate([np.asarray(o, dtype=host_dtype) for o in observations])
         self._setup(cat, lengths, nstates, device, chunk, warm)
 
     @classmethod
@@ -99,9 +152,14 @@ class TrajectoryBatch(object):
         if cat.numel() != self.rows:
             raise ValueError('concatenated observations have %d frames, lengths sum to %d' % (cat.numel(), self.rows))
         self.discrete = not cat.dtype.is_floating_point
+        self._sym_range = None          # (min, max) symbol of an integer batch, computed on first discrete call
         with torch.cuda.device(self.device):
-            self.obs = cat.to(device=self.device, dtype=torch.int32 if self.discrete else torch.float64).contiguous().clone() \
-                if cat.is_cuda else cat.to(device=self.device, dtype=torch.int32 if self.discrete else torch.float64)
+            want = torch.int32 if self.discrete else torch.float64
+            if getattr(self, '_adopt', False) and cat.is_cuda and cat.dtype == want and cat.device == self.device:
+                self.obs = cat                       # built by __init__ for this batch: no second copy
+            else:
+                self.obs = cat.to(device=self.device, dtype=want).contiguous().clone() if cat.is_cuda \
+                    else cat.to(device=self.device, dtype=want)
             self._handle = C.c_void_p()
             if self._own_ranges is None:
                 rc = lib.bhmm_b200_batch_create(C.byref(self._handle), self.offsets.ctypes.data_as(C.POINTER(C.c_longlong)),
@@ -199,12 +257,32 @@ class TrajectoryBatch(object):
         """Cut a concatenated per-frame array back into the list of per-trajectory arrays."""
         return [flat[self.offsets[k]:self.offsets[k + 1]] for k in range(self.K)]
 
+    # -------------------------------------------------------------------------------------------- input checks
+    def _require_discrete(self, M):
+        """The discrete kernels index B[:, sym], Bnum[:, sym] and hist[:, sym] unchecked: refuse a float batch (its
+        float64 buffer would be reinterpreted as int32) and symbols outside [0, M) -- the reference raises IndexError
+        for those in DiscreteOutputModel.p_obs (discrete.py:146-153).  The range is reduced once per observation buffer."""
+        if not self.discrete:
+            raise TypeError('this batch holds float observations; a discrete output model needs integer symbols')
+        key = (self.obs.data_ptr(), self.obs._version)
+        if self._sym_range is None or self._sym_range[0] != key:
+            lo, hi = self.torch.aminmax(self.obs)
+            self._sym_range = (key, int(lo.item()), int(hi.item()))
+        _, lo, hi = self._sym_range
+        if lo < 0 or hi >= int(M):
+            raise IndexError('observation symbols span [%d, %d] but the output model has %d symbols' % (lo, hi, int(M)))
+
+    def _require_gaussian(self):
+        if self.discrete:
+            raise TypeError('this batch holds integer symbols; a Gaussian output model needs float observations')
+
     # -------------------------------------------------------------------------------------------- E-step
     def estep_gaussian(self, A, pi, means, sigmas, ignore_outliers=True, gamma_out=None):
         """One E-step; returns the packed statistics as a DEVICE tensor (see ``unpack_stats``).
 
         ``gamma_out``: optional (rows,N) float64 CUDA tensor that receives the state probabilities.
         """
+        self._require_gaussian()
         A_, pi_, m_, s_ = f64(A), f64(pi), f64(means), f64(sigmas)
         g = C.c_void_p(gamma_out.data_ptr()) if gamma_out is not None else None
         with self.torch.cuda.device(self.device):
@@ -217,6 +295,7 @@ class TrajectoryBatch(object):
     def estep_discrete(self, A, pi, B, ignore_outliers=False, gamma_out=None):
         """One E-step for a discrete output model; returns (stats, Bnum) device tensors."""
         A_, pi_, B_ = f64(A), f64(pi), f64(B)
+        self._require_discrete(B_.shape[1])
         N, M = B_.shape
         if getattr(self, '_Bnum', None) is None or tuple(self._Bnum.shape) != (N, M):
             self._Bnum = self.torch.zeros((N, M), dtype=self.torch.float64, device=self.device)
@@ -237,6 +316,7 @@ class TrajectoryBatch(object):
 
     def viterbi_gaussian(self, A, pi, means, sigmas, ignore_outliers=True):
         """Viterbi paths of all trajectories as one concatenated int32 DEVICE tensor."""
+        self._require_gaussian()
         A_, pi_, m_, s_ = f64(A), f64(pi), f64(means), f64(sigmas)
         path = self._path_buffer()
         with self.torch.cuda.device(self.device):
@@ -248,6 +328,7 @@ class TrajectoryBatch(object):
 
     def viterbi_discrete(self, A, pi, B, ignore_outliers=False):
         A_, pi_, B_ = f64(A), f64(pi), f64(B)
+        self._require_discrete(B_.shape[1])
         path = self._path_buffer()
         with self.torch.cuda.device(self.device):
             rc = lib.bhmm_b200_viterbi_discrete(self._handle, C.c_void_p(self.obs.data_ptr()), dptr(A_), dptr(pi_),
@@ -269,6 +350,7 @@ class TrajectoryBatch(object):
         [C (N*N) | n0 (N) | frames per state (N)], float64 [sum o (N) | sum o^2 (N)] (all DEVICE tensors) and the
         log-likelihood of the forward pass.  ``uniforms``: optional (rows,) float64 CUDA tensor, one draw per
         frame (parity with the reference's glibc stream); default is device Philox keyed by (seed, sweep)."""
+        self._require_gaussian()
         A_, pi_, m_, s_ = f64(A), f64(pi), f64(means), f64(sigmas)
         path = self._path_buffer()
         counts, sums = self._gibbs_buffers()
@@ -286,6 +368,7 @@ class TrajectoryBatch(object):
     def gibbs_discrete(self, A, pi, B, seed=0, sweep=0, uniforms=None, ignore_outliers=False):
         """Discrete counterpart; returns (path, counts, symbol histogram (N,M) int64, loglik)."""
         A_, pi_, B_ = f64(A), f64(pi), f64(B)
+        self._require_discrete(B_.shape[1])
         N, M = B_.shape
         path = self._path_buffer()
         counts, _ = self._gibbs_buffers()
@@ -364,6 +447,11 @@ class SubBatchedTrajectories(object):
                     lo = mid
                 else:
                     hi = mid - 1
+            wave = int(lib.bhmm_b200_wave_chains(int(nstates))) if chunk <= 0 else 0
+            if wave > 0 and lo - a > wave:
+                # whole waves: a group of 1365 trajectories on a wave of 1184 chains runs two rounds, the second one
+                # almost empty; the remainder forms a smaller group whose trajectories the planner cuts to fill a wave
+                lo = a + ((lo - a) // wave) * wave
             groups.append((a, lo))
             a = lo
         return groups

@@ -28,7 +28,7 @@ class BayesianHMMSampler(object):
 
     def __init__(self, observations, nstates, initial_model=None, reversible=True, stationary=False,
                  transition_matrix_sampling_steps=1000, p0_prior='mixed', transition_matrix_prior='mixed',
-                 output='gaussian', chunk=0, warm=0, shard=True):
+                 output='gaussian', chunk=0, warm=0, shard=True, batch=None):
         if len(observations) == 0:
             raise Exception("No observations were provided.")
         if initial_model is None:
@@ -79,9 +79,13 @@ class BayesianHMMSampler(object):
             raise ValueError('transition matrix prior mode undefined: ' + str(transition_matrix_prior))
         self.transition_matrix_sampling_steps = transition_matrix_sampling_steps
         self.model.output_model.set_implementation(config.kernel)
-        self._batch = make_batch(self.observations, nstates, chunk=chunk, warm=warm) if self.nobs else None
+        # batch=: an engine batch that already holds these trajectories on the GPU (no second upload)
+        self._batch = batch if batch is not None else (make_batch(self.observations, nstates, chunk=chunk, warm=warm) if self.nobs else None)
         self._sweep = 0
-        self._seed = 0
+        # Philox key of the hidden-path draws.  Without an explicit seed= in sample() it comes from the agreed host stream
+        # (np.random.seed makes a run reproducible, two samplers do not share their uniforms; the reference continues
+        # the libc rand() stream, _hidden.c:321-327)
+        self._seed = int(self._rng.randint(0, 2 ** 31 - 1))
         self.timings = {'hidden': 0.0, 'parameters': 0.0}
         self.last_loglik = None
 
@@ -122,7 +126,19 @@ class BayesianHMMSampler(object):
         st = {}
         # a different Philox key per rank keeps the shards' draws independent
         seed = self._seed * 1000003 + dist.rank()
-        if self._output == 'gaussian':
+        N = self.nstates
+        if self._batch is None:
+            # empty shard (more ranks than trajectories): zero statistics, so that the collectives below still match
+            import torch
+            path, ll = None, 0.0
+            counts = torch.zeros(N * N + 2 * N, dtype=torch.int64, device='cuda')
+            if self._output == 'gaussian':
+                sums = dist.allreduce_sum(torch.zeros(2 * N, dtype=torch.float64, device='cuda'))
+                st['so'], st['soo'] = np.split(sums.cpu().numpy(), 2)
+            else:
+                M = np.shape(om.output_probabilities)[1]
+                st['hist'] = dist.allreduce_sum(torch.zeros((N, M), dtype=torch.int64, device='cuda')).cpu().numpy()
+        elif self._output == 'gaussian':
             path, counts, sums, ll = self._batch.gibbs_gaussian(A, pi, om.means, om.sigmas, seed=seed, sweep=self._sweep,
                                                                 ignore_outliers=om.ignore_outliers)
             sums = dist.allreduce_sum(sums.clone())
@@ -132,10 +148,11 @@ class BayesianHMMSampler(object):
                                                                 sweep=self._sweep, ignore_outliers=om.ignore_outliers)
             st['hist'] = dist.allreduce_sum(hist.clone()).cpu().numpy()
         counts = dist.allreduce_sum(counts.clone())
-        st.update(self._batch.unpack_counts(counts))
+        c = counts.cpu().numpy()
+        st.update(C=c[:N * N].reshape(N, N).copy(), n0=c[N * N:N * N + N].copy(), count=c[N * N + N:].copy())
         self._sweep += 1
         self.last_loglik = ll
-        if keep_paths:
+        if keep_paths and self._batch is not None:
             self.model.hidden_state_trajectories = [p.copy() for p in self._batch.split(path.cpu().numpy())]
         return st
 

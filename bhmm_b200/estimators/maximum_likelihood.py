@@ -5,7 +5,10 @@ transition_counts on host arrays (maximum_likelihood.py:221-269), keeps every ga
 in the M-step (:284-330).  Here one fused E-step per iteration runs over all trajectories on the GPU
 (bhmm_b200.engine.TrajectoryBatch) and returns only the sufficient statistics the M-step needs; with several
 ranks (torch.distributed initialised) the trajectories are sharded and the statistics all-reduced
-(bhmm_b200.dist).  The M-step itself is tiny host math, identical on every rank.
+(bhmm_b200.dist).  On the non-reversible branch the M-step runs on the GPU as well (engine.mstep_device: transition
+matrix, initial distribution, Gaussian means/sigmas or the discrete output matrix from the reduced statistics), and one
+small device-to-host copy per iteration brings back the updated parameters and the log-likelihood; the reversible /
+stationary / fixed-distribution branches and count matrices with empty entries use the host code (util/tmatrix.py).
 """
 import copy
 import time
@@ -13,7 +16,7 @@ import time
 import numpy as np
 
 from .. import dist
-from ..engine import TrajectoryBatch, make_batch, unpack_stats
+from ..engine import TrajectoryBatch, make_batch, unpack_stats, mstep_device, mstep_discrete_device, unpack_mstep
 from ..util import config
 from ..util.logger import logger
 from ..util import tmatrix as _tmatrix
@@ -29,7 +32,7 @@ class MaximumLikelihoodEstimator(object):
     """
 
     def __init__(self, observations, nstates, initial_model=None, output='gaussian', reversible=True, stationary=False,
-                 p=None, accuracy=1e-3, maxit=1000, maxit_P=100000, chunk=0, warm=0, shard=True):
+                 p=None, accuracy=1e-3, maxit=1000, maxit_P=100000, chunk=0, warm=0, shard=True, device_mstep=True, batch=None):
         if initial_model is None:
             raise NotImplementedError('bhmm_b200 needs initial_model= (bhmm.init_hmm is outside the hot path)')
         self._nstates = nstates
@@ -60,11 +63,15 @@ class MaximumLikelihoodEstimator(object):
         self._maxit = maxit
         self._maxit_P = maxit_P
         self._likelihoods = None
-        self._batch = make_batch(self._observations, nstates, chunk=chunk, warm=warm) if self._nobs else None
+        # batch=: an engine batch that already holds these trajectories on the GPU (no second upload)
+        self._batch = batch if batch is not None else (make_batch(self._observations, nstates, chunk=chunk, warm=warm) if self._nobs else None)
         self._hmm.output_model.set_implementation(config.kernel)
         self.count_matrix = None
         self.initial_count = None
         self.timings = {'estep': 0.0, 'mstep': 0.0}
+        self._device_mstep = bool(device_mstep)
+        self.device_msteps = 0          # iterations whose M-step ran on the GPU
+        self._dev = None                # device tensors of the last E-step (reduced statistics, B numerators)
 
     # ---- properties of the reference estimator
     @property
@@ -118,16 +125,56 @@ class MaximumLikelihoodEstimator(object):
         om = self._hmm.output_model
         Bnum = None
         if self._batch is None:
-            raise RuntimeError('this rank holds no trajectories: use at most one rank per trajectory')
-        if self._output == 'gaussian':
+            # a rank whose shard is empty (more ranks than trajectories) contributes zero statistics: the other ranks are
+            # already waiting in the all-reduce, raising here would deadlock the job
+            import torch
+            N = self._nstates
+            stats = torch.zeros(1 + N + N * N + 3 * N, dtype=torch.float64, device='cuda')
+            if self._output != 'gaussian':
+                Bnum = torch.zeros(tuple(np.shape(om.output_probabilities)), dtype=torch.float64, device='cuda')
+        elif self._output == 'gaussian':
             stats = self._batch.estep_gaussian(A, pi, om.means, om.sigmas, ignore_outliers=om.ignore_outliers)
         else:
             stats, Bnum = self._batch.estep_discrete(A, pi, om.output_probabilities, ignore_outliers=om.ignore_outliers)
         stats = dist.allreduce_sum(stats)
+        if Bnum is not None:
+            Bnum = dist.allreduce_sum(Bnum)
+        self._dev = (stats, Bnum)
+        if self._device_mstep and self._device_mstep_applies():
+            return None                  # the statistics stay on the GPU: _update_model_device reads back parameters only
+        return self._host_stats()
+
+    def _host_stats(self):
+        stats, Bnum = self._dev
         st = unpack_stats(stats.cpu().numpy(), self._nstates)
         if Bnum is not None:
-            st['Bnum'] = dist.allreduce_sum(Bnum).cpu().numpy()
+            st['Bnum'] = Bnum.cpu().numpy()
         return st
+
+    def _device_mstep_applies(self):
+        """The GPU M-step implements the non-reversible estimator C / rowsum with pi = gamma0 / sum: that is what the
+        reference reaches (maximum_likelihood.py:307-320) when the CURRENT matrix is not reversible and nothing is fixed."""
+        return (not self._stationary and self._fixed_initial_distribution is None
+                and self._fixed_stationary_distribution is None and not self._hmm.is_reversible)
+
+    def _update_model_device(self):
+        """M-step on the GPU; one device-to-host copy of [A | pi | means | sigmas | flags | loglik].  Returns the
+        log-likelihood, or None when the kernel flagged a case for the host code (an empty count, a collapsed sigma)."""
+        stats, Bnum = self._dev
+        N = self._nstates
+        om = self._hmm.output_model
+        packed = mstep_device(stats, N, means_old=om.means if self._output == 'gaussian' else None, mincount=1e-16)
+        B = mstep_discrete_device(Bnum) if Bnum is not None else None
+        res = unpack_mstep(packed.cpu().numpy(), N)
+        if res['flags'] != 0:
+            return None
+        self._hmm.update(res['pi'], res['A'])
+        if self._output == 'gaussian':
+            om._means, om._sigmas = res['means'], res['sigmas']
+        else:
+            om._output_probabilities = B.cpu().numpy()
+        self.device_msteps += 1
+        return res['loglik']
 
     def _update_model(self, st, maxiter=10000000):
         """M-step (maximum_likelihood.py:284-330) from the reduced statistics."""
@@ -158,6 +205,8 @@ class MaximumLikelihoodEstimator(object):
         A = self._hmm.transition_matrix
         pi = self._hmm.initial_distribution
         om = self._hmm.output_model
+        if self._batch is None:
+            return np.empty(0, dtype=object)
         if self._output == 'gaussian':
             path = self._batch.viterbi_gaussian(A, pi, om.means, om.sigmas, ignore_outliers=om.ignore_outliers)
         else:
@@ -180,14 +229,21 @@ class MaximumLikelihoodEstimator(object):
         while not converged and it < self.maxit:
             t1 = time.time()
             st = self._estep()
-            loglik = st['loglik']
+            loglik = None
+            if st is None:               # GPU M-step: applied now, the convergence test below only needs loglik
+                loglik = self._update_model_device()
+                if loglik is None:
+                    st = self._host_stats()
+            if st is not None:
+                loglik = st['loglik']
             assert np.isfinite(loglik), it
             t2 = time.time()
             if it > 0:
                 dL = loglik - self._likelihoods[it - 1]
                 if dL < self._accuracy:
                     converged = True
-            self._update_model(st, maxiter=self._maxit_P)
+            if st is not None:
+                self._update_model(st, maxiter=self._maxit_P)
             t3 = time.time()
             self.timings['estep'] += t2 - t1
             self.timings['mstep'] += t3 - t2
@@ -200,6 +256,8 @@ class MaximumLikelihoodEstimator(object):
             it += 1
         self._likelihoods = self._likelihoods[:it]
         self._hmm.likelihood = loglik
+        if st is None:
+            st = self._host_stats()      # statistics of the last E-step (count matrix, initial counts), read once
         self.count_matrix = st['C']
         self.initial_count = st['gamma0']
         self._hmm.hidden_state_trajectories = self.compute_viterbi_paths()

@@ -19,7 +19,7 @@ from .._lib import lib, dptr, iptr, f64, check
 from ..util import config
 
 __all__ = ['set_implementation', 'forward', 'backward', 'state_probabilities', 'state_counts',
-           'transition_counts', 'viterbi', 'sample_path']
+           'transition_counts', 'viterbi', 'sample_path', 'set_device_cache', 'device_cache_stats']
 
 # implementation codes (bhmm/hidden/api.py:36-41 has python=0, c=1; 'cuda' is the one added here)
 __IMPL_CUDA__ = 2
@@ -40,6 +40,108 @@ def set_implementation(impl):
     if impl.lower() != 'cuda':
         warnings.warn('Implementation ' + impl + ' is not provided by bhmm_b200. Using the cuda implementation.')
     __impl__ = __IMPL_CUDA__
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Device-side cache keyed on the identity of the caller's host buffers.
+#
+# The reference estimators call p_obs -> forward -> backward -> state_probabilities -> transition_counts per trajectory
+# on the SAME preallocated host arrays (maximum_likelihood.py:128-133,249-265: self._pobs / _alpha / _beta;
+# bayesian_sampling.py:200-201,325-329).  A literal drop-in re-uploads pobs three times and alpha / beta twice per
+# trajectory.  With the cache on, every (T,N) table this module (or OutputModel.p_obs) WROTE into a host array is also
+# kept on the GPU, keyed by the array's data pointer; when a later call receives that array as an INPUT, the device copy
+# is used instead of a second host-to-device transfer.  Results are still copied back into the host arrays on every call
+# (numpy semantics are unchanged); only redundant uploads disappear: 7 (T,N) uploads per trajectory become 0.
+#
+# A host array that the caller modifies between two calls would make a stale hit.  Guards: the entry remembers shape and
+# a fingerprint of 64 strided elements plus the first and last row, checked on every hit; a mismatch drops the entry and
+# uploads.  The cache is OFF by default (exact literal semantics) and switched on by ``bhmm_b200.install()`` for the
+# reference estimators, whose buffers are private.
+# ------------------------------------------------------------------------------------------------------------------
+_cache_on = False
+_cache = {}            # data pointer -> dict(dev=tensor (rows,N), rows, N, probe)
+_cache_order = []
+_CACHE_MAX = 8
+_cache_counters = {'hits': 0, 'misses': 0, 'stale': 0}
+
+
+def set_device_cache(on=True):
+    """Switch the buffer-identity device cache on or off (dropping every entry)."""
+    global _cache_on
+    _cache_on = bool(on)
+    _cache.clear()
+    del _cache_order[:]
+
+
+def device_cache_stats():
+    return dict(_cache_counters, entries=len(_cache), enabled=_cache_on)
+
+
+def _probe(a, rows):
+    flat = a[:rows].reshape(-1)
+    n = flat.shape[0]
+    if n == 0:
+        return ()
+    idx = np.linspace(0, n - 1, num=min(n, 64)).astype(np.int64)
+    N = a.shape[1]
+    return (flat[idx].tobytes(), flat[:N].tobytes(), flat[n - N:].tobytes())
+
+
+def _torch_dev():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.CudaUnavailableError('bhmm_b200.hidden needs a CUDA device (no CPU fallback)')
+    return torch
+
+
+def _remember(host, dev, rows):
+    """`dev` (rows,N) holds exactly what was just written to host[:rows]."""
+    if not _cache_on or not isinstance(host, np.ndarray) or not host.flags['C_CONTIGUOUS']:
+        return
+    key = host.__array_interface__['data'][0]
+    if key not in _cache:
+        _cache_order.append(key)
+        while len(_cache_order) > _CACHE_MAX:
+            _cache.pop(_cache_order.pop(0), None)
+    _cache[key] = dict(dev=dev, rows=rows, N=host.shape[1], probe=_probe(host, rows))
+
+
+def _lookup(host, rows, N):
+    """Device copy of host[:rows] if this module produced it and it still looks untouched, else None."""
+    if not _cache_on or not isinstance(host, np.ndarray) or host.dtype != np.float64 or not host.flags['C_CONTIGUOUS']:
+        return None
+    e = _cache.get(host.__array_interface__['data'][0])
+    if e is None or e['N'] != N or e['rows'] < rows or host.ndim != 2 or host.shape[1] != N:
+        _cache_counters['misses'] += 1
+        return None
+    if _probe(host, e['rows']) != e['probe']:
+        _cache_counters['stale'] += 1
+        _cache.pop(host.__array_interface__['data'][0], None)
+        return None
+    _cache_counters['hits'] += 1
+    return e['dev']
+
+
+def _to_device(host, rows, N):
+    """Cached device copy or a fresh upload of host[:rows] ((rows,N) float64)."""
+    d = _lookup(host, rows, N)
+    if d is not None:
+        return d
+    torch = _torch_dev()
+    return torch.as_tensor(f64(host)[:rows]).cuda()
+
+
+def _small(a):
+    return _torch_dev().as_tensor(f64(a)).cuda()
+
+
+def _stream():
+    torch = _torch_dev()
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _require_f64():
@@ -72,9 +174,21 @@ def forward(A, pobs, pi, T=None, alpha_out=None):
     if alpha_out is not None and T > alpha_out.shape[0]:
         raise TypeError('alpha_out must at least have length T in order to fit trajectory.')
     buf, ret = _out_buffer(alpha_out, T, N)
-    A_, pobs_, pi_ = f64(A), f64(pobs), f64(pi)
-    logprob = lib.bhmm_b200_forward(dptr(buf), dptr(A_), dptr(pobs_), dptr(pi_), N, T)
-    check()
+    if _cache_on:
+        torch = _torch_dev()
+        d_pobs = _to_device(pobs, T, N)
+        d_alpha = torch.empty((T, N), dtype=torch.float64, device='cuda')
+        lp = ctypes.c_double(0.0)
+        d_A, d_pi = _small(A), _small(pi)               # named: the tensors must outlive the call
+        check(lib.bhmm_b200_forward_dev(_ptr(d_alpha), _ptr(d_A), _ptr(d_pobs), _ptr(d_pi), N, T,
+                                        ctypes.byref(lp), _stream()))
+        torch.from_numpy(buf[:T]).copy_(d_alpha)
+        _remember(buf, d_alpha, T)
+        logprob = lp.value
+    else:
+        A_, pobs_, pi_ = f64(A), f64(pobs), f64(pi)
+        logprob = lib.bhmm_b200_forward(dptr(buf), dptr(A_), dptr(pobs_), dptr(pi_), N, T)
+        check()
     if buf is not ret:
         ret[:T] = buf[:T]
     return logprob, ret
@@ -91,9 +205,18 @@ def backward(A, pobs, T=None, beta_out=None):
     if beta_out is not None and T > beta_out.shape[0]:
         raise ValueError('beta_out must at least have length T in order to fit trajectory.')
     buf, ret = _out_buffer(beta_out, T, N)
-    A_, pobs_ = f64(A), f64(pobs)
-    lib.bhmm_b200_backward(dptr(buf), dptr(A_), dptr(pobs_), N, T)
-    check()
+    if _cache_on:
+        torch = _torch_dev()
+        d_pobs = _to_device(pobs, T, N)
+        d_beta = torch.empty((T, N), dtype=torch.float64, device='cuda')
+        d_A = _small(A)
+        check(lib.bhmm_b200_backward_dev(_ptr(d_beta), _ptr(d_A), _ptr(d_pobs), N, T, _stream()))
+        torch.from_numpy(buf[:T]).copy_(d_beta)
+        _remember(buf, d_beta, T)
+    else:
+        A_, pobs_ = f64(A), f64(pobs)
+        lib.bhmm_b200_backward(dptr(buf), dptr(A_), dptr(pobs_), N, T)
+        check()
     if buf is not ret:
         ret[:T] = buf[:T]
     return ret
@@ -117,8 +240,16 @@ def state_probabilities(alpha, beta, T=None, gamma_out=None):
         if gamma_out.shape[0] != rows:
             raise ValueError('gamma_out has %d rows, expected %d' % (gamma_out.shape[0], rows))
     buf, ret = _out_buffer(gamma_out, rows, N)
-    a_, b_ = f64(alpha), f64(beta)
-    check(lib.bhmm_b200_state_probabilities(dptr(buf), dptr(a_), dptr(b_), N, rows))
+    if _cache_on:
+        torch = _torch_dev()
+        d_a, d_b = _to_device(alpha, rows, N), _to_device(beta, rows, N)
+        d_g = torch.empty((rows, N), dtype=torch.float64, device='cuda')
+        check(lib.bhmm_b200_state_probabilities_dev(_ptr(d_g), _ptr(d_a), _ptr(d_b), N, rows, _stream()))
+        torch.from_numpy(buf[:rows]).copy_(d_g)
+        _remember(buf, d_g, rows)
+    else:
+        a_, b_ = f64(alpha), f64(beta)
+        check(lib.bhmm_b200_state_probabilities(dptr(buf), dptr(a_), dptr(b_), N, rows))
     if gamma_out is None:
         return buf[:T] if T < rows else buf
     if buf is not ret:
@@ -151,9 +282,17 @@ def transition_counts(alpha, beta, A, pobs, T=None, out=None):
         Cbuf = np.zeros((N, N), dtype=np.float64, order='C')
     else:
         Cbuf = out
-    a_, b_, A_, p_ = f64(alpha), f64(beta), f64(A), f64(pobs)
-    rc = lib.bhmm_b200_transition_counts(dptr(Cbuf), dptr(A_), dptr(p_), dptr(a_), dptr(b_), N, T)
-    check(rc)
+    if _cache_on:
+        torch = _torch_dev()
+        d_a, d_b, d_p = _to_device(alpha, T, N), _to_device(beta, T, N), _to_device(pobs, T, N)
+        d_C = torch.empty((N, N), dtype=torch.float64, device='cuda')
+        d_A = _small(A)
+        check(lib.bhmm_b200_transition_counts_dev(_ptr(d_C), _ptr(d_A), _ptr(d_p), _ptr(d_a), _ptr(d_b), N, T, _stream()))
+        torch.from_numpy(Cbuf).copy_(d_C)
+    else:
+        a_, b_, A_, p_ = f64(alpha), f64(beta), f64(A), f64(pobs)
+        rc = lib.bhmm_b200_transition_counts(dptr(Cbuf), dptr(A_), dptr(p_), dptr(a_), dptr(b_), N, T)
+        check(rc)
     if out is not None and Cbuf is not out:
         out[...] = Cbuf
         return out

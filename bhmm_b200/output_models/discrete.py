@@ -52,8 +52,20 @@ class DiscreteOutputModel(OutputModel):
             res = out
         direct = isinstance(res, np.ndarray) and res.dtype == np.float64 and res.flags['C_CONTIGUOUS']
         buf = res if direct else np.zeros((T, N), dtype=np.float64)
-        check(lib.bhmm_b200_discrete_p_obs(iptr(sym), dptr(f64(self._output_probabilities)), N, M, T,
-                                           int(bool(self.ignore_outliers)), dptr(buf)))
+        from ..hidden import api as _hapi
+        if _hapi._cache_on and T > 0:
+            # buffer-identity cache (hidden/api.py): keep the gathered tile on the GPU for the calls that follow
+            torch = _hapi._torch_dev()
+            d_sym = torch.as_tensor(sym).cuda()
+            d_B = _hapi._small(self._output_probabilities)
+            d_p = torch.empty((T, N), dtype=torch.float64, device='cuda')
+            check(lib.bhmm_b200_discrete_p_obs_dev(_hapi._ptr(d_sym), _hapi._ptr(d_B), N, M, T,
+                                                   int(bool(self.ignore_outliers)), _hapi._ptr(d_p), _hapi._stream()))
+            torch.from_numpy(buf[:T]).copy_(d_p)
+            _hapi._remember(buf, d_p, T)
+        else:
+            check(lib.bhmm_b200_discrete_p_obs(iptr(sym), dptr(f64(self._output_probabilities)), N, M, T,
+                                               int(bool(self.ignore_outliers)), dptr(buf)))
         if not direct:
             res[:T] = buf
         return res

@@ -142,6 +142,10 @@ int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm);
 /* 1 when the batch runs the small-N one-thread-per-chain kernels (N <= 16), 0 for the general-N team kernels.
  * The environment variable BHMM_B200_FAMILY=team forces the latter at creation time. */
 int bhmm_b200_batch_uses_lane_kernels(const bhmm_b200_batch* b);
+/* Chains that fill the GPU exactly once for this state count (resident blocks of the statistics kernel x chains per block);
+ * 0 without a device.  Callers that cut a data set into groups (engine.SubBatchedTrajectories) size the groups in multiples
+ * of it so that no round of the persistent kernels runs mostly empty. */
+int bhmm_b200_wave_chains(int N);
 /* Viterbi-only batch: the workspace holds no (rows, N) forward variables -- observations, uint8 back-pointer map and path
  * only (N + 4 + 8 bytes per frame instead of 9 N + 12) -- so that one very long trajectory (C5: 1e9 frames x 32 states = 44 GB)
  * fits one GPU for bhmm_b200_viterbi_*; E-step and sampling calls on such a batch return BHMM_B200_ERR_UNSUPPORTED.  Call
@@ -197,6 +201,18 @@ int bhmm_b200_gibbs_discrete(bhmm_b200_batch* b, const int* d_obs, const double*
  * d_hist (device int64, N*M) += [path==i][obs==m]. */
 int bhmm_b200_path_symbol_histogram(const int* d_path, const int* d_obs, long long rows, int N, int M,
                                     long long* d_hist, void* stream);
+
+/* M-step on the device from the (all-reduced) packed statistics of bhmm_b200_estep_* (replaces the host
+ * arithmetic of maximum_likelihood.py:284-330 on the non-reversible branch: estimate_P -> C / rowsum,
+ * _tmatrix_disconnected.py:110-115; pi = gamma0 / sum, :318-320; GaussianOutputModel.estimate gaussian.py:214-272 via the
+ * shifted moments).  d_means_old: the means the E-step ran with (NULL for a discrete model: no Gaussian part).
+ * d_out (device, N*N + 3N + 2 doubles) = [A | pi | means | sigmas | flags | loglik]; flags counts C entries <= mincount (+1 each:
+ * the caller must use the general-connectivity estimator instead) and sigmas below machine epsilon (+1024 each). */
+int bhmm_b200_mstep_dev(const double* d_stats, const double* d_means_old, int N, double mincount, double* d_out,
+                        void* stream);
+/* DiscreteOutputModel.estimate's normalisation (discrete.py:214-215): d_B (N,M) = d_Bnum / rowsum; d_Bt (M,N), optional,
+ * receives the transposed table. */
+int bhmm_b200_mstep_discrete_dev(const double* d_Bnum, int N, int M, double* d_B, double* d_Bt, void* stream);
 
 #ifdef __cplusplus
 }

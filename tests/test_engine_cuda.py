@@ -69,9 +69,11 @@ def test_estep_gaussian_statistics(eng, oracle_port, golden, family, chunk, warm
     batch.close()
 
 
-def test_em_iterations_match_reference_estimator(eng, golden):
+@pytest.mark.parametrize('device_mstep', [True, False])
+def test_em_iterations_match_reference_estimator(eng, golden, device_mstep):
     """6 Baum-Welch iterations from the fixture's initial model reproduce MaximumLikelihoodEstimator.fit
-    (log-likelihood history, A, pi, means, sigmas within 1e-10; Viterbi paths identical)."""
+    (log-likelihood history, A, pi, means, sigmas within 1e-10; Viterbi paths identical), with the M-step on the GPU
+    (engine.mstep_device) and with the host M-step."""
     from bhmm_b200.estimators import MaximumLikelihoodEstimator
     from bhmm_b200.hmm import HMM
     from bhmm_b200.output_models import GaussianOutputModel
@@ -79,8 +81,9 @@ def test_em_iterations_match_reference_estimator(eng, golden):
     obs = em_obs(g)
     init = HMM(g['pi0'], g['A0'], GaussianOutputModel(3, means=g['means0'], sigmas=g['sigmas0']))
     est = MaximumLikelihoodEstimator(obs, 3, initial_model=init, reversible=False, stationary=False,
-                                     accuracy=-np.inf, maxit=6)
+                                     accuracy=-np.inf, maxit=6, device_mstep=device_mstep)
     model = est.fit()
+    assert est.device_msteps == (6 if device_mstep else 0)
     np.testing.assert_allclose(est.likelihoods, g['likelihoods'], rtol=RTOL)
     np.testing.assert_allclose(model.transition_matrix, g['A'], rtol=RTOL)
     np.testing.assert_allclose(model.initial_distribution, g['pi'], rtol=RTOL, atol=1e-300)
@@ -92,7 +95,8 @@ def test_em_iterations_match_reference_estimator(eng, golden):
         assert np.array_equal(model.hidden_state_trajectories[k], g['viterbi%d' % k])
 
 
-def test_em_discrete_matches_reference_estimator(eng, golden):
+@pytest.mark.parametrize('device_mstep', [True, False])
+def test_em_discrete_matches_reference_estimator(eng, golden, device_mstep):
     from bhmm_b200.estimators import MaximumLikelihoodEstimator
     from bhmm_b200.hmm import HMM
     from bhmm_b200.output_models import DiscreteOutputModel
@@ -100,13 +104,45 @@ def test_em_discrete_matches_reference_estimator(eng, golden):
     obs = em_obs(g)
     init = HMM(g['pi0'], g['A0'], DiscreteOutputModel(g['B0']))
     est = MaximumLikelihoodEstimator(obs, 4, initial_model=init, reversible=False, stationary=False,
-                                     accuracy=-np.inf, maxit=4, output='discrete')
+                                     accuracy=-np.inf, maxit=4, output='discrete', device_mstep=device_mstep)
     model = est.fit()
+    assert est.device_msteps == (4 if device_mstep else 0)
     np.testing.assert_allclose(est.likelihoods, g['likelihoods'], rtol=RTOL)
     np.testing.assert_allclose(model.transition_matrix, g['A'], rtol=RTOL)
     np.testing.assert_allclose(model.output_model.output_probabilities, g['B'], rtol=1e-9, atol=1e-300)
     for k in range(len(obs)):
         assert np.array_equal(model.hidden_state_trajectories[k], g['viterbi%d' % k])
+
+
+def test_device_mstep_flags_cases_for_the_host(eng):
+    """engine.mstep_device against the host formulas on random statistics; an empty count or a collapsed sigma sets the
+    flags word so that the estimator falls back to the general host code (util/tmatrix.estimate_P, gaussian.py:271-272)."""
+    import torch
+    rng = np.random.default_rng(5)
+    for N in (1, 3, 10, 100):
+        Cm = rng.random((N, N)) * 50 + 1e-3
+        g0, w = rng.random(N) + 0.1, rng.random(N) * 1e3 + 1.0
+        wd = (rng.random(N) - 0.5) * w
+        wdd = (rng.random(N) + 0.3) * w + wd * wd / w
+        mu = np.linspace(-3, 3, N)
+        stats = np.concatenate([[-123.5], g0, Cm.ravel(), w, wd, wdd])
+        dev = torch.as_tensor(stats).cuda()
+        res = eng.unpack_mstep(eng.mstep_device(dev, N, means_old=mu).cpu().numpy(), N)
+        assert res['flags'] == 0 and res['loglik'] == -123.5
+        np.testing.assert_allclose(res['A'], Cm / Cm.sum(axis=1)[:, None], rtol=1e-14)
+        np.testing.assert_allclose(res['pi'], g0 / g0.sum(), rtol=1e-14)
+        np.testing.assert_allclose(res['means'], mu + wd / w, rtol=1e-14, atol=1e-15)
+        np.testing.assert_allclose(res['sigmas'], np.sqrt(wdd / w - (wd / w) ** 2), rtol=1e-12)
+        if N >= 3:
+            bad = stats.copy()
+            bad[1 + N + 1] = 0.0                                      # C[0, 1] = 0: connectivity is the host's business
+            assert eng.unpack_mstep(eng.mstep_device(torch.as_tensor(bad).cuda(), N, means_old=mu).cpu().numpy(), N)['flags'] == 1
+            bad = stats.copy()
+            bad[1 + N + N * N + 2 * N + 2] = bad[1 + N + N * N + N + 2] ** 2 / bad[1 + N + N * N + 2]   # variance of state 2 = 0
+            assert eng.unpack_mstep(eng.mstep_device(torch.as_tensor(bad).cuda(), N, means_old=mu).cpu().numpy(), N)['flags'] >= 1024
+        Bn = torch.as_tensor(rng.random((N, 37)) + 1e-3).cuda()
+        np.testing.assert_allclose(eng.mstep_discrete_device(Bn).cpu().numpy(),
+                                   Bn.cpu().numpy() / Bn.cpu().numpy().sum(axis=1)[:, None], rtol=1e-14)
 
 
 @pytest.mark.parametrize('N,K,T', [(2, 3, 50), (10, 6, 3000), (20, 3, 900), (32, 4, 1500), (40, 2, 500), (100, 2, 260)])
