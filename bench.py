@@ -641,12 +641,9 @@ def run_c5(args, torch, td, dev, world, rank, local):
     N = 32
     T = int(args.frames) if args.frames else int(1e9 if world >= 4 else 2.5e8 * world)
     desc = WORKLOADS['c5'][3] + ' (%d frames on %d GPU%s)' % (T, world, 's' if world > 1 else '')
-    rng = np.random.default_rng(7)
-    X = rng.random((N, N)) + 0.2
-    X += np.eye(N) * N * 0.5
-    A = X / X.sum(axis=1)[:, None]
-    pi = np.ones(N) / N
-    means, sigmas = np.linspace(-5, 5, N), np.linspace(0.5, 2.0, N)
+    from bhmm_b200.util import testsystems as ts
+    # the dalton recipe at N = 32 (metastable: lifetimes 10 ... 100 frames), so that the certified hand-overs are not trivial
+    pi, A, means, sigmas = ts.dalton_parameters(N, rng=np.random.default_rng(5))
     halo = 8 * max(128, 48 * N)
     lo, hi = (T * rank) // world, (T * (rank + 1)) // world
     a, b = max(0, lo - halo), min(T, hi + halo)

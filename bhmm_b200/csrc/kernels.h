@@ -132,6 +132,8 @@ int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st);
 int launch_backward_stats_panel(const BwdArgs& a, int em, cudaStream_t st);
 bool panel_viterbi_ok(int N);                // 32 < N <= 104: Viterbi with the matrix column in registers
 int launch_viterbi_panel(const VitArgs& a, int em, cudaStream_t st);
+bool lane_viterbi_ok(int N);                 // N <= 16: the chunked Viterbi runs one thread per chain (lane_viterbi.cu)
+int launch_viterbi_chain_lane(const VitChainArgs& a, int em, cudaStream_t st);
 bool panel_viterbi_chain_ok(int N);          // N <= 32: time-chunked Viterbi for trajectories cut into chains
 int launch_viterbi_chain(const VitChainArgs& a, int em, cudaStream_t st);
 // counter += number of decisions ON the resolved paths whose margin was flagged (0: the paths are certified)

@@ -1438,6 +1438,7 @@ int launch_viterbi_chain(const VitChainArgs& a, int em, cudaStream_t st)
 {
     if (a.N < 1 || a.N > 32) return BHMM_ERR_UNSUPPORTED;
     if (a.ch.n <= 0) return BHMM_OK;
+    if (lane_viterbi_ok(a.N)) return launch_viterbi_chain_lane(a, em, st);      // N <= 16: one thread per chain (lane_viterbi.cu)
     const int grid = (int)std::max(1LL, std::min<long long>(((long long)a.ch.n + PW - 1) / PW, (long long)panel_sms() * 4));
     switch (em) {
         case EM_POBS: k_viterbi_chain32<EM_POBS><<<grid, PW * 32, 0, st>>>(a); return BHMM_OK;

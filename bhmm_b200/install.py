@@ -90,5 +90,25 @@ def install(bhmm_module=None, device_cache=True):
         return d_p_obs(self, obs, out=out)
     dm.DiscreteOutputModel.p_obs = discrete_p_obs
 
+    # DiscreteOutputModel.estimate dispatches its scatter-add on the implementation too (discrete.py:205-213 ->
+    # impl_c/_discrete.c:1-32 _update_pout): 'cuda' runs the drop-in bhmm_b200_discrete_update_pout per trajectory
+    d_estimate = dm.DiscreteOutputModel.estimate
+
+    def discrete_estimate(self, observations, weights):
+        if getattr(self, '__impl__', None) != _IMPL_CUDA:
+            return d_estimate(self, observations, weights)
+        import numpy as np
+        from ._lib import lib, dptr, iptr, check
+        N, M = self._output_probabilities.shape
+        B = np.zeros((N, M))
+        for k in range(len(observations)):
+            sym = np.ascontiguousarray(observations[k], dtype=np.int32)
+            w = np.ascontiguousarray(weights[k], dtype=np.float64)
+            lib.bhmm_b200_discrete_update_pout(iptr(sym), dptr(w), sym.shape[0], N, M, dptr(B))
+            check()
+        B /= np.sum(B, axis=1)[:, None]
+        self._output_probabilities = B
+    dm.DiscreteOutputModel.estimate = discrete_estimate
+
     api.__bhmm_b200_installed__ = True
     return bhmm_module

@@ -138,7 +138,7 @@ def test_device_mstep_flags_cases_for_the_host(eng):
             bad[1 + N + 1] = 0.0                                      # C[0, 1] = 0: connectivity is the host's business
             assert eng.unpack_mstep(eng.mstep_device(torch.as_tensor(bad).cuda(), N, means_old=mu).cpu().numpy(), N)['flags'] == 1
             bad = stats.copy()
-            bad[1 + N + N * N + 2 * N + 2] = bad[1 + N + N * N + N + 2] ** 2 / bad[1 + N + N * N + 2]   # variance of state 2 = 0
+            bad[1 + N + N * N + 2 * N + 2] = 0.0                    # sum gamma d^2 = 0 for state 2: variance clamps to 0
             assert eng.unpack_mstep(eng.mstep_device(torch.as_tensor(bad).cuda(), N, means_old=mu).cpu().numpy(), N)['flags'] >= 1024
         Bn = torch.as_tensor(rng.random((N, 37)) + 1e-3).cuda()
         np.testing.assert_allclose(eng.mstep_discrete_device(Bn).cpu().numpy(),
