@@ -1036,6 +1036,520 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide(const BwdArgs a)
 }
 
 // ================================================================================================
+// "wide2" kernels: the wide kernels with TWO chain sets (16 chains) per block and one set of barriers for both.
+//
+// First B200 profile of the wide kernels at N = 100 (profiles/r2_wide13_ncu.md): the FP64 tensor pipe is busy a third of the
+// time; a frame is DMMA phase (all 13 warps queue on the pipe) followed by a latency phase (chain sums through shared memory,
+// shuffles, a division, the emission) in which the pipe idles, separated by block barriers at which 13 warps on 4 schedulers
+// wait for the scheduler that carries 4 of them.  Here every warp walks two independent groups of 8 chains with the SAME B
+// fragments: the latency phase and the barriers are paid once per two frames of work.  Also: the previous frame's vector is
+// no longer rescaled operand by operand (26 DMUL per lane and frame on the pipe the DMMAs need) -- the product runs on the
+// raw vector and the result is scaled once; four accumulator pairs instead of two shorten the dependent DMMA chains; the
+// outlier machinery (second copy of the vector, two extra reductions) is compiled out when the rule is off (OUTL = false:
+// discrete models by default, caller tables always); the backward kernel reads its B fragments from shared memory when
+// they do not fit the register file next to the xi accumulators (BSM, NT = 13: no spills).
+// ================================================================================================
+constexpr int WS = 2;                                       // chain sets per block
+
+template <int NT, bool OUTL>
+constexpr size_t wide2_forward_smem()
+{
+    return sizeof(double) * ((size_t)WS * 2 * PCH * WideGeom<NT>::NPS * (OUTL ? 2 : 1) + (size_t)WS * 2 * (OUTL ? 3 : 1) * NT * PCH);
+}
+
+template <int EM, int NT, bool OUTL>
+__global__ void WIDE_KERNEL_ATTR(NT) k_forward_wide2(const FwdArgs a)
+{
+    constexpr int KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS, NR = OUTL ? 3 : 1, ROW = PCH * NPS;
+    extern __shared__ double wsm[];
+    double* const Sx = wsm;                                 // [WS][2][ROW]   the frame's vector with the densities ...
+    double* const Sd = Sx + WS * 2 * ROW;                   // [WS][2][ROW]   ... and with all densities set to one (OUTL only)
+    double* const red = Sd + (OUTL ? WS * 2 * ROW : 0);     // [WS][2][NR][NT][PCH] per tile and chain: sum of Sx (, sum of Sd, any density != 0)
+    const int N = a.N;
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, w = threadIdx.x >> 5;
+    const unsigned qmask = 0xFu << (4 * g);
+    const int s0 = 8 * w + 2 * q;
+    const bool ok0 = s0 < N, ok1 = s0 + 1 < N;
+    // state pairs are 16-byte aligned in (rows, N) arrays when N is even and the arrays are
+    const bool pair_ok = ((N & 1) == 0) && (((reinterpret_cast<uintptr_t>(a.alpha) | reinterpret_cast<uintptr_t>(a.hand_end) |
+                                              reinterpret_cast<uintptr_t>(a.hand_used)) & 15u) == 0);
+    double Bf[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const int k = 4 * ks + q, col = 8 * w + g;
+        Bf[ks] = (k < N && col < N) ? a.A[k * N + col] : 0.0;
+    }
+    double mu[2] = {0.0, 0.0}, isg[2] = {1.0, 1.0}, lnrm[2] = {0.0, 0.0};
+    if (EM == EM_GAUSS) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (s0 + r < N) {
+                const double sg = a.em.sigma[s0 + r];
+                mu[r] = a.em.mu[s0 + r];
+                isg[r] = 1.0 / (sqrt(2.0) * sg);
+                lnrm[r] = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * sg));
+            }
+    }
+    auto store2 = [&](double* dst, double x0, double x1) {   // dst -> element s0 of a (rows, N) row
+        if (pair_ok && ok1) *reinterpret_cast<double2*>(dst) = make_double2(x0, x1);
+        else { if (ok0) dst[0] = x0; if (ok1) dst[1] = x1; }
+    };
+
+    for (int base = blockIdx.x * (WS * PCH); base < a.ch.n; base += gridDim.x * (WS * PCH)) {
+        bool have[WS];
+        int c[WS], t0[WS], tstart[WS], mode[WS], tend[WS], maxpre[WS];
+        long long trow[WS];
+        int total = 0;
+#pragma unroll
+        for (int z = 0; z < WS; ++z) {
+            const int idx = base + z * PCH + g;
+            have[z] = idx < a.ch.n;
+            c[z] = -1; t0[z] = 0; tstart[z] = 0; mode[z] = 0; trow[z] = 0;   // mode 0: pi, 1: uniform warm-up, 2: exact vector
+            int len = 0;
+            if (have[z]) {
+                c[z] = a.ch.list ? a.ch.list[idx] : idx;
+                len = a.ch.len[c[z]];
+                t0[z] = a.ch.t0[c[z]];
+                trow[z] = a.ch.row0[c[z]] - t0[z];
+                if (t0[z] == 0) { tstart[z] = 0; mode[z] = 0; }
+                else if (a.ch.exact) { tstart[z] = t0[z] - 1; mode[z] = 2; }
+                else { tstart[z] = max(0, t0[z] - (a.ch.warmv ? a.ch.warmv[c[z]] : a.ch.warm)); mode[z] = (tstart[z] == 0) ? 0 : 1; }
+            }
+            tend[z] = t0[z] + len;
+            maxpre[z] = __reduce_max_sync(FULL, have[z] ? (t0[z] - tstart[z]) : 0);
+            total = max(total, maxpre[z] + __reduce_max_sync(FULL, len));
+        }
+        for (int k = threadIdx.x; k < WS * 2 * ROW; k += blockDim.x) { Sx[k] = 0.0; if (OUTL) Sd[k] = 0.0; }
+        for (int k = threadIdx.x; k < WS * 2 * NR * NT * PCH; k += blockDim.x) red[k] = 0.0;
+        __syncthreads();
+
+        double vec[WS][2], v[WS][2], dd[WS][2], o_next[WS], pn[WS][2];
+        int symA[WS];
+        LogAcc acc[WS];
+        auto frame_row = [&](int z, int s) -> long long {
+            int t = t0[z] - maxpre[z] + s;
+            t = min(max(t, tstart[z] + (mode[z] == 2 ? 1 : 0)), tend[z] - 1);
+            return trow[z] + t;
+        };
+#pragma unroll
+        for (int z = 0; z < WS; ++z) {
+            vec[z][0] = vec[z][1] = v[z][0] = v[z][1] = dd[z][0] = dd[z][1] = 0.0;
+            o_next[z] = 0.0; pn[z][0] = pn[z][1] = 0.0; symA[z] = 0;
+            if (have[z] && mode[z] == 2) {
+                if (ok0) vec[z][0] = a.hand_end[(long long)(c[z] - 1) * N + s0];
+                if (ok1) vec[z][1] = a.hand_end[(long long)(c[z] - 1) * N + s0 + 1];
+            }
+            if (have[z]) {
+                if (EM == EM_GAUSS) o_next[z] = a.em.obs[frame_row(z, 0)];
+                if (EM == EM_DISC) {
+                    wide_table2<EM>(a.em, 0, a.em.sym[frame_row(z, 0)], N, s0, ok0, ok1, pn[z]);
+                    symA[z] = a.em.sym[frame_row(z, 1)];
+                }
+                if (EM == EM_POBS) wide_table2<EM>(a.em, frame_row(z, 0), 0, N, s0, ok0, ok1, pn[z]);
+            }
+        }
+
+        for (int s = 0; s <= total; ++s) {
+            const int cur = s & 1, prev = cur ^ 1;
+            double rc[WS];
+            bool use_d[WS];
+            // ---- finish frame s-1 of both sets: the chains' sums are complete, normalise, store
+#pragma unroll
+            for (int z = 0; z < WS; ++z) {
+                rc[z] = 1.0;
+                use_d[z] = false;
+                if (s > 0) {
+                    const int tp = t0[z] - maxpre[z] + s - 1;
+                    const bool onp = have[z] && tp >= tstart[z] && tp < tend[z];
+                    const double* rp = red + (size_t)(z * 2 + prev) * NR * NT * PCH;
+                    double cs = 0.0, cd = 0.0, nz = 0.0;
+#pragma unroll
+                    for (int w2 = 0; w2 < NT; w2 += 4)
+                        if (w2 + q < NT) {
+                            cs += rp[(w2 + q) * PCH + g];
+                            if (OUTL) { cd += rp[(NT + w2 + q) * PCH + g]; nz += rp[(2 * NT + w2 + q) * PCH + g]; }
+                        }
+                    cs = quad_sum(cs);
+                    if (OUTL) {
+                        cd = quad_sum(cd);
+                        nz = quad_sum(nz);
+                        if (a.em.ignore_outliers && onp && nz == 0.0) { use_d[z] = true; cs = cd; }   // outputmodel.py:126-130
+                    }
+                    rc[z] = (cs != 0.0) ? 1.0 / cs : 1.0;   // _hidden.c:31-34, :58-61: divide iff c != 0
+                    if (onp) {
+                        const double out0 = (use_d[z] ? dd[z][0] : v[z][0]) * rc[z], out1 = (use_d[z] ? dd[z][1] : v[z][1]) * rc[z];
+                        if (tp >= t0[z]) {
+                            if (a.alpha) store2(a.alpha + (trow[z] + tp) * N + s0, out0, out1);
+                            if (w == 0 && q == 0) acc[z].add(cs);
+                            if (tp == tend[z] - 1) store2(a.hand_end + (long long)c[z] * N + s0, out0, out1);
+                        } else if (tp == t0[z] - 1) {
+                            store2(a.hand_used + (long long)c[z] * N + s0, out0, out1);
+                        }
+                    }
+                }
+            }
+            if (s == total) break;
+
+            // ---- frame s of both sets
+#pragma unroll
+            for (int z = 0; z < WS; ++z) {
+                const int t = t0[z] - maxpre[z] + s;
+                const bool on = have[z] && t >= tstart[z] && t < tend[z];
+                const bool init = on && t == tstart[z];
+                double p[2] = {0.0, 0.0};
+                if (have[z]) {
+                    if (EM == EM_GAUSS) {
+                        const double o = o_next[z];
+                        o_next[z] = a.em.obs[frame_row(z, s + 1)];
+                        wide_gauss2(o, mu, isg, lnrm, ok0, ok1, p);
+                    } else {
+                        p[0] = pn[z][0]; p[1] = pn[z][1];
+                        if (EM == EM_DISC) {
+                            wide_table2<EM>(a.em, 0, symA[z], N, s0, ok0, ok1, pn[z]);
+                            symA[z] = a.em.sym[frame_row(z, s + 2)];
+                        } else {
+                            wide_table2<EM>(a.em, frame_row(z, s + 1), 0, N, s0, ok0, ok1, pn[z]);
+                        }
+                    }
+                }
+                const double* src = ((OUTL && use_d[z]) ? Sd : Sx) + (size_t)(z * 2 + prev) * ROW + g * NPS;
+                double e[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};   // four accumulator pairs: short dependent DMMA chains
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) dmma(e[ks & 3][0], e[ks & 3][1], src[4 * ks + q], Bf[ks]);
+                const double d0 = ((e[0][0] + e[1][0]) + (e[2][0] + e[3][0])) * rc[z];   // the raw vector's product, scaled once
+                const double d1 = ((e[0][1] + e[1][1]) + (e[2][1] + e[3][1])) * rc[z];
+                bool nzflag = (p[0] != 0.0) || (p[1] != 0.0);
+                if (init) {
+                    if (mode[z] == 0) { dd[z][0] = ok0 ? a.pi[s0] : 0.0; dd[z][1] = ok1 ? a.pi[s0 + 1] : 0.0; }
+                    else if (mode[z] == 1) { dd[z][0] = ok0 ? 1.0 : 0.0; dd[z][1] = ok1 ? 1.0 : 0.0; }
+                    else { dd[z][0] = vec[z][0]; dd[z][1] = vec[z][1]; }
+                    if (mode[z] == 2) { v[z][0] = vec[z][0]; v[z][1] = vec[z][1]; nzflag = true; }
+                    else { v[z][0] = dd[z][0] * p[0]; v[z][1] = dd[z][1] * p[1]; }
+                } else if (on) {
+                    dd[z][0] = d0; dd[z][1] = d1;
+                    v[z][0] = d0 * p[0]; v[z][1] = d1 * p[1];
+                } else {
+                    dd[z][0] = dd[z][1] = v[z][0] = v[z][1] = 0.0;
+                    nzflag = false;
+                }
+                const double pv = quad_sum(v[z][0] + v[z][1]);
+                *reinterpret_cast<double2*>(Sx + (size_t)(z * 2 + cur) * ROW + g * NPS + s0) = make_double2(v[z][0], v[z][1]);
+                double* rp = red + (size_t)(z * 2 + cur) * NR * NT * PCH;
+                if (OUTL) {
+                    const double pd = quad_sum(dd[z][0] + dd[z][1]);
+                    const bool nzq = (__ballot_sync(FULL, nzflag) & qmask) != 0u;
+                    *reinterpret_cast<double2*>(Sd + (size_t)(z * 2 + cur) * ROW + g * NPS + s0) = make_double2(dd[z][0], dd[z][1]);
+                    if (q == 0) { rp[(NT + w) * PCH + g] = pd; rp[(2 * NT + w) * PCH + g] = nzq ? 1.0 : 0.0; }
+                }
+                if (q == 0) rp[w * PCH + g] = pv;
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int z = 0; z < WS; ++z)
+            if (have[z] && w == 0 && q == 0) a.chain_ll[c[z]] = acc[z].value();
+        __syncthreads();                                    // the buffers are cleared for the next chain groups
+    }
+}
+
+template <int NT, bool OUTL, bool BSM>
+constexpr size_t wide2_backward_smem()
+{
+    return sizeof(double) * ((size_t)WS * 2 * PCH * WideGeom<NT>::NPS * (OUTL ? 2 : 1)       // Sw (, Sb)
+                             + (size_t)WS * PCH * WideGeom<NT>::NPS                          // Su
+                             + (size_t)WS * 2 * NT * PCH + (OUTL ? (size_t)WS * NT * PCH : 0)   // red (, redn)
+                             + (BSM ? (size_t)NT * WideGeom<NT>::KS * 32 : 0));              // B fragments
+}
+
+// Backward + statistics, two chain sets per block.  Per step and set (frame f downwards): publish w = p_f bn (and bn for
+// the outlier rule) -- barrier 1 -- xi product of the previous step, d = A w for the warp's tile, partial sums of
+// alpha_{f-1} d and of d -- barrier 2 -- S and sum d complete: u = alpha_{f-1} / S published, gamma and moments, bn = d / sum d.
+template <int EM, int NT, bool OUTL, bool BSM>
+__global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide2(const BwdArgs a)
+{
+    constexpr int KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS, ROW = PCH * NPS;
+    extern __shared__ double wsm[];
+    double* const Sw = wsm;                                 // [WS][2][ROW]
+    double* const Sb = Sw + WS * 2 * ROW;                   // [WS][2][ROW]  (OUTL only)
+    double* const Su = Sb + (OUTL ? WS * 2 * ROW : 0);      // [WS][ROW]
+    double* const red = Su + WS * ROW;                      // [WS][2][NT][PCH] partial S, partial sum of d
+    double* const redn = red + WS * 2 * NT * PCH;           // [WS][NT][PCH]    any density != 0 (OUTL only)
+    double* const Bsm = redn + (OUTL ? WS * NT * PCH : 0);  // [NT][KS][32]     B fragments (BSM only)
+    const int N = a.N;
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, w = threadIdx.x >> 5;
+    const unsigned qmask = 0xFu << (4 * g);
+    const int s0 = 8 * w + 2 * q;
+    const bool ok0 = s0 < N, ok1 = s0 + 1 < N;
+    const bool pair_ok = ((N & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.alpha) & 15u) == 0);
+    // d = A w: contraction index j = 4 ks + q, output i = 8 w + g
+    double Bt[BSM ? 1 : KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const int j = 4 * ks + q, i = 8 * w + g;
+        const double x = (i < N && j < N) ? a.A[i * N + j] : 0.0;
+        if (BSM) Bsm[(w * KS + ks) * 32 + lane] = x;
+        else Bt[BSM ? 0 : ks] = x;
+    }
+    const double* const Bw = Bsm + (size_t)w * KS * 32 + lane;
+    double X[NT][2];
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) { X[mt][0] = 0.0; X[mt][1] = 0.0; }
+    double mu[2] = {0.0, 0.0}, isg[2] = {1.0, 1.0}, lnrm[2] = {0.0, 0.0};
+    if (EM == EM_GAUSS) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (s0 + r < N) {
+                const double sg = a.em.sigma[s0 + r];
+                mu[r] = a.em.mu[s0 + r];
+                isg[r] = 1.0 / (sqrt(2.0) * sg);
+                lnrm[r] = log(1.0 / (sqrt(2.0 * 3.14159265358979323846) * sg));
+            }
+    }
+    double st_g[2] = {0.0, 0.0}, st_gd[2] = {0.0, 0.0}, st_gdd[2] = {0.0, 0.0};
+    const long long nstat = (long long)N * N + 4 * N;
+    double* out = a.partials + (long long)blockIdx.x * nstat;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) out[(long long)N * N + j] = 0.0;   // gamma0: atomics below
+    __syncthreads();
+
+    auto load2 = [&](const double* src, double& x0, double& x1) {   // src -> element s0 of a (rows, N) row
+        if (pair_ok && ok1) { const double2 t = *reinterpret_cast<const double2*>(src); x0 = t.x; x1 = t.y; }
+        else { x0 = ok0 ? src[0] : 0.0; x1 = ok1 ? src[1] : 0.0; }
+    };
+    auto xi_product = [&](int z, int buf) {
+        const double* sw = Sw + (size_t)(z * 2 + buf) * ROW;
+        const double* su = Su + (size_t)z * ROW;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const double wb = sw[(4 * kk + q) * NPS + 8 * w + g];
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt) dmma(X[mt][0], X[mt][1], su[(4 * kk + q) * NPS + 8 * mt + g], wb);
+        }
+    };
+
+    for (int base = blockIdx.x * (WS * PCH); base < a.ch.n; base += gridDim.x * (WS * PCH)) {
+        bool have[WS], virt[WS], pending_xi[WS];
+        int c[WS], t0[WS], T[WS], e[WS], fstart[WS], mode[WS], maxpre[WS];
+        long long trow[WS];
+        int total = 0;
+#pragma unroll
+        for (int z = 0; z < WS; ++z) {
+            const int idx = base + z * PCH + g;
+            have[z] = idx < a.ch.n;
+            c[z] = -1; t0[z] = 0; T[z] = 0; e[z] = 0; fstart[z] = 0; mode[z] = 0; virt[z] = false; trow[z] = 0;
+            pending_xi[z] = false;
+            if (have[z]) {
+                c[z] = a.ch.list ? a.ch.list[idx] : idx;
+                const int len = a.ch.len[c[z]];
+                t0[z] = a.ch.t0[c[z]];
+                T[z] = a.ch.T[c[z]];
+                trow[z] = a.ch.row0[c[z]] - t0[z];
+                e[z] = t0[z] + len;
+                if (e[z] >= T[z]) { virt[z] = true; fstart[z] = T[z]; }
+                else if (a.ch.exact) { fstart[z] = e[z]; mode[z] = 2; }
+                else { fstart[z] = min(T[z] - 1, e[z] + (a.ch.warmv ? a.ch.warmv[c[z]] : a.ch.warm) - 1); }
+            }
+            maxpre[z] = __reduce_max_sync(FULL, have[z] ? (fstart[z] - (e[z] - 1)) : 0);
+            total = max(total, maxpre[z] + __reduce_max_sync(FULL, have[z] ? (e[z] - (t0[z] + 1)) : 0));
+        }
+        for (int k = threadIdx.x; k < WS * 2 * ROW; k += blockDim.x) { Sw[k] = 0.0; if (OUTL) Sb[k] = 0.0; }
+        for (int k = threadIdx.x; k < WS * ROW; k += blockDim.x) Su[k] = 0.0;
+        __syncthreads();
+
+        double bn[WS][2], o_next[WS], al_next[WS][2], pn[WS][2];
+        int symA[WS];
+        auto frame_of = [&](int z, int s) -> int { return (e[z] - 1) + maxpre[z] - s; };
+        auto em_row = [&](int z, int s) -> long long { return trow[z] + min(max(frame_of(z, s), t0[z]), T[z] - 1); };
+        auto al_row = [&](int z, int s) -> long long { return trow[z] + min(max(frame_of(z, s) - 1, t0[z]), e[z] - 1); };
+#pragma unroll
+        for (int z = 0; z < WS; ++z) {
+            bn[z][0] = ok0 ? 1.0 / N : 0.0;                  // beta_{T-1} = 1/N (_hidden.c:76-77); warm-up start
+            bn[z][1] = ok1 ? 1.0 / N : 0.0;
+            o_next[z] = 0.0; al_next[z][0] = al_next[z][1] = 0.0; pn[z][0] = pn[z][1] = 0.0; symA[z] = 0;
+            if (have[z] && mode[z] == 2) {
+                if (ok0) bn[z][0] = a.hand_end[(long long)(c[z] + 1) * N + s0];
+                if (ok1) bn[z][1] = a.hand_end[(long long)(c[z] + 1) * N + s0 + 1];
+            }
+            if (have[z]) {
+                if (EM == EM_GAUSS) o_next[z] = a.em.obs[em_row(z, 0)];
+                if (EM == EM_DISC) {
+                    wide_table2<EM>(a.em, 0, a.em.sym[em_row(z, 0)], N, s0, ok0, ok1, pn[z]);
+                    symA[z] = a.em.sym[em_row(z, 1)];
+                }
+                if (EM == EM_POBS) wide_table2<EM>(a.em, em_row(z, 0), 0, N, s0, ok0, ok1, pn[z]);
+                load2(a.alpha + al_row(z, 0) * N + s0, al_next[z][0], al_next[z][1]);
+            }
+        }
+
+        for (int s = 0; s < total; ++s) {
+            const int cur = s & 1;
+            int f[WS], sym_emit[WS];
+            bool on[WS], isvirt[WS], act[WS];
+            double al[WS][2], wv[WS][2], d[WS][2], gq[WS][2];
+            // ---- publish w = p bn (and bn) of both sets
+#pragma unroll
+            for (int z = 0; z < WS; ++z) {
+                f[z] = frame_of(z, s);
+                on[z] = have[z] && f[z] <= fstart[z] && f[z] >= t0[z] + 1;
+                isvirt[z] = on[z] && virt[z] && f[z] == T[z];
+                al[z][0] = al_next[z][0]; al[z][1] = al_next[z][1];
+                double p[2] = {0.0, 0.0};
+                sym_emit[z] = 0;                            // symbol of frame f-1, the frame this step emits
+                if (have[z]) {
+                    load2(a.alpha + al_row(z, s + 1) * N + s0, al_next[z][0], al_next[z][1]);
+                    if (EM == EM_GAUSS) {
+                        const double o = o_next[z];
+                        o_next[z] = a.em.obs[em_row(z, s + 1)];   // frame f-1: also the emitted frame's observation
+                        wide_gauss2(o, mu, isg, lnrm, ok0, ok1, p);
+                    } else {
+                        p[0] = pn[z][0]; p[1] = pn[z][1];
+                        if (EM == EM_DISC) {
+                            sym_emit[z] = symA[z];
+                            wide_table2<EM>(a.em, 0, symA[z], N, s0, ok0, ok1, pn[z]);
+                            symA[z] = a.em.sym[em_row(z, s + 2)];
+                        } else {
+                            wide_table2<EM>(a.em, em_row(z, s + 1), 0, N, s0, ok0, ok1, pn[z]);
+                        }
+                    }
+                }
+                act[z] = on[z] && !isvirt[z];
+                wv[z][0] = act[z] ? p[0] * bn[z][0] : 0.0;
+                wv[z][1] = act[z] ? p[1] * bn[z][1] : 0.0;
+                *reinterpret_cast<double2*>(Sw + (size_t)(z * 2 + cur) * ROW + g * NPS + s0) = make_double2(wv[z][0], wv[z][1]);
+                if (OUTL) {
+                    const bool nzq = (__ballot_sync(FULL, (p[0] != 0.0) || (p[1] != 0.0)) & qmask) != 0u;
+                    *reinterpret_cast<double2*>(Sb + (size_t)(z * 2 + cur) * ROW + g * NPS + s0) =
+                        make_double2(act[z] ? bn[z][0] : 0.0, act[z] ? bn[z][1] : 0.0);
+                    if (q == 0) redn[(z * NT + w) * PCH + g] = nzq ? 1.0 : 0.0;
+                }
+            }
+            __syncthreads();                                // ---- barrier 1
+
+#pragma unroll
+            for (int z = 0; z < WS; ++z)
+                if (pending_xi[z]) xi_product(z, cur ^ 1);
+
+            // ---- d = A w for both sets with one pass over the B fragments
+            bool use_b[WS];
+            const double* src[WS];
+#pragma unroll
+            for (int z = 0; z < WS; ++z) {
+                use_b[z] = false;
+                if (OUTL) {
+                    double nz = 0.0;
+#pragma unroll
+                    for (int w2 = 0; w2 < NT; w2 += 4)
+                        if (w2 + q < NT) nz += redn[(z * NT + w2 + q) * PCH + g];
+                    nz = quad_sum(nz);
+                    use_b[z] = a.em.ignore_outliers && act[z] && nz == 0.0;   // outputmodel.py:126-130
+                }
+                src[z] = ((OUTL && use_b[z]) ? Sb : Sw) + (size_t)(z * 2 + cur) * ROW + g * NPS;
+            }
+            double acc[WS][2][2];
+#pragma unroll
+            for (int z = 0; z < WS; ++z) { acc[z][0][0] = acc[z][0][1] = acc[z][1][0] = acc[z][1][1] = 0.0; }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const double b = BSM ? Bw[ks * 32] : Bt[BSM ? 0 : ks];
+#pragma unroll
+                for (int z = 0; z < WS; ++z) dmma(acc[z][ks & 1][0], acc[z][ks & 1][1], src[z][4 * ks + q], b);
+            }
+#pragma unroll
+            for (int z = 0; z < WS; ++z) {
+                d[z][0] = acc[z][0][0] + acc[z][1][0];
+                d[z][1] = acc[z][0][1] + acc[z][1][1];
+                if (isvirt[z]) { d[z][0] = ok0 ? 1.0 : 0.0; d[z][1] = ok1 ? 1.0 : 0.0; }
+                if (OUTL && use_b[z]) {                      // the xi product of the next step reads W from Sw
+                    wv[z][0] = act[z] ? bn[z][0] : 0.0; wv[z][1] = act[z] ? bn[z][1] : 0.0;
+                    *reinterpret_cast<double2*>(Sw + (size_t)(z * 2 + cur) * ROW + g * NPS + s0) = make_double2(wv[z][0], wv[z][1]);
+                }
+                if (act[z] && f[z] == e[z]) {
+                    if (ok0) a.hand_used[(long long)c[z] * N + s0] = bn[z][0];
+                    if (ok1) a.hand_used[(long long)c[z] * N + s0 + 1] = bn[z][1];
+                }
+                const bool emit = on[z] && (f[z] - 1) < e[z];
+                gq[z][0] = emit ? al[z][0] * d[z][0] : 0.0;
+                gq[z][1] = emit ? al[z][1] * d[z][1] : 0.0;
+                const double pS = quad_sum(gq[z][0] + gq[z][1]), pb = quad_sum(d[z][0] + d[z][1]);
+                if (q == 0) { red[((z * 2 + 0) * NT + w) * PCH + g] = pS; red[((z * 2 + 1) * NT + w) * PCH + g] = pb; }
+            }
+            __syncthreads();                                // ---- barrier 2
+
+#pragma unroll
+            for (int z = 0; z < WS; ++z) {
+                const bool emit = on[z] && (f[z] - 1) < e[z];
+                const bool xi = emit && !isvirt[z];
+                double S = 0.0, sbn = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < NT; w2 += 4)
+                    if (w2 + q < NT) { S += red[((z * 2 + 0) * NT + w2 + q) * PCH + g]; sbn += red[((z * 2 + 1) * NT + w2 + q) * PCH + g]; }
+                S = quad_sum(S);
+                sbn = quad_sum(sbn);
+                const double rS = 1.0 / S;
+                *reinterpret_cast<double2*>(Su + (size_t)z * ROW + g * NPS + s0) =
+                    make_double2(xi ? al[z][0] * rS : 0.0, xi ? al[z][1] * rS : 0.0);
+                pending_xi[z] = __any_sync(FULL, xi);
+                if (emit) {
+                    const long long orow = trow[z] + (f[z] - 1);
+                    const double gam[2] = {gq[z][0] * rS, gq[z][1] * rS};
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        if (s0 + r >= N) continue;
+                        st_g[r] += gam[r];
+                        if (f[z] - 1 == 0) atomicAdd(out + (long long)N * N + s0 + r, gam[r]);
+                        if (EM == EM_GAUSS) {
+                            const double dv = o_next[z] - mu[r];
+                            st_gd[r] = fma(gam[r], dv, st_gd[r]);
+                            st_gdd[r] = fma(gam[r], dv * dv, st_gdd[r]);
+                        }
+                        if (EM == EM_DISC && a.Bnum) atomicAdd(a.Bnum + (long long)(s0 + r) * a.em.M + sym_emit[z], gam[r]);
+                        if (a.gamma) a.gamma[orow * N + s0 + r] = gam[r];
+                    }
+                    if (f[z] - 1 == t0[z] && t0[z] > 0) {
+                        const double r2 = (sbn != 0.0) ? 1.0 / sbn : 1.0;
+                        if (ok0) a.hand_end[(long long)c[z] * N + s0] = d[z][0] * r2;
+                        if (ok1) a.hand_end[(long long)c[z] * N + s0 + 1] = d[z][1] * r2;
+                    }
+                }
+                if (on[z]) {
+                    const double r2 = (sbn != 0.0) ? 1.0 / sbn : 1.0;          // _hidden.c:104-107
+                    bn[z][0] = d[z][0] * r2;
+                    bn[z][1] = d[z][1] * r2;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int z = 0; z < WS; ++z)
+            if (pending_xi[z]) xi_product(z, (total - 1) & 1);
+        __syncthreads();                                    // the buffers are cleared for the next chain groups
+    }
+
+    // ---- the block's row of partial statistics: [X (N*N) | gamma0 (N) | sum gamma | sum gamma d | sum gamma d^2]
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+        const int i = 8 * mt + g;
+        if (i < N) {
+            if (ok0) out[(long long)i * N + s0] = X[mt][0];
+            if (ok1) out[(long long)i * N + s0 + 1] = X[mt][1];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+            st_g[r] += __shfl_xor_sync(FULL, st_g[r], off);
+            st_gd[r] += __shfl_xor_sync(FULL, st_gd[r], off);
+            st_gdd[r] += __shfl_xor_sync(FULL, st_gdd[r], off);
+        }
+        if (g == 0 && s0 + r < N) {
+            out[(long long)N * N + N + s0 + r] = st_g[r];
+            out[(long long)N * N + 2 * N + s0 + r] = st_gd[r];
+            out[(long long)N * N + 3 * N + s0 + r] = st_gdd[r];
+        }
+    }
+}
+
+// ================================================================================================
 // Viterbi for 32 < N <= 104 with the transition-matrix column in registers (same opt-in as the panel kernels).
 // k_viterbi_team walks its two N-long loops (first-maximum scan, sequential row sum) one shared-memory round trip at a
 // time: ~6000 cycles per frame at N = 100 (C4: 4.27 s for 4096 x 1e5 frames).  Here thread j keeps A[:, j] in registers, the
@@ -1330,16 +1844,39 @@ int wide_tiles(int N) { return (N <= 16) ? 0 : (N <= 32 ? 4 : (N <= 64 ? 8 : (N 
 #define WIDE_DISPATCH(NTV, CALL4, CALL8, CALL13) \
     do { if ((NTV) == 4) { CALL4; } else if ((NTV) == 8) { CALL8; } else { CALL13; } } while (0)
 
+// chains per block: the two-set kernels (wide2) serve NT >= 8, the one-set kernels NT = 4
+int wide_cpb(int NT) { return NT >= 8 ? WS * PCH : PCH; }
+
+template <typename K>
+int wide2_prepare(K kernel, size_t smem)
+{
+    static bool done = false;                               // one static per kernel instantiation
+    if (!done) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            bhmm_set_error(BHMM_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for a wide2 kernel");
+            return BHMM_ERR_CUDA;
+        }
+        done = true;
+    }
+    return BHMM_OK;
+}
+
 int wide_blocks_per_sm(int NT)
 {
     static int per[17] = {0};
     if (per[NT] == 0) {
         int v = 0;
         cudaError_t e = cudaErrorUnknown;
-        WIDE_DISPATCH(NT,
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 4>, 4 * 32, 0),
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 8>, 8 * 32, 0),
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 13>, 13 * 32, 0));
+        if (NT == 4) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 4>, 4 * 32, 0);
+        else if (NT == 8) {
+            if (wide2_prepare(k_backward_stats_wide2<EM_GAUSS, 8, true, false>, wide2_backward_smem<8, true, false>()) == BHMM_OK)
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide2<EM_GAUSS, 8, true, false>, 8 * 32,
+                                                                  wide2_backward_smem<8, true, false>());
+        } else {
+            if (wide2_prepare(k_backward_stats_wide2<EM_GAUSS, 13, true, true>, wide2_backward_smem<13, true, true>()) == BHMM_OK)
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide2<EM_GAUSS, 13, true, true>, 13 * 32,
+                                                                  wide2_backward_smem<13, true, true>());
+        }
         per[NT] = (e == cudaSuccess && v > 0) ? v : 1;
     }
     return per[NT];
@@ -1347,29 +1884,50 @@ int wide_blocks_per_sm(int NT)
 
 int wide_blocks(int NT, int n_chains)
 {
-    const long long groups = ((long long)n_chains + PCH - 1) / PCH;
+    const int cpb = wide_cpb(NT);
+    const long long groups = ((long long)n_chains + cpb - 1) / cpb;
     const long long cap = (long long)panel_sms() * wide_blocks_per_sm(NT);
     return (int)std::max(1LL, std::min(groups, cap));
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+template <int EM, int NT, bool OUTL>
+int launch_forward_wide2(const FwdArgs& a, int grid, cudaStream_t st)
+{
+    constexpr size_t smem = wide2_forward_smem<NT, OUTL>();
+    { const int rc_ = wide2_prepare(k_forward_wide2<EM, NT, OUTL>, smem); if (rc_ != BHMM_OK) return rc_; }
+    k_forward_wide2<EM, NT, OUTL><<<grid, NT * 32, smem, st>>>(a);
+    return BHMM_OK;
+}
+
 template <int EM>
 int launch_forward_wide_em(const FwdArgs& a, int NT, cudaStream_t st)
 {
     const int grid = wide_blocks(NT, a.ch.n);
-    WIDE_DISPATCH(NT, (k_forward_wide<EM, 4><<<grid, 4 * 32, 0, st>>>(a)), (k_forward_wide<EM, 8><<<grid, 8 * 32, 0, st>>>(a)),
-                  (k_forward_wide<EM, 13><<<grid, 13 * 32, 0, st>>>(a)));
+    if (NT == 4) { k_forward_wide<EM, 4><<<grid, 4 * 32, 0, st>>>(a); return BHMM_OK; }
+    const bool outl = (EM != EM_POBS) && a.em.ignore_outliers;
+    if (NT == 8) return outl ? launch_forward_wide2<EM, 8, EM != EM_POBS>(a, grid, st) : launch_forward_wide2<EM, 8, false>(a, grid, st);
+    return outl ? launch_forward_wide2<EM, 13, EM != EM_POBS>(a, grid, st) : launch_forward_wide2<EM, 13, false>(a, grid, st);
+}
+
+template <int EM, int NT, bool OUTL>
+int launch_backward_wide2(const BwdArgs& a, cudaStream_t st)
+{
+    constexpr bool BSM = NT > 8;                            // NT = 13: B fragments + xi accumulators exceed 128 registers
+    constexpr size_t smem = wide2_backward_smem<NT, OUTL, BSM>();
+    { const int rc_ = wide2_prepare(k_backward_stats_wide2<EM, NT, OUTL, BSM>, smem); if (rc_ != BHMM_OK) return rc_; }
+    k_backward_stats_wide2<EM, NT, OUTL, BSM><<<a.grid, NT * 32, smem, st>>>(a);
     return BHMM_OK;
 }
 
 template <int EM>
 int launch_backward_wide_em(const BwdArgs& a, int NT, cudaStream_t st)
 {
-    WIDE_DISPATCH(NT, (k_backward_stats_wide<EM, 4><<<a.grid, 4 * 32, 0, st>>>(a)),
-                  (k_backward_stats_wide<EM, 8><<<a.grid, 8 * 32, 0, st>>>(a)),
-                  (k_backward_stats_wide<EM, 13><<<a.grid, 13 * 32, 0, st>>>(a)));
-    return BHMM_OK;
+    if (NT == 4) { k_backward_stats_wide<EM, 4><<<a.grid, 4 * 32, 0, st>>>(a); return BHMM_OK; }
+    const bool outl = (EM != EM_POBS) && a.em.ignore_outliers;
+    if (NT == 8) return outl ? launch_backward_wide2<EM, 8, EM != EM_POBS>(a, st) : launch_backward_wide2<EM, 8, false>(a, st);
+    return outl ? launch_backward_wide2<EM, 13, EM != EM_POBS>(a, st) : launch_backward_wide2<EM, 13, false>(a, st);
 }
 #endif   // PANEL_HOST_NO_LAUNCHERS
 
@@ -1396,7 +1954,7 @@ bool panel_enabled(int N) { return panel_mode() > 0 && wide_tiles(N) > 0; }
 void panel_shape(int N, int* threads, int* chains_per_row)
 {
     *threads = use_panel32(N) ? PW * 32 : wide_tiles(N) * 32;
-    *chains_per_row = PCH;
+    *chains_per_row = use_panel32(N) ? PCH : wide_cpb(wide_tiles(N));
 }
 
 int panel_stats_rows(int N, int n_chains)
