@@ -16,6 +16,7 @@ struct bhmm_b200_batch {
     long long rows = 0;
     std::vector<long long> offsets;
     int chunk = 0, warm_f = 0, warm_b = 0, warm_min = 32;
+    int req_chunk = 0, req_warm = 0;   // what the caller asked for (0 = automatic); kept for re-planning
     bool lane = false;          // small-N fast path (lane_kernels.cuh) instead of the team family
     bool no_alpha = false;      // Viterbi-only batch: no (rows, N) forward variables in the workspace
     double* d_g0buf = nullptr;
@@ -124,6 +125,8 @@ int batch_carve(bhmm_b200_batch* b, cudaStream_t st)
 
 void batch_plan(bhmm_b200_batch* b, int chunk, int warm)
 {
+    b->req_chunk = chunk;
+    b->req_warm = warm;
     const int w = warm > 0 ? warm : (b->lane ? auto_warm_lane(b->N) : auto_warm(b->N));
     b->chunk = chunk > 0 ? chunk : (b->lane ? auto_chunk_lane(b->rows, b->N, w) : auto_chunk(b->rows, b->N, w));
     if (chunk <= 0) {
@@ -449,6 +452,16 @@ extern "C" int bhmm_b200_batch_replan(bhmm_b200_batch* b, int chunk, int warm)
 }
 
 extern "C" int bhmm_b200_batch_uses_lane_kernels(const bhmm_b200_batch* b) { return b && b->lane ? 1 : 0; }
+
+extern "C" int bhmm_b200_batch_set_family(bhmm_b200_batch* b, int lane)
+{
+    if (!b) return BHMM_ERR_INVALID;
+    const bool want = lane != 0 && lane_supported(b->N, EM_GAUSS);
+    if (want == b->lane) return BHMM_OK;
+    b->lane = want;
+    batch_plan(b, b->req_chunk, b->req_warm);
+    return BHMM_OK;
+}
 
 extern "C" int bhmm_b200_wave_chains(int N)
 {

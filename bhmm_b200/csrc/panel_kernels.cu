@@ -1049,7 +1049,7 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide(const BwdArgs a)
 // discrete models by default, caller tables always); the backward kernel reads its B fragments from shared memory when
 // they do not fit the register file next to the xi accumulators (BSM, NT = 13: no spills).
 // ================================================================================================
-constexpr int WS = 2;                                       // chain sets per block
+constexpr int WS = 2;                                       // chain sets per block (forward; the backward kernel takes it as a template parameter)
 
 template <int NT, bool OUTL>
 constexpr size_t wide2_forward_smem()
@@ -1252,7 +1252,7 @@ __global__ void WIDE_KERNEL_ATTR(NT) k_forward_wide2(const FwdArgs a)
     }
 }
 
-template <int NT, bool OUTL, bool BSM>
+template <int NT, bool OUTL, bool BSM, int WS>
 constexpr size_t wide2_backward_smem()
 {
     return sizeof(double) * ((size_t)WS * 2 * PCH * WideGeom<NT>::NPS * (OUTL ? 2 : 1)       // Sw (, Sb)
@@ -1264,7 +1264,7 @@ constexpr size_t wide2_backward_smem()
 // Backward + statistics, two chain sets per block.  Per step and set (frame f downwards): publish w = p_f bn (and bn for
 // the outlier rule) -- barrier 1 -- xi product of the previous step, d = A w for the warp's tile, partial sums of
 // alpha_{f-1} d and of d -- barrier 2 -- S and sum d complete: u = alpha_{f-1} / S published, gamma and moments, bn = d / sum d.
-template <int EM, int NT, bool OUTL, bool BSM>
+template <int EM, int NT, bool OUTL, bool BSM, int WS>
 __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide2(const BwdArgs a)
 {
     constexpr int KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS, ROW = PCH * NPS;
@@ -1844,19 +1844,22 @@ int wide_tiles(int N) { return (N <= 16) ? 0 : (N <= 32 ? 4 : (N <= 64 ? 8 : (N 
 #define WIDE_DISPATCH(NTV, CALL4, CALL8, CALL13) \
     do { if ((NTV) == 4) { CALL4; } else if ((NTV) == 8) { CALL8; } else { CALL13; } } while (0)
 
+// chain sets per block of the backward kernel at NT = 13 (128 registers per thread: two sets spill 200-300 bytes per thread,
+// and with 165 KB of the L1 carved out as shared memory the spills go to L2 -- measured: long-scoreboard stalls, no gain)
+#ifndef BWS13
+#define BWS13 1
+#endif
 // chains per block: the two-set kernels (wide2) serve NT >= 8, the one-set kernels NT = 4
 int wide_cpb(int NT) { return NT >= 8 ? WS * PCH : PCH; }
 
+// dynamic shared memory above 48 KB is an opt-in per kernel; set on every launch (a few microseconds: a cache keyed on the
+// function-pointer TYPE -- the first version -- is shared by all instantiations and left most kernels without the attribute)
 template <typename K>
 int wide2_prepare(K kernel, size_t smem)
 {
-    static bool done = false;                               // one static per kernel instantiation
-    if (!done) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            bhmm_set_error(BHMM_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for a wide2 kernel");
-            return BHMM_ERR_CUDA;
-        }
-        done = true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        bhmm_set_error(BHMM_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for a wide2 kernel");
+        return BHMM_ERR_CUDA;
     }
     return BHMM_OK;
 }
@@ -1869,17 +1872,28 @@ int wide_blocks_per_sm(int NT)
         cudaError_t e = cudaErrorUnknown;
         if (NT == 4) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide<EM_GAUSS, 4>, 4 * 32, 0);
         else if (NT == 8) {
-            if (wide2_prepare(k_backward_stats_wide2<EM_GAUSS, 8, true, false>, wide2_backward_smem<8, true, false>()) == BHMM_OK)
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide2<EM_GAUSS, 8, true, false>, 8 * 32,
-                                                                  wide2_backward_smem<8, true, false>());
+            if (wide2_prepare(k_backward_stats_wide2<EM_GAUSS, 8, true, false, 2>, wide2_backward_smem<8, true, false, 2>()) == BHMM_OK)
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide2<EM_GAUSS, 8, true, false, 2>, 8 * 32,
+                                                                  wide2_backward_smem<8, true, false, 2>());
         } else {
-            if (wide2_prepare(k_backward_stats_wide2<EM_GAUSS, 13, true, true>, wide2_backward_smem<13, true, true>()) == BHMM_OK)
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide2<EM_GAUSS, 13, true, true>, 13 * 32,
-                                                                  wide2_backward_smem<13, true, true>());
+            if (wide2_prepare(k_backward_stats_wide2<EM_GAUSS, 13, true, true, BWS13>, wide2_backward_smem<13, true, true, BWS13>()) == BHMM_OK)
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_backward_stats_wide2<EM_GAUSS, 13, true, true, BWS13>, 13 * 32,
+                                                                  wide2_backward_smem<13, true, true, BWS13>());
         }
         per[NT] = (e == cudaSuccess && v > 0) ? v : 1;
     }
     return per[NT];
+}
+
+// chains per block and round of the backward + statistics kernel (its grid is the number of rows of partial statistics)
+int wide_cpb_bwd(int NT) { return NT > 8 ? BWS13 * PCH : wide_cpb(NT); }
+
+int wide_blocks_bwd(int NT, int n_chains)
+{
+    const int cpb = wide_cpb_bwd(NT);
+    const long long groups = ((long long)n_chains + cpb - 1) / cpb;
+    const long long cap = (long long)panel_sms() * wide_blocks_per_sm(NT);
+    return (int)std::max(1LL, std::min(groups, cap));
 }
 
 int wide_blocks(int NT, int n_chains)
@@ -1915,9 +1929,10 @@ template <int EM, int NT, bool OUTL>
 int launch_backward_wide2(const BwdArgs& a, cudaStream_t st)
 {
     constexpr bool BSM = NT > 8;                            // NT = 13: B fragments + xi accumulators exceed 128 registers
-    constexpr size_t smem = wide2_backward_smem<NT, OUTL, BSM>();
-    { const int rc_ = wide2_prepare(k_backward_stats_wide2<EM, NT, OUTL, BSM>, smem); if (rc_ != BHMM_OK) return rc_; }
-    k_backward_stats_wide2<EM, NT, OUTL, BSM><<<a.grid, NT * 32, smem, st>>>(a);
+    constexpr int BWS = NT > 8 ? BWS13 : 2;
+    constexpr size_t smem = wide2_backward_smem<NT, OUTL, BSM, BWS>();
+    { const int rc_ = wide2_prepare(k_backward_stats_wide2<EM, NT, OUTL, BSM, BWS>, smem); if (rc_ != BHMM_OK) return rc_; }
+    k_backward_stats_wide2<EM, NT, OUTL, BSM, BWS><<<a.grid, NT * 32, smem, st>>>(a);
     return BHMM_OK;
 }
 
@@ -1959,7 +1974,7 @@ void panel_shape(int N, int* threads, int* chains_per_row)
 
 int panel_stats_rows(int N, int n_chains)
 {
-    return use_panel32(N) ? panel_blocks(n_chains) * PW : wide_blocks(wide_tiles(N), n_chains);
+    return use_panel32(N) ? panel_blocks(n_chains) * PW : wide_blocks_bwd(wide_tiles(N), n_chains);
 }
 
 // Viterbi with the matrix column in registers: 32 < N <= 104 (N <= 32 keeps the packed one-warp teams)

@@ -272,9 +272,19 @@ class TrajectoryBatch(object):
         if lo < 0 or hi >= int(M):
             raise IndexError('observation symbols span [%d, %d] but the output model has %d symbols' % (lo, hi, int(M)))
 
-    def _require_gaussian(self):
+    def _require_gaussian(self, sigmas=None):
         if self.discrete:
             raise TypeError('this batch holds integer symbols; a Gaussian output model needs float observations')
+        if sigmas is not None and self.N <= 16:
+            # The lane kernels' lazily rescaled recursion has head-room for densities up to 1 / (1e-100 sqrt(2 pi)); a
+            # smaller sigma runs on the team kernels, which normalise every frame like the reference (no limit there,
+            # _gaussian.c:18-20).  The batch returns to its own family with the next ordinary model.
+            tiny = bool(np.any(~(np.asarray(sigmas, dtype=np.float64) >= 1e-100)))
+            want_team = tiny or os.environ.get('BHMM_B200_FAMILY') == 'team'
+            if want_team == self.uses_lane_kernels:
+                check(lib.bhmm_b200_batch_set_family(self._handle, 0 if want_team else 1))
+                if self._shared is None:
+                    self._attach()
 
     # -------------------------------------------------------------------------------------------- E-step
     def estep_gaussian(self, A, pi, means, sigmas, ignore_outliers=True, gamma_out=None):
@@ -282,7 +292,7 @@ class TrajectoryBatch(object):
 
         ``gamma_out``: optional (rows,N) float64 CUDA tensor that receives the state probabilities.
         """
-        self._require_gaussian()
+        self._require_gaussian(sigmas)
         A_, pi_, m_, s_ = f64(A), f64(pi), f64(means), f64(sigmas)
         g = C.c_void_p(gamma_out.data_ptr()) if gamma_out is not None else None
         with self.torch.cuda.device(self.device):
@@ -316,7 +326,7 @@ class TrajectoryBatch(object):
 
     def viterbi_gaussian(self, A, pi, means, sigmas, ignore_outliers=True):
         """Viterbi paths of all trajectories as one concatenated int32 DEVICE tensor."""
-        self._require_gaussian()
+        self._require_gaussian(sigmas)
         A_, pi_, m_, s_ = f64(A), f64(pi), f64(means), f64(sigmas)
         path = self._path_buffer()
         with self.torch.cuda.device(self.device):
@@ -350,7 +360,7 @@ class TrajectoryBatch(object):
         [C (N*N) | n0 (N) | frames per state (N)], float64 [sum o (N) | sum o^2 (N)] (all DEVICE tensors) and the
         log-likelihood of the forward pass.  ``uniforms``: optional (rows,) float64 CUDA tensor, one draw per
         frame (parity with the reference's glibc stream); default is device Philox keyed by (seed, sweep)."""
-        self._require_gaussian()
+        self._require_gaussian(sigmas)
         A_, pi_, m_, s_ = f64(A), f64(pi), f64(means), f64(sigmas)
         path = self._path_buffer()
         counts, sums = self._gibbs_buffers()

@@ -146,6 +146,10 @@ int bhmm_b200_batch_uses_lane_kernels(const bhmm_b200_batch* b);
  * 0 without a device.  Callers that cut a data set into groups (engine.SubBatchedTrajectories) size the groups in multiples
  * of it so that no round of the persistent kernels runs mostly empty. */
 int bhmm_b200_wave_chains(int N);
+/* Switch a batch between the lane kernels (lane != 0; N <= 16 only) and the general-N team / panel kernels, re-plan its
+ * chains and invalidate the workspace layout (query bhmm_b200_batch_workspace_bytes and attach again).  Used for models the
+ * lane kernels refuse (a Gaussian sigma below 1e-100). */
+int bhmm_b200_batch_set_family(bhmm_b200_batch* b, int lane);
 /* Viterbi-only batch: the workspace holds no (rows, N) forward variables -- observations, uint8 back-pointer map and path
  * only (N + 4 + 8 bytes per frame instead of 9 N + 12) -- so that one very long trajectory (C5: 1e9 frames x 32 states = 44 GB)
  * fits one GPU for bhmm_b200_viterbi_*; E-step and sampling calls on such a batch return BHMM_B200_ERR_UNSUPPORTED.  Call
