@@ -129,8 +129,12 @@ int auto_chunk_lane(long long rows, int N, int warm)
     // exactly one wave of resident blocks (occupancy of the register-hungriest lane kernel for this N)
     const long long target = (long long)sms * lane_blocks_per_sm(N, EM_GAUSS) * lane_threads();
     long long c = (rows + target - 1) / target;
-    c = std::max<long long>(c, 2LL * warm);
-    c = std::max<long long>(c, 64);
+    // A step of the lane kernels takes the same time with one resident warp per scheduler as with two (latency bound,
+    // DESIGN.md 5.4), so the time of a pass is (chunk + warm-up) steps whatever the number of chains: a full wave of short
+    // chains beats fewer, longer ones even when the warm-up exceeds the chunk (strong scaling: C3's 1024 trajectories over
+    // 8 GPUs leave 338 frames per chain of a full wave; the old floor of 2 x warm-up ran a third of a wave for 1584 steps
+    // instead of a full one for 866).  The floor only keeps the chain tables small for tiny inputs.
+    c = std::max<long long>(c, std::max(64, warm / 4));
     return (int)std::min<long long>(c, 1 << 30);
 }
 
