@@ -647,8 +647,10 @@ def run_c5(args, torch, td, dev, world, rank, local):
     halo = 8 * max(128, 48 * N)
     lo, hi = (T * rank) // world, (T * (rank + 1)) // world
     a, b = max(0, lo - halo), min(T, hi + halo)
-    x = c5.frames(a, b, means, sigmas, dev)
-    batch = TrajectoryBatch.from_concatenated(x, [b - a], N, device=dev, own_ranges=[(lo - a, hi - a)])
+    x = c5.frames_markov(a, b, pi, A, means, sigmas, dev)     # drawn from the model, block-seeded (identical in the overlaps)
+    shard = TimeShardedTrajectories.from_local_piece(x, a, T, N, rank, world, device=dev)
+    batch = shard.batch
+    del x
     batch.set_profiling(True)
     tm = Timer(dev, world)
     sampler = ClockSampler(local)
@@ -683,24 +685,30 @@ def run_c5(args, torch, td, dev, world, rank, local):
     clocks = sampler.stop() if rank == 0 else None
     st = unpack_stats(stats.cpu().numpy(), N)
     info = batch.info()
-    batch.close()
-    del batch, x
+    # ---- Viterbi path of the WHOLE trajectory across the shards (engine.TimeShardedTrajectories.viterbi): chain-parallel
+    # back-pointer maps per shard, certified borders, paths resolved from the last shard to the first.  The forward-variable
+    # workspace of the E-step is released first (the Viterbi batch holds 8 + N + 8 bytes per frame).
+    shard.release_estep_workspace()
     torch.cuda.empty_cache()
-    vit = None
-    if rank == 0:
-        # Viterbi of the WHOLE trajectory on one GPU (observations 8 T bytes, back-pointer map T N bytes)
-        Tv = T if T * (8 + N + 8) < 0.8 * torch.cuda.mem_get_info()[0] else int(0.8 * torch.cuda.mem_get_info()[0] / (16 + N))
-        xv = c5.frames(0, Tv, means, sigmas, dev)
-        vb = TrajectoryBatch.from_concatenated(xv, [Tv], N, device=dev, viterbi_only=True)
-        vb.viterbi_gaussian(A, pi, means, sigmas)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        path = vb.viterbi_gaussian(A, pi, means, sigmas)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        vit = {'frames': Tv, 'seconds': dt, 'frames_per_s': Tv / dt, 'path_checksum': int(path.to(torch.int64).sum().item()),
-               'info': vb.info()}
-        vb.close()
+    model = (A, pi, means, sigmas, True)
+    if world > 1:
+        shard.viterbi(model)                                 # warm-up (plans, warm-up length adaptation)
+        tm.start()
+        paths, vworst = shard.viterbi(model)
+        vms = tm.stop()
+    else:
+        TimeShardedTrajectories.viterbi_combine([shard], model)
+        tm.start()
+        paths, vworst = TimeShardedTrajectories.viterbi_combine([shard], model)
+        vms = tm.stop()
+        paths = [paths[0]]
+    chk = torch.tensor([int(paths[0].astype(np.int64).sum())], dtype=torch.int64, device=dev)
+    if world > 1:
+        td.all_reduce(chk, op=td.ReduceOp.SUM)
+    vit = {'frames': T, 'seconds': vms * 1e-3, 'frames_per_s': T / (vms * 1e-3), 'path_checksum': int(chk.item()),
+           'worst_border_mismatch': vworst, 'info': shard._vbatch.info(),
+           'note': 'whole trajectory across %d time shard(s); includes the device-to-host copy of the owned paths' % world}
+    shard._vbatch.close()
     if world > 1:
         td.barrier()
     if rank != 0:

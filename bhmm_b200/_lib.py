@@ -83,6 +83,8 @@ _proto('bhmm_b200_batch_replan', C.c_int, _vp, C.c_int, C.c_int)
 _proto('bhmm_b200_batch_uses_lane_kernels', C.c_int, _vp)
 _proto('bhmm_b200_wave_chains', C.c_int, C.c_int)
 _proto('bhmm_b200_batch_set_family', C.c_int, _vp, C.c_int)
+_proto('bhmm_b200_batch_set_viterbi_phase', C.c_int, _vp, C.c_int)
+_proto('bhmm_b200_batch_set_viterbi_end_state', C.c_int, _vp, C.c_int, C.c_int)
 _proto('bhmm_b200_batch_set_viterbi_only', C.c_int, _vp, C.c_int)
 _proto('bhmm_b200_batch_workspace_bytes', C.c_size_t, _vp)
 _proto('bhmm_b200_batch_attach_workspace', C.c_int, _vp, _vp, C.c_size_t)

@@ -17,6 +17,11 @@ struct bhmm_b200_batch {
     std::vector<long long> offsets;
     int chunk = 0, warm_f = 0, warm_b = 0, warm_min = 32;
     int req_chunk = 0, req_warm = 0;   // what the caller asked for (0 = automatic); kept for re-planning
+    // Viterbi on a time shard (owned ranges): phase 0 = map + path in one call, 1 = back-pointer map only, 2 = path only;
+    // vit_end[k] >= 0: the state of trajectory k at its last local frame, handed over by the shard that owns the next frames
+    int vit_phase = 0;
+    bool vit_map_chunked = false;
+    std::vector<int> vit_end;
     bool lane = false;          // small-N fast path (lane_kernels.cuh) instead of the team family
     bool no_alpha = false;      // Viterbi-only batch: no (rows, N) forward variables in the workspace
     double* d_g0buf = nullptr;
@@ -563,15 +568,27 @@ static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const do
                           int* d_path, cudaStream_t st)
 {
     const int N = b->N;
-    if (!b->own_lo.empty()) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "Viterbi needs whole trajectories (batch has owned ranges)"); return BHMM_ERR_UNSUPPORTED; }
+    // A batch with owned ranges is a TIME SHARD of longer trajectories: its chains cover the owned frames
+    // and warm up on the halo before them; the hand-over at the shard border is certified by the caller across shards
+    // (bhmm_b200_batch_border_handovers), the state at the last owned frame comes from the shard that owns the next frames
+    // (bhmm_b200_batch_set_viterbi_end_state), and the local trajectory must END with the owned range (no right halo).
+    const bool sharded = !b->own_lo.empty();
+    const int phase = b->vit_phase;
+    if (sharded) {
+        if (!(panel_viterbi_chain_ok(N) && N <= 256)) { bhmm_set_error(BHMM_ERR_UNSUPPORTED, "Viterbi on a time shard needs the chain-parallel Viterbi kernels (N <= 32, BHMM_B200_PANEL != 0)"); return BHMM_ERR_UNSUPPORTED; }
+        for (int k = 0; k < b->K; ++k) {
+            if (b->own_hi[k] != b->offsets[k + 1] - b->offsets[k]) { bhmm_set_error(BHMM_ERR_INVALID, "Viterbi on a time shard: the local trajectory must end with its owned range"); return BHMM_ERR_INVALID; }
+            if (!b->w.chunked && b->own_lo[k] != 0) { bhmm_set_error(BHMM_ERR_INVALID, "Viterbi on a time shard: plan without chains"); return BHMM_ERR_INVALID; }
+        }
+    } else if (phase != 0) { bhmm_set_error(BHMM_ERR_INVALID, "Viterbi phases are for time shards"); return BHMM_ERR_INVALID; }
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     // Default (BHMM_B200_PANEL=0 turns it off): trajectories that the plan cuts into chains (one very long trajectory, C5) run their
     // max-product recursions chain-parallel with certified hand-overs.  A decision whose margin is too small to be
     // certified only matters if the resolved path goes through it: that is checked after the path chase, and then -- or when
     // the hand-overs cannot be certified -- the sequential kernel recomputes the whole map.
-    bool chunked_map = false;
-    if (panel_viterbi_chain_ok(N) && b->w.chunked) {
+    bool chunked_map = (phase == 2) ? b->vit_map_chunked : false;
+    if (phase != 2 && panel_viterbi_chain_ok(N) && b->w.chunked) {
         VitChainArgs va{};
         va.em = em; va.N = N; va.A = b->d_A; va.pi = b->d_pi; va.backptr = b->d_F;
         va.hand_used = b->w.hu_f; va.hand_end = b->w.he_f; va.flagmap = b->d_vflag;
@@ -587,16 +604,34 @@ static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const do
             // the warm-up length learns from this pass like the forward filter's (estep_common)
             b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT, b->edge_f);
         }
-        else if (rc != BHMM_ERR_NOT_CERTIFIED) return rc;
+        else if (rc != BHMM_ERR_NOT_CERTIFIED || sharded) return rc;
         else bhmm_set_error(BHMM_OK, "");
     }
     for (int pass = 0; pass < 2; ++pass) {
-        if (!chunked_map) {
+        if (!chunked_map && phase != 2) {
             VitArgs a{};
             a.em = em; a.N = N; a.K = b->K; a.offsets = b->d_offsets; a.A = b->d_A; a.pi = b->d_pi;
             a.backptr = b->d_F; a.path = d_path;
             RC_TRY(launch_viterbi_team(a, emkind, st));
             LAUNCHED(1);
+        }
+        if (phase == 1) { b->vit_map_chunked = chunked_map; break; }
+        if (sharded) {
+            // rows before the first owned decision were never written: clear map and flags there; a handed-over end state
+            // replaces the last row ("the last row holds the final arg max for every s'", k_chase_* convention)
+            for (int k = 0; k < b->K; ++k) {
+                const long long r0 = b->offsets[k], Tk = b->offsets[k + 1] - r0, lo = b->own_lo[k];
+                if (lo > 1) {
+                    CUDA_TRY(cudaMemsetAsync(b->d_F + (size_t)r0 * N, 0, (size_t)(lo - 1) * N, st));
+                    if (chunked_map) CUDA_TRY(cudaMemsetAsync(b->d_vflag + r0, 0, sizeof(unsigned) * (size_t)(lo - 1), st));
+                }
+                const int es = k < (int)b->vit_end.size() ? b->vit_end[k] : -1;
+                if (es >= 0) {
+                    if (es >= N) { bhmm_set_error(BHMM_ERR_INVALID, "Viterbi end state out of range"); return BHMM_ERR_INVALID; }
+                    CUDA_TRY(cudaMemsetAsync(b->d_F + (size_t)(r0 + Tk - 1) * N, es, (size_t)N, st));
+                    if (chunked_map) CUDA_TRY(cudaMemsetAsync(b->d_vflag + r0 + Tk - 1, 0, sizeof(unsigned), st));
+                }
+            }
         }
         if (N <= 256) {     // uint8 maps written by the kernel: resolve the paths by segment-wise map composition
             RC_TRY(launch_chase(b->d_F, b->seg, N, b->seg_map, b->seg_enter, d_path, st));
@@ -610,9 +645,28 @@ static int viterbi_common(bhmm_b200_batch* b, Emission& em, int emkind, const do
         CUDA_TRY(cudaMemcpyAsync(&flagged, b->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         if (flagged == 0) break;
+        if (sharded) {
+            bhmm_set_error(BHMM_ERR_NOT_CERTIFIED, "Viterbi on a time shard: the path goes through a decision whose margin is below the certified tolerance; run the trajectory on one device");
+            return BHMM_ERR_NOT_CERTIFIED;
+        }
         chunked_map = false;                                // a near-tie on the path: sequential kernel, resolve again
     }
     return finish_stream(st);
+}
+
+extern "C" int bhmm_b200_batch_set_viterbi_phase(bhmm_b200_batch* b, int phase)
+{
+    if (!b || phase < 0 || phase > 2) return BHMM_ERR_INVALID;
+    b->vit_phase = phase;
+    return BHMM_OK;
+}
+
+extern "C" int bhmm_b200_batch_set_viterbi_end_state(bhmm_b200_batch* b, int k, int state)
+{
+    if (!b || k < 0 || k >= b->K) return BHMM_ERR_INVALID;
+    if ((int)b->vit_end.size() != b->K) b->vit_end.assign(b->K, -1);
+    b->vit_end[k] = state;
+    return BHMM_OK;
 }
 
 extern "C" int bhmm_b200_viterbi_gaussian(bhmm_b200_batch* b, const double* d_obs, const double* A, const double* pi,

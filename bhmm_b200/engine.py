@@ -347,6 +347,14 @@ class TrajectoryBatch(object):
         check(rc)
         return path
 
+    def set_viterbi_phase(self, phase):
+        """Time shards only (include/bhmm_b200.h): 0 = map + path, 1 = back-pointer map only, 2 = path only."""
+        check(lib.bhmm_b200_batch_set_viterbi_phase(self._handle, int(phase)))
+
+    def set_viterbi_end_state(self, k, state):
+        """Time shards only: the state of trajectory k at its last local frame (-1: the shard holds the trajectory's end)."""
+        check(lib.bhmm_b200_batch_set_viterbi_end_state(self._handle, int(k), int(state)))
+
     # -------------------------------------------------------------------------------------------- Gibbs
     def _gibbs_buffers(self):
         N = self.N
@@ -657,8 +665,16 @@ class TimeShardedTrajectories(object):
     from is compared with the vector its neighbour actually computed at the same frame (component-wise, relatively);
     ``certify`` raises when a border disagrees by more than ``tol``.
 
-    One process per shard (``torch.distributed``), or several shards in one process for tests (``combine``).
-    Viterbi and hidden-path sampling need whole trajectories and are not available on shards.
+    One process per shard (``torch.distributed``), or several shards in one process for tests (``combine``,
+    ``viterbi_combine``).
+
+    Viterbi works across shards as well (``viterbi_gaussian`` / ``viterbi_discrete``): every shard builds the back-pointer
+    map of its owned frames with the chain-parallel Viterbi kernels, warming its max-product vector up on the halo BEFORE
+    its range; the vector each shard started from is certified against the one its left neighbour computed (same
+    component-wise relative test as for the E-step); then the paths are resolved from the last shard to the first, each
+    shard handing the state at its neighbour's last frame -- one integer per trajectory -- to the left.  A path that goes
+    through a decision whose margin is below the certified tolerance raises (run that trajectory on one device).
+    Hidden-path sampling needs whole trajectories and is not available on shards.
     """
 
     def __init__(self, observations, nstates, rank, world, halo=None, device=None, chunk=0, warm=0, tol=1e-11):
@@ -687,11 +703,150 @@ class TimeShardedTrajectories(object):
                                                        own_ranges=own)
         self.K = len(lengths)
 
+    def release_estep_workspace(self):
+        """Free the E-step batch's device workspace (forward variables, chain tables); the observations stay resident for
+        the Viterbi shard (8 + N + 8 bytes per frame instead of 8 + 8 N)."""
+        self.batch.close()
+        self.batch._workspace = None
+
+    @classmethod
+    def from_local_piece(cls, piece, start, total_frames, nstates, rank, world, device=None, chunk=0, warm=0, tol=1e-11):
+        """ONE trajectory of ``total_frames`` frames whose piece [start, start + len(piece)) -- this rank's owned range
+        [T r / world, T (r+1) / world) plus halo -- is already resident (a CUDA tensor or a host array): what a loader that
+        generates or reads each rank's frames separately uses (bench.py --workload c5)."""
+        self = cls.__new__(cls)
+        self.N, self.rank, self.world, self.tol = int(nstates), int(rank), int(world), float(tol)
+        T = int(total_frames)
+        lo, hi = (T * self.rank) // self.world, (T * (self.rank + 1)) // self.world
+        n = int(piece.shape[0])
+        if start > lo or start + n < hi or hi <= lo:
+            raise ValueError('the piece [%d, %d) does not cover the owned range [%d, %d)' % (start, start + n, lo, hi))
+        self.halo = max(lo - start, start + n - hi)
+        self.global_ranges = [(lo, hi, T)]
+        self.batch = TrajectoryBatch.from_concatenated(piece, [n], self.N, device=device, chunk=chunk, warm=warm,
+                                                       own_ranges=[(lo - start, hi - start)])
+        self.K = 1
+        return self
+
     def close(self):
         self.batch.close()
+        if getattr(self, '_vbatch', None) is not None:
+            self._vbatch.close()
+            self._vbatch = None
 
     def info(self):
         return self.batch.info()
+
+    # ------------------------------------------------------------------------------------------ Viterbi across shards
+    def _viterbi_batch(self):
+        """The shard's Viterbi batch: frames [a, hi) of every trajectory (left halo + owned range, NO right halo: the
+        max-product recursion only looks back), no forward-variable workspace."""
+        if getattr(self, '_vbatch', None) is None:
+            b = self.batch
+            pieces, lengths, own = [], [], []
+            for k in range(self.K):
+                lo_l, hi_l = b._own_ranges[k]
+                r0 = int(b.offsets[k])
+                hi_l = max(hi_l, lo_l + 1) if hi_l <= lo_l else hi_l
+                pieces.append(b.obs[r0:r0 + hi_l])
+                lengths.append(hi_l)
+                own.append((lo_l, hi_l))
+            cat = b.torch.cat(pieces) if len(pieces) > 1 else pieces[0]
+            self._vbatch = TrajectoryBatch.from_concatenated(cat, lengths, self.N, device=b.device, own_ranges=own,
+                                                             viterbi_only=True)
+        return self._vbatch
+
+    def _viterbi_call(self, model, kind):
+        vb = self._viterbi_batch()
+        if kind == 'gaussian':
+            A, pi, means, sigmas, io = model
+            return vb.viterbi_gaussian(A, pi, means, sigmas, ignore_outliers=io)
+        A, pi, B, io = model
+        return vb.viterbi_discrete(A, pi, B, ignore_outliers=io)
+
+    def viterbi_map(self, model, kind='gaussian'):
+        """Phase 1: back-pointer map of the owned frames.  Returns the (K, 2, N) border vectors [used at lo - 1, end at hi - 1]."""
+        vb = self._viterbi_batch()
+        vb.set_viterbi_phase(1)
+        self._viterbi_call(model, kind)
+        return np.array([vb.border_handovers(k)[:2] for k in range(self.K)])
+
+    def viterbi_resolve(self, model, end_states, kind='gaussian'):
+        """Phase 2: resolve the paths given the state of every trajectory at this shard's last owned frame (None / -1: the
+        shard holds the trajectory's end).  Returns (list of owned-range paths (int32 numpy), states at frame lo - 1)."""
+        vb = self._viterbi_batch()
+        vb.set_viterbi_phase(2)
+        for k in range(self.K):
+            vb.set_viterbi_end_state(k, -1 if end_states is None else int(end_states[k]))
+        flat = self._viterbi_call(model, kind).cpu().numpy()
+        paths, left = [], []
+        for k in range(self.K):
+            lo_l, hi_l = vb._own_ranges[k]
+            r0 = int(vb.offsets[k])
+            lo_g, hi_g, _ = self.global_ranges[k]
+            paths.append(flat[r0 + lo_l:r0 + hi_l].copy() if hi_g > lo_g else np.zeros(0, dtype=np.int32))
+            left.append(int(flat[r0 + lo_l - 1]) if lo_l > 0 else -1)
+        return paths, left
+
+    @staticmethod
+    def certify_viterbi(borders_by_rank, ranges_by_rank, tol):
+        """Worst relative mismatch of the max-product hand-overs at the shard borders; raises above ``tol``."""
+        world, worst = len(borders_by_rank), 0.0
+        for k in range(len(ranges_by_rank[0])):
+            owners = [r for r in range(world) if ranges_by_rank[r][k][1] > ranges_by_rank[r][k][0]]
+            for left, right in zip(owners, owners[1:]):
+                worst = max(worst, _rel_mismatch(borders_by_rank[right][k][0], borders_by_rank[left][k][1]))
+        if worst > tol:
+            raise RuntimeError('time-sharded Viterbi: a shard border disagrees by %.3g (tolerance %.3g); the halo is too '
+                               'short for this model -- increase halo=' % (worst, tol))
+        return worst
+
+    @classmethod
+    def viterbi_combine(cls, shards, model, kind='gaussian'):
+        """Single-process use (tests): all shards in one process.  Returns (list over trajectories of the full int32 paths,
+        worst border mismatch)."""
+        borders = [s.viterbi_map(model, kind) for s in shards]
+        worst = cls.certify_viterbi(borders, [s.global_ranges for s in shards], shards[0].tol)
+        K = shards[0].K
+        parts = [[None] * len(shards) for _ in range(K)]
+        end = None
+        for r in range(len(shards) - 1, -1, -1):
+            own = [shards[r].global_ranges[k][1] > shards[r].global_ranges[k][0] for k in range(K)]
+            paths, left = shards[r].viterbi_resolve(model, end, kind)
+            for k in range(K):
+                parts[k][r] = paths[k]
+            # a shard that owns nothing of trajectory k passes the state it received on to the left
+            end = [left[k] if own[k] else (-1 if end is None else end[k]) for k in range(K)]
+        return [np.concatenate(parts[k]) for k in range(K)], worst
+
+    def viterbi(self, model, kind='gaussian'):
+        """Distributed use (one process per shard, torch.distributed initialised).  Returns (owned-range paths of this
+        shard, worst border mismatch)."""
+        import torch.distributed as td
+        torch = self.batch.torch
+        dev = self.batch.device
+        mine = torch.from_numpy(self.viterbi_map(model, kind)).to(dev)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        td.all_gather(gathered, mine)
+        ranges = [[((T * r) // self.world, (T * (r + 1)) // self.world, T) for (_, _, T) in self.global_ranges]
+                  for r in range(self.world)]
+        worst = self.certify_viterbi([g.cpu().numpy() for g in gathered], ranges, self.tol)
+        end = torch.full((self.K,), -1, dtype=torch.int64, device=dev)
+        paths = None
+        for r in range(self.world - 1, -1, -1):
+            if r == self.rank:
+                e = end.cpu().numpy()
+                paths, left = self.viterbi_resolve(model, None if r == self.world - 1 else e, kind)
+                own = [ranges[r][k][1] > ranges[r][k][0] for k in range(self.K)]
+                end = torch.tensor([left[k] if own[k] else int(e[k]) for k in range(self.K)], dtype=torch.int64, device=dev)
+            td.broadcast(end, src=r)
+        return paths, worst
+
+    def viterbi_gaussian(self, A, pi, means, sigmas, ignore_outliers=True):
+        return self.viterbi((A, pi, means, sigmas, ignore_outliers), 'gaussian')
+
+    def viterbi_discrete(self, A, pi, B, ignore_outliers=False):
+        return self.viterbi((A, pi, B, ignore_outliers), 'discrete')
 
     def estep_gaussian_local(self, A, pi, means, sigmas, ignore_outliers=True):
         """Local statistics (device tensor) and the (K, 4, N) border hand-overs of this shard."""

@@ -188,6 +188,16 @@ int bhmm_b200_viterbi_gaussian(bhmm_b200_batch* b, const double* d_obs, const do
                                void* stream);
 int bhmm_b200_viterbi_discrete(bhmm_b200_batch* b, const int* d_obs, const double* A, const double* pi,
                                const double* B, int M, int ignore_outliers, int* d_path, void* stream);
+/* Viterbi of trajectories that are cut in TIME across devices.  A shard is a batch with owned ranges
+ * (bhmm_b200_batch_create_ranges) whose local trajectories END with their owned range: halo frames before it, none after.
+ * phase 1: bhmm_b200_viterbi_* only builds the back-pointer map of the owned frames (chain-parallel, hand-overs inside the
+ * shard certified; the border hand-over is exported by bhmm_b200_batch_border_handovers, rows 0 and 1, for the caller to
+ * compare across shards).  phase 2: only resolves the path, ending in the state set by
+ * bhmm_b200_batch_set_viterbi_end_state (the state of trajectory k at its last local frame, i.e. path[own_lo - 1] of the
+ * shard that owns the following frames; -1 = this shard holds the trajectory's end).  phase 0 (default) does both.
+ * d_path is filled for the local rows; rows before own_lo - 1 are meaningless. */
+int bhmm_b200_batch_set_viterbi_phase(bhmm_b200_batch* b, int phase);
+int bhmm_b200_batch_set_viterbi_end_state(bhmm_b200_batch* b, int k, int state);
 /* One Gibbs hidden-path sweep (bayesian_sampling.py:283-331): emission + forward + backward sampling of every
  * trajectory, then the path statistics of generic_hmm.py:297-334,398-431.  Uniforms: d_u (device, one per row,
  * u[row] is the draw of that frame) or, when d_u is NULL, device Philox4x32-10 keyed by (seed, sweep).

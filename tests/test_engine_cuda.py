@@ -1,6 +1,8 @@
 """Parity of the batched, device-resident engine (TrajectoryBatch -> bhmm_b200_batch_* C ABI) against the CPU
 oracle and the reference fixtures: fused E-step statistics, EM iterations, batched Viterbi and the Gibbs
 hidden-path sweep.  float64 within 1e-10 relative, integer outputs bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -525,9 +527,17 @@ def test_time_sharded_trajectories(eng, oracle_port, N, world):
     np.testing.assert_allclose(st['wsum'], ref['wsum'], rtol=RTOL)
     np.testing.assert_allclose(st['wdd'], wdd, rtol=1e-9)
     assert abs(st['C'].sum() - sum(len(o) - 1 for o in obs)) < 1e-6
-    # shards cannot produce whole-trajectory paths
+    # a shard's E-step batch (frames after its owned range) is not a Viterbi shard
     with pytest.raises(Exception):
         shards[0].batch.viterbi_gaussian(A, pi, means, sigmas)
+    # Viterbi ACROSS the shards (N <= 32): chain-parallel maps per shard with certified borders, paths resolved from the last
+    # shard to the first with one state per trajectory handed to the left; equal to the sequential paths of the oracle
+    if N <= 32 and os.environ.get('BHMM_B200_PANEL', '1') != '0':
+        paths, vworst = eng.TimeShardedTrajectories.viterbi_combine(shards, (A, pi, means, sigmas, True))
+        assert vworst <= 1e-11
+        for o, p in zip(obs, paths):
+            want = oracle_port.viterbi(A, oracle_port.gaussian_p_obs(o, means, sigmas), pi)
+            assert p.shape == want.shape and np.array_equal(p, want), int(np.sum(p != want))
     for s in shards:
         s.close()
     # a halo that is far too short is detected, not silently accepted

@@ -38,6 +38,41 @@ def frames(lo, hi, means, sigmas, dev, seed=1234):
     return torch.cat(out)
 
 
+MBLOCK = 100000
+
+
+def frames_markov(lo, hi, pi, A, means, sigmas, dev, seed=4321):
+    """Observations of frames [lo, hi) of one long trajectory drawn FROM THE MODEL ("generated on device in
+    blocks each started from pi"): block b = frames [b*MBLOCK, (b+1)*MBLOCK) is a Markov chain started from pi with its own
+    seed, so that neighbouring ranks see identical observations in their overlap; the chains of all blocks of the range
+    advance together (one vectorised inverse-CDF draw per frame)."""
+    import numpy as np
+    b0, b1 = lo // MBLOCK, (hi - 1) // MBLOCK
+    K = b1 - b0 + 1
+    N = len(pi)
+    cumA = torch.as_tensor(np.cumsum(A, axis=1), device=dev)
+    cumA[:, -1] = 1.0
+    cpi = torch.as_tensor(np.cumsum(pi), device=dev)
+    cpi[-1] = 1.0
+    U = torch.empty((MBLOCK, K), dtype=torch.float64, device=dev)
+    Z = torch.empty((K, MBLOCK), dtype=torch.float64, device=dev)
+    g = torch.Generator(device=dev)
+    for k in range(K):
+        g.manual_seed(seed + b0 + k)
+        U[:, k] = torch.rand(MBLOCK, generator=g, device=dev, dtype=torch.float64)
+        Z[k] = torch.randn(MBLOCK, generator=g, device=dev, dtype=torch.float64)
+    S = torch.empty((MBLOCK, K), dtype=torch.int64, device=dev)
+    s = (U[0][:, None] > cpi[None, :]).sum(dim=1).clamp_(max=N - 1)
+    S[0] = s
+    for t in range(1, MBLOCK):
+        s = (U[t][:, None] > cumA[s]).sum(dim=1).clamp_(max=N - 1)
+        S[t] = s
+    del U
+    S = S.t().contiguous()
+    x = (torch.as_tensor(means, device=dev)[S] + torch.as_tensor(sigmas, device=dev)[S] * Z).reshape(-1)
+    return x[lo - b0 * MBLOCK:hi - b0 * MBLOCK].contiguous()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--frames', type=float, default=1e8)
