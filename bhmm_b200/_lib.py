@@ -82,6 +82,8 @@ _proto('bhmm_b200_batch_destroy', None, _vp)
 _proto('bhmm_b200_batch_replan', C.c_int, _vp, C.c_int, C.c_int)
 _proto('bhmm_b200_batch_uses_lane_kernels', C.c_int, _vp)
 _proto('bhmm_b200_wave_chains', C.c_int, C.c_int)
+_proto('bhmm_b200_batch_scan_count', C.c_double, _vp)
+_proto('bhmm_b200_batch_debug_handovers', C.c_int, _vp, C.c_int, _dp, _dp)
 _proto('bhmm_b200_batch_set_family', C.c_int, _vp, C.c_int)
 _proto('bhmm_b200_batch_set_viterbi_phase', C.c_int, _vp, C.c_int)
 _proto('bhmm_b200_batch_set_viterbi_end_state', C.c_int, _vp, C.c_int, C.c_int)

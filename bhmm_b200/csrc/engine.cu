@@ -5,6 +5,7 @@
 // of MaximumLikelihoodEstimator.fit (maximum_likelihood.py:383-385), compute_viterbi_paths (:332-352) and
 // BayesianHMMSampler._updateHiddenStateTrajectories (bayesian_sampling.py:283-291).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -49,6 +50,7 @@ struct bhmm_b200_batch {
     int* d_err = nullptr;
     unsigned* d_vflag = nullptr;   // chunked Viterbi: near-tie flags per row of the back-pointer map
     Arena disc;                 // B staging + Bt for the discrete model (sized on first use)
+    Arena scan;                 // transfer operators of the exact-scan fallback (scan_kernels.cu; allocated when first needed)
     RunInfo info;
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profile = false;
@@ -193,6 +195,25 @@ int upload_small(double* dst, const double* src, size_t n, cudaStream_t st)
     return BHMM_OK;
 }
 
+// Installs the exact-scan fallback (scan_kernels.cu) on the batch's chain work for the duration of a pass; the callback
+// captures the caller's emission by reference, hence the guard that removes it again.
+struct ScanGuard {
+    bhmm_b200_batch* b;
+    ScanGuard(bhmm_b200_batch* b_, const Emission& em, int emkind) : b(b_)
+    {
+        const int N = b->N;
+        if (!exact_scan_ok(N) || !b->w.chunked) return;
+        b->w.scan = [this, &em, emkind, N](int dir, cudaStream_t st) -> int {
+            const size_t need = exact_scan_bytes(b->w.n_total, N);
+            if (b->scan.ensure(need) != BHMM_OK) { bhmm_set_error(BHMM_ERR_NO_MEM, "exact scan: device memory for the chain operators"); return BHMM_ERR_NO_MEM; }
+            Chains all = b->w.ch;
+            return launch_exact_scan(all, b->w.n_total, em, emkind, b->d_A, N, dir, dir > 0 ? b->w.he_f : b->w.he_b,
+                                     reinterpret_cast<double*>(b->scan.base), st);
+        };
+    }
+    ~ScanGuard() { b->w.scan = nullptr; }
+};
+
 void begin_info(bhmm_b200_batch* b)
 {
     b->info = RunInfo();
@@ -224,6 +245,7 @@ int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     b->w.ch.warm = b->warm_f;
+    ScanGuard scan_guard(b, em, emkind);
     LaneArgs la{};
     LaneHostParams hp{A, pi, mu, sigma};
     if (b->lane) {
@@ -247,9 +269,10 @@ int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
     if (b->w.chunked) b->warm_f = adapt_warm(b->warm_f, b->w.need_f, b->info.worst_f, b->info.fix_f > 0, b->warm_min, b->plan.maxT, b->edge_f);
 
     b->w.need_b = 0.0;
+    bool exact_bwd = false;
     for (int attempt = 0;; ++attempt) {
         Chains all = b->w.ch;
-        all.list = nullptr; all.n = b->w.n_total; all.exact = 0; all.warm = b->warm_b; all.warmv = nullptr;
+        all.list = nullptr; all.n = b->w.n_total; all.exact = exact_bwd ? 1 : 0; all.warm = b->warm_b; all.warmv = nullptr;
         if (d_Bnum) CUDA_TRY(cudaMemsetAsync(d_Bnum, 0, sizeof(double) * (size_t)N * em.M, st));
         if (b->profile) cudaEventRecord(b->ev[2], st);
         if (b->lane) {
@@ -267,15 +290,30 @@ int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
         LAUNCHED(1);
         if (b->profile) cudaEventRecord(b->ev[3], st);
         if (!b->w.chunked) break;
-        const long long nfail = certify_sync(b->w, N, -1, &b->info.worst_b, st);
+        const long long nfail = certify_sync(b->w, N, -1, &b->info.worst_b, st, exact_bwd ? EXACT_SCAN_TOL : 0.0);
         if (nfail < 0) { bhmm_set_error(BHMM_ERR_CUDA, cudaGetErrorString(cudaGetLastError())); return BHMM_ERR_CUDA; }
         if (nfail == 0) { b->warm_b = adapt_warm(b->warm_b, b->w.need_b, b->info.worst_b, false, b->warm_min, b->plan.maxT, b->edge_b); break; }
         // statistics of a failed pass cannot be patched chain by chain: lengthen the warm-up (at least +32 frames, up to
         // the longest trajectory, which is an exact start) and redo the pass.
-        if (b->warm_b >= b->plan.maxT) { bhmm_set_error(BHMM_ERR_NOT_CERTIFIED, "backward hand-overs not certified"); return BHMM_ERR_NOT_CERTIFIED; }
-        b->warm_b = adapt_warm(b->warm_b, b->w.need_b, b->info.worst_b, true, b->warm_min, b->plan.maxT, b->edge_b);
+        if (exact_bwd || b->warm_b >= b->plan.maxT) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "backward hand-overs not certified (%lld chains, worst mismatch %.3g%s)", nfail, b->info.worst_b,
+                     exact_bwd ? ", after the exact scan" : "");
+            bhmm_set_error(BHMM_ERR_NOT_CERTIFIED, msg);
+            return BHMM_ERR_NOT_CERTIFIED;
+        }
         b->info.fix_b += 1;
         b->info.rerun += (double)b->w.n_total;
+        if (attempt >= 1 && b->w.scan) {
+            // a longer warm-up did not help either: the model does not forget.  Exact starts from the transfer-operator
+            // scan (the hand-over vectors the failed pass left behind are exact at the trajectory ends), then the pass once more
+            RC_TRY(b->w.scan(-1, st));
+            LAUNCHED(2);
+            b->w.scans += 1;
+            exact_bwd = true;
+            continue;
+        }
+        b->warm_b = adapt_warm(b->warm_b, b->w.need_b, b->info.worst_b, true, b->warm_min, b->plan.maxT, b->edge_b);
     }
     const int prow = b->lane ? lane_blocks(b->w.n_total) : b->stats_grid;
     RC_TRY(launch_finalize_stats(b->d_partials, prow, b->w.chain_ll, b->w.n_total, b->d_A, N, d_stats, st));
@@ -318,6 +356,7 @@ int gibbs_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
     RC_TRY(upload_small(b->d_A, A, (size_t)N * N, st));
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     b->w.ch.warm = b->warm_f;
+    ScanGuard scan_guard(b, em, emkind);
     if (b->lane) {
         // lane family: forward on the interleaved layout, then the two-pass hypothesis sampler (lane_kernels.cuh)
         LaneArgs la{};
@@ -426,6 +465,7 @@ extern "C" void bhmm_b200_batch_destroy(bhmm_b200_batch* b)
     if (!b) return;
     b->arena.release();
     b->disc.release();
+    b->scan.release();
     for (int k = 0; k < 4; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
     delete b;
 }
@@ -467,6 +507,18 @@ extern "C" int bhmm_b200_batch_set_family(bhmm_b200_batch* b, int lane)
     batch_plan(b, b->req_chunk, b->req_warm);
     return BHMM_OK;
 }
+
+// Diagnostic: all hand-over vectors of the last pass, (chains, N) each: dir > 0 forward, dir < 0 backward.
+extern "C" int bhmm_b200_batch_debug_handovers(const bhmm_b200_batch* b, int dir, double* used, double* end)
+{
+    if (!b || !b->carved || !used || !end) return BHMM_ERR_INVALID;
+    const size_t n = sizeof(double) * (size_t)b->w.n_total * b->N;
+    CUDA_TRY(cudaMemcpy(used, dir > 0 ? b->w.hu_f : b->w.hu_b, n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(end, dir > 0 ? b->w.he_f : b->w.he_b, n, cudaMemcpyDeviceToHost));
+    return BHMM_OK;
+}
+
+extern "C" double bhmm_b200_batch_scan_count(const bhmm_b200_batch* b) { return b ? b->w.scans : 0.0; }
 
 extern "C" int bhmm_b200_wave_chains(int N)
 {

@@ -70,6 +70,10 @@ struct ChainWork {
     unsigned long long* cert_out = nullptr;   // device [n_fail, worst bits, sum warm, count]
     int warm_cap = 1;            // longest trajectory: a warm-up that long is an exact start
     double need_f = 0, need_b = 0;   // certification's estimate of the warm-up the hardest hand-over needs
+    // Exact fallback for models whose filter does not forget (scan_kernels.cu): fills he_f (dir > 0) or he_b (dir < 0) with
+    // the exact hand-over vectors of every chain; set by the engine around a pass, empty when unavailable (N > 32)
+    std::function<int(int dir, cudaStream_t st)> scan;
+    double scans = 0;            // how many times the fallback ran (reported through bhmm_b200_batch_scan_count)
 };
 // next warm-up length from the current one, the certification's need estimate and the largest mismatch of the pass
 int adapt_warm(int current, double need, double worst, bool failed, int warm_min, int warm_cap, double* edge);
@@ -95,7 +99,8 @@ int run_forward(ChainWork& w, const Emission& em, int emkind, int N, const doubl
 int run_backward(ChainWork& w, const Emission& em, int emkind, int N, const double* dA, double* d_beta,
                  RunInfo& info, cudaStream_t st);
 // certification read-back: returns number of failing chains (or <0 on CUDA error), updates worst
-long long certify_sync(ChainWork& w, int N, int dir, double* worst, cudaStream_t st);
+constexpr double EXACT_SCAN_TOL = 1e-11;   // hand-over tolerance of the pass that follows the exact scan (capi.cu)
+long long certify_sync(ChainWork& w, int N, int dir, double* worst, cudaStream_t st, double tol_floor = 0.0);
 
 // glibc srand()/rand() restatement (TYPE_3, r[i] = r[i-31] + r[i-3]); reproduces the reference's uniforms
 struct GlibcRand {

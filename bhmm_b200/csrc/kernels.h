@@ -132,6 +132,11 @@ int launch_forward_panel(const FwdArgs& a, int em, cudaStream_t st);
 int launch_backward_stats_panel(const BwdArgs& a, int em, cudaStream_t st);
 bool panel_viterbi_ok(int N);                // 32 < N <= 104: Viterbi with the matrix column in registers
 int launch_viterbi_panel(const VitArgs& a, int em, cudaStream_t st);
+// ---- exact time-parallel chain starts (scan_kernels.cu): transfer operators per chain + a scan over them, N <= 32
+bool exact_scan_ok(int N);
+size_t exact_scan_bytes(int n_chains, int N);
+int launch_exact_scan(const Chains& all, int n_total, const Emission& em, int emkind, const double* dA, int N, int dir,
+                      double* he, double* ops, cudaStream_t st);
 bool lane_viterbi_ok(int N);                 // N <= 16: the chunked Viterbi runs one thread per chain (lane_viterbi.cu)
 int launch_viterbi_chain_lane(const VitChainArgs& a, int em, cudaStream_t st);
 bool panel_viterbi_chain_ok(int N);          // N <= 32: time-chunked Viterbi for trajectories cut into chains

@@ -229,6 +229,11 @@ class TrajectoryBatch(object):
                     fixups_bwd=int(info[4]), worst_fwd=float(info[5]), worst_bwd=float(info[6]), rerun=int(info[7]))
 
     @property
+    def exact_scans(self):
+        """How often the exact transfer-operator scan replaced the warm-up starts (models that do not forget; N <= 32)."""
+        return int(lib.bhmm_b200_batch_scan_count(self._handle))
+
+    @property
     def uses_lane_kernels(self):
         """True when the small-N one-thread-per-chain kernels run (N <= 16), False for the general-N team kernels."""
         return bool(lib.bhmm_b200_batch_uses_lane_kernels(self._handle))

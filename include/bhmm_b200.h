@@ -146,6 +146,12 @@ int bhmm_b200_batch_uses_lane_kernels(const bhmm_b200_batch* b);
  * 0 without a device.  Callers that cut a data set into groups (engine.SubBatchedTrajectories) size the groups in multiples
  * of it so that no round of the persistent kernels runs mostly empty. */
 int bhmm_b200_wave_chains(int N);
+/* How many times the exact transfer-operator scan (scan_kernels.cu) replaced the certified warm-up starts of this batch's
+ * chains since it was created: the fallback for models whose filter does not forget its start (N <= 32). */
+double bhmm_b200_batch_scan_count(const bhmm_b200_batch* b);
+/* Diagnostic: the hand-over vectors of the last pass, (chains, N) doubles each (host buffers): the vector every chain was
+ * started from and the vector it computed at its own border; dir > 0 forward, dir < 0 backward. */
+int bhmm_b200_batch_debug_handovers(const bhmm_b200_batch* b, int dir, double* used, double* end);
 /* Switch a batch between the lane kernels (lane != 0; N <= 16 only) and the general-N team / panel kernels, re-plan its
  * chains and invalidate the workspace layout (query bhmm_b200_batch_workspace_bytes and attach again).  Used for models the
  * lane kernels refuse (a Gaussian sigma below 1e-100). */

@@ -39,5 +39,14 @@ inline int __shfl_sync(unsigned, int v, int src)
     emu::rendezvous(w.g);
     return r;
 }
+inline double __shfl_sync(unsigned, double v, int src)
+{
+    emu::Warp& w = emu::my_warp();
+    w.sd[emu::lane_id()] = v;
+    emu::rendezvous(w.g);
+    const double r = w.sd[src & 31];
+    emu::rendezvous(w.g);
+    return r;
+}
 inline void __threadfence_block() {}
 inline void __threadfence() {}

@@ -548,6 +548,43 @@ def test_time_sharded_trajectories(eng, oracle_port, N, world):
         s.close()
 
 
+@pytest.mark.parametrize('N', [4, 12, 20, 32])
+def test_exact_scan_for_models_that_do_not_forget(eng, oracle_port, N):
+    """North star (4): a nearly reducible transition matrix with uninformative emissions never forgets its start, so the
+    warm-up starts of the chains fail their certification and chain-by-chain repairs would walk the trajectory
+    sequentially.  The engine falls back to the exact time-parallel start -- transfer operators of all chains and a scan
+    over them (scan_kernels.cu) -- in both directions, and the statistics still match the oracle."""
+    rng = np.random.default_rng(900 + N)
+    eps = 2e-5
+    A = (1.0 - eps) * np.eye(N) + eps * np.ones((N, N)) / N
+    A /= A.sum(axis=1)[:, None]
+    pi = rng.random(N) + 0.5
+    pi /= pi.sum()
+    means, sigmas = np.linspace(-0.02, 0.02, N), np.ones(N)      # emissions that tell the states apart very slowly
+    obs = [rng.standard_normal(T) for T in (9000, 4000, 300)]
+    batch = eng.TrajectoryBatch(obs, N, chunk=400, warm=32)
+    st = eng.unpack_stats(batch.estep_gaussian(A, pi, means, sigmas).cpu().numpy(), N)
+    info = batch.info()
+    assert info['chains'] > 20
+    assert batch.exact_scans >= 2, (batch.exact_scans, info)    # forward and backward fell back to the scan
+    assert info['fixups_fwd'] <= 4 and info['fixups_bwd'] <= 4, info   # ... instead of one repair sweep per chain
+    ref, wd, wdd = oracle_stats_gaussian(oracle_port, obs, A, pi, means, sigmas)
+    assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])
+    np.testing.assert_allclose(st['gamma0'], ref['gamma0'], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-8, atol=1e-9 * ref['C'].max())
+    np.testing.assert_allclose(st['wsum'], ref['wsum'], rtol=1e-9)
+    # a model that mixes keeps the certified warm-up starts
+    A2 = rng.random((N, N)) + 0.1
+    A2 /= A2.sum(axis=1)[:, None]
+    m2 = np.linspace(-3, 3, N)
+    o2 = [m2[rng.integers(0, N, size=T)] + rng.standard_normal(T) for T in (9000, 4000)]
+    b2 = eng.TrajectoryBatch(o2, N, chunk=400, warm=200)
+    b2.estep_gaussian(A2, pi, m2, sigmas)
+    assert b2.exact_scans == 0
+    batch.close()
+    b2.close()
+
+
 def test_viterbi_only_batch(eng, oracle_port):
     """A Viterbi-only batch (no forward-variable workspace: how one C5-sized trajectory fits a GPU for Viterbi) returns the
     same paths as a full batch and refuses the E-step."""

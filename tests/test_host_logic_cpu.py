@@ -226,3 +226,60 @@ def test_gibbs_transition_matrix_update_reversible_and_not():
         assert np.all(p0 >= 0) and abs(p0.sum() - 1.0) < 1e-12
         if reversible:
             assert tmatrix.is_reversible(T)
+
+
+def test_device_cache_bookkeeping_without_a_device():
+    """The buffer-identity cache of bhmm_b200.hidden is host-side bookkeeping: entries are keyed by the
+    host array's data pointer, served only while shape and fingerprint still match, dropped when the caller changed the
+    array, and bounded in number.  (Device tensors are stand-ins here; the GPU path is tests/test_reference_on_cuda.py.)"""
+    from bhmm_b200.hidden import api
+    api.set_device_cache(True)
+    try:
+        a = np.random.default_rng(1).random((50, 3))
+        api._remember(a, 'DEV-A', 40)
+        assert api._lookup(a, 40, 3) == 'DEV-A' and api._lookup(a, 10, 3) == 'DEV-A'    # a prefix of what was written
+        assert api._lookup(a, 45, 3) is None                                            # more rows than were written
+        assert api._lookup(a, 40, 4) is None                                            # another state count
+        assert api._lookup(a.copy(), 40, 3) is None                                     # equal content, other buffer
+        a[39, 2] += 1.0                                                                 # the caller touched the last row
+        assert api._lookup(a, 40, 3) is None
+        st = api.device_cache_stats()
+        assert st['stale'] == 1 and st['entries'] == 0
+        keep = [np.zeros((4, 2)) + k for k in range(api._CACHE_MAX + 3)]
+        for k, b in enumerate(keep):
+            api._remember(b, k, 4)
+        assert api.device_cache_stats()['entries'] == api._CACHE_MAX
+        assert api._lookup(keep[0], 4, 2) is None and api._lookup(keep[-1], 4, 2) == len(keep) - 1
+        f = np.asfortranarray(np.ones((5, 3)))
+        api._remember(f, 'X', 5)                                                        # not C-contiguous: never cached
+        assert api._lookup(f, 5, 3) is None
+    finally:
+        api.set_device_cache(False)
+    assert api.device_cache_stats()['entries'] == 0 and not api.device_cache_stats()['enabled']
+
+
+def test_reference_arm_runs_without_the_product_library(tmp_path):
+    """`bench.py --impl reference` times the reference's C code in spawned single-threaded workers and must not map
+    libbhmm_b200.so (the arm imported bhmm_b200 for its data generator)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json, io, contextlib\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--cpu-traj-per-core', '1', '--workload', 'small']\n"
+            "import bench\n"
+            "if __name__ == '__main__':\n"
+            "    bench.main()\n"
+            "    maps = open('/proc/self/maps').read()\n"
+            "    print('MAPPED_PRODUCT' if 'libbhmm_b200' in maps else 'CLEAN')\n")
+    script = tmp_path / 'run_ref.py'
+    script.write_text(code)
+    r = subprocess.run([sys.executable, str(script)], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=600, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+    line = json.loads(lines[0])
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['cores'] >= 1
+    assert line['cpu_baseline']['single_core_as_shipped'] > 0 and line['e2e']['h2d_bytes_per_step'] == 0
+    assert 'CLEAN' in r.stdout
