@@ -56,7 +56,10 @@ def test_panel_family_through_the_engine(engine_emu):
     with a two-frame warm-up exercises the failed-certification paths (exact forward fix-ups, backward retries with a longer
     warm-up, Viterbi fix-ups)."""
     r = _drive(1, ['32,40,40', '21,40,40', '40,0,0', 's32', '32,40,2,300', 'l8'], trace=True)
-    assert 'block 32 ' not in r.stderr                  # no team chain kernel was launched
+    import re
+    # no team chain kernel was launched (one warp per block WITH the transition matrix in dynamic shared memory; the exact
+    # scan's k_scan_starts also runs 32-thread blocks, without shared memory: the slowly mixing spec triggers it)
+    assert not re.search(r'block 32 smem [1-9]', r.stderr)
     assert 'block 256 ' in r.stderr                     # wide kernels, 8 warps (N = 40)
     # structural ties: the chunked Viterbi flags decisions on its path and the sequential team kernel takes over
     r = _drive(1, ['ties'], trace=True)
