@@ -1649,6 +1649,146 @@ __global__ void __launch_bounds__(((NMAX + 31) / 32) * 32) k_viterbi_regs(const 
 }
 
 // ================================================================================================
+// Viterbi for 32 < N <= 128 with the transition matrix in SHARED memory and R trajectories per block ("k_viterbi_multi").
+//
+// k_viterbi_regs keeps A[:, j] in registers: 208 registers per thread, two blocks (= two trajectories) per SM, and every
+// frame is one long dependent chain -- compare-select scan, then the 104-long sequential row sum: measured 4.2-4.7 s for C4's
+// 4.096e8 frames, no faster than the team kernel.  Here thread j still owns state j, but A is read from shared memory
+// (row-major with a padded stride: thread j reads A[i][j], consecutive words, conflict-free) and is shared by the R
+// trajectories the block walks in lock step: the loaded entry is used R times, the R scans and the R sequential sums are
+// independent instruction streams that fill each other's latency, and only the running maximum and its index are carried
+// through the scan (the winning v_i and A_ij are re-read from shared memory afterwards instead of being dragged along by
+// selects).  Warp r computes the sequential sum of trajectory r.  Arithmetic and order are _hidden.c:229-265's: products
+// v_i A_ij, first maximum with strict '>', (p_j v_best) A_best,j, j-sequential sum, true division: bit-exact.
+// Output: the shifted back-pointer map of k_viterbi_team's CHASE mode (uint8), resolved by the k_chase_* kernels.
+// ================================================================================================
+template <int EM, int R>
+__global__ void __launch_bounds__(128) k_viterbi_multi(const VitArgs a, int NPS)
+{
+    extern __shared__ double vsm[];
+    const int N = a.N, j = threadIdx.x, nthr = blockDim.x, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double* const As = vsm;                                 // [N][NPS]
+    double* const vb = As + (size_t)N * NPS;                // [R][NPS] normalised rows
+    double* const ub = vb + R * NPS;                        // [R][NPS] unnormalised rows
+    double* const ssum = ub + R * NPS;                      // [R]
+    int* const anynz = reinterpret_cast<int*>(ssum + R);    // [R][4] per warp: any density != 0 (outlier rule)
+    const bool jv = j < N;
+    for (int k = threadIdx.x; k < N * NPS; k += nthr) {
+        const int i = k / NPS, c = k - i * NPS;
+        As[k] = (c < N) ? a.A[i * N + c] : 0.0;
+    }
+    for (int k = threadIdx.x; k < 2 * R * NPS; k += nthr) vb[k] = 0.0;
+    double mu = 0.0, sigma = 1.0;
+    if (EM == EM_GAUSS && jv) { mu = a.em.mu[j]; sigma = a.em.sigma[j]; }
+    const double pi_j = jv ? a.pi[j] : 0.0;
+    unsigned char* bp = reinterpret_cast<unsigned char*>(a.backptr);
+    const bool outl = (EM != EM_POBS) && a.em.ignore_outliers;
+    __syncthreads();
+
+    for (int k0 = blockIdx.x * R; k0 < a.K; k0 += gridDim.x * R) {
+        long long row0[R];
+        int T[R], Tmax = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = k0 + r;
+            row0[r] = (k < a.K) ? a.offsets[k] : 0;
+            T[r] = (k < a.K) ? (int)(a.offsets[k + 1] - row0[r]) : 0;
+            Tmax = max(Tmax, T[r]);
+        }
+        auto em_raw = [&](int r, int t) -> double {
+            if (!jv || t >= T[r]) return 0.0;
+            const long long row = row0[r] + t;
+            if (EM == EM_POBS) return a.em.pobs[row * N + j];
+            if (EM == EM_GAUSS) return a.em.obs[row];
+            return a.em.Bt[(long long)a.em.sym[row] * N + j];
+        };
+        double raw_next[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) raw_next[r] = em_raw(r, 0);
+        for (int t = 0; t < Tmax; ++t) {
+            double p[R], vn[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double raw = raw_next[r];
+                raw_next[r] = em_raw(r, t + 1);
+                p[r] = 0.0;
+                if (jv && t < T[r]) p[r] = (EM == EM_GAUSS) ? gauss_pdf(raw, mu, sigma) : raw;
+            }
+            if (outl) {                                     // outputmodel.py:126-130, one vote per trajectory
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const unsigned nzw = __ballot_sync(FULL, p[r] != 0.0);
+                    if ((threadIdx.x & 31) == 0) anynz[r * 4 + wid] = nzw != 0u;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    int any = 0;
+                    for (int w2 = 0; w2 < nwarp; ++w2) any |= anynz[r * 4 + w2];
+                    if (!any) p[r] = (jv && t < T[r]) ? 1.0 : 0.0;
+                }
+            }
+            if (t == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) vn[r] = __dmul_rn(p[r], pi_j);
+            } else {
+                double m[R];
+                int bi[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) { m[r] = __dmul_rn(vb[r * NPS], As[j]); bi[r] = 0; }
+#pragma unroll 4
+                for (int i = 1; i < N; ++i) {
+                    const double aij = As[i * NPS + j];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double h = __dmul_rn(vb[r * NPS + i], aij);
+                        if (h > m[r]) { m[r] = h; bi[r] = i; }              // first maximum, _hidden.c:186-200
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (jv && t < T[r]) bp[(row0[r] + t - 1) * N + j] = (unsigned char)bi[r];
+                    vn[r] = __dmul_rn(__dmul_rn(p[r], vb[r * NPS + bi[r]]), As[bi[r] * NPS + j]);   // _hidden.c:247-250
+                }
+            }
+            // (ub's readers -- the sums of the previous frame -- finished before that frame's third barrier)
+            if (j < NPS) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) ub[r * NPS + j] = (jv && t < T[r]) ? vn[r] : 0.0;
+            }
+            __syncthreads();
+            for (int r = wid; r < R; r += nwarp) {          // j-sequential sum (_hidden.c:254-259), one warp per trajectory
+                double sacc = 0.0;
+                for (int i = 0; i < N; ++i) sacc = __dadd_rn(sacc, ub[r * NPS + i]);
+                if ((threadIdx.x & 31) == 0) ssum[r] = sacc;
+            }
+            __syncthreads();
+            if (j < NPS) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (t < T[r]) vb[r * NPS + j] = jv ? __ddiv_rn(vn[r], ssum[r]) : 0.0;
+            }
+            __syncthreads();
+        }
+        // path[T-1] = first maximum of the last row (_hidden.c:268): the last row of the map holds it for every s'
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (T[r] <= 0) continue;
+            int best = 0;
+            double mm = vb[r * NPS];
+            for (int i = 1; i < N; ++i) {
+                const double x = vb[r * NPS + i];
+                if (x > mm) { mm = x; best = i; }
+            }
+            if (jv) bp[(row0[r] + T[r] - 1) * N + j] = (unsigned char)best;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < 2 * R * NPS; k += nthr) vb[k] = 0.0;
+        __syncthreads();
+    }
+}
+
+// ================================================================================================
 // Time-chunked Viterbi, N <= 32 (C5: one trajectory of 1e9 frames, where the strictly sequential recursion of
 // k_viterbi_team would take minutes).  One warp per chain, lane j = state j, A[:, j] in registers.  A chain that does not
 // start its trajectory warms its normalised max-product vector up on the frames before it (the max-product filter forgets
@@ -1980,10 +2120,31 @@ int panel_stats_rows(int N, int n_chains)
 // Viterbi with the matrix column in registers: 32 < N <= 104 (N <= 32 keeps the packed one-warp teams)
 bool panel_viterbi_ok(int N) { return panel_mode() > 0 && N > 32 && N <= 104; }
 
+#ifndef VITERBI_MULTI_R
+#define VITERBI_MULTI_R 4
+#endif
+
 template <int EM>
 static int launch_viterbi_regs_em(const VitArgs& a, cudaStream_t st)
 {
     if (a.K <= 0) return BHMM_OK;
+    static int use_regs = -1;                               // BHMM_B200_VITERBI_REGS=1: the register kernel (comparison)
+    if (use_regs < 0) { const char* e = getenv("BHMM_B200_VITERBI_REGS"); use_regs = (e && e[0] == '1') ? 1 : 0; }
+    if (!use_regs) {
+        constexpr int R = VITERBI_MULTI_R;
+        const int threads = a.N <= 64 ? 64 : 128;
+        const int NPS = (a.N + 1) & ~1;
+        const size_t smem = sizeof(double) * ((size_t)a.N * NPS + 2 * (size_t)R * NPS + R) + sizeof(int) * 4 * R;
+        if (cudaFuncSetAttribute(k_viterbi_multi<EM, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            bhmm_set_error(BHMM_ERR_CUDA, "cudaFuncSetAttribute failed for k_viterbi_multi");
+            return BHMM_ERR_CUDA;
+        }
+        int per = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_viterbi_multi<EM, R>, threads, smem) != cudaSuccess || per <= 0) per = 1;
+        const long long groups = ((long long)a.K + R - 1) / R;
+        k_viterbi_multi<EM, R><<<(int)std::min<long long>(groups, (long long)panel_sms() * per), threads, smem, st>>>(a, NPS);
+        return BHMM_OK;
+    }
     int per = 0;
     if (a.N <= 64) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_viterbi_regs<EM, 64>, 64, 0) != cudaSuccess || per <= 0) per = 1;

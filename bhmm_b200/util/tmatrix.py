@@ -132,11 +132,15 @@ def sample_P_reversible(C, nsteps=1000, P0=None, rng=None):
 
     Parametrisation: a symmetric non-negative weight matrix X with T_ij = x_ij / sum_k x_ik, which is reversible with
     stationary vector proportional to the row sums of X.  Target: prod_ij T_ij^(c_ij) with respect to the flat measure on
-    the x_ij (i <= j) -- c_ij are the caller's posterior counts, i.e. observed counts plus prior counts, exactly what the
-    reference hands to its sampler.  `nsteps` Metropolis sweeps over the weights on the sparsity pattern of C + C^T,
-    log-normal random-walk proposals (the Jacobian of the log parametrisation is part of the acceptance ratio), started
-    at the reversible maximum-likelihood estimate (or P0); the scale of X, which T does not depend on, is renormalised
-    after every sweep.
+    the NORMALISED weights (the simplex sum_{i<=j} x_ij = 1) -- c_ij are the caller's posterior counts, i.e. observed
+    counts plus prior counts, exactly what the reference hands to its sampler.  T does not depend on the scale of X, so
+    the flat measure on the unnormalised weights would be improper (round-1 advisor finding: a chain that is merely
+    renormalised after every sweep samples a 1/x-type prior instead); the scale is therefore given an independent
+    Exp(1) weight per x_ij -- normalised independent Gamma(1, 1) variables are uniform on the simplex and independent of
+    their sum -- which makes the target proper without changing the law of T.  `nsteps` Metropolis sweeps over the
+    weights on the sparsity pattern of C + C^T, log-normal random-walk proposals (the Jacobian of the log
+    parametrisation is part of the acceptance ratio), started at the reversible maximum-likelihood estimate (or P0)
+    scaled to the prior mean of the total weight.
     """
     rng = np.random.default_rng() if rng is None else rng
     C = np.asarray(C, dtype=np.float64)
@@ -151,6 +155,7 @@ def sample_P_reversible(C, nsteps=1000, P0=None, rng=None):
     X = 0.5 * (X + X.T)
     Csym = C + C.T
     pattern = [(i, j) for i in range(n) for j in range(i, n) if Csym[i, j] > 0 and X[i, j] > 0]
+    X *= len(pattern) / sum(X[i, j] for (i, j) in pattern)     # total weight at its prior mean (one Exp(1) per weight)
     rows = X.sum(axis=1)
     crow = C.sum(axis=1)
     sigma = 0.5
@@ -167,7 +172,7 @@ def sample_P_reversible(C, nsteps=1000, P0=None, rng=None):
                 ri, rj = rows[i] + d, rows[j] + d
                 dlog = (C[i, j] + C[j, i]) * np.log(new / old) - crow[i] * np.log(ri / rows[i]) \
                     - crow[j] * np.log(rj / rows[j])
-            dlog += np.log(new / old)                    # Jacobian of the log-normal proposal
+            dlog += np.log(new / old) - d                # Jacobian of the log-normal proposal; Exp(1) weight of x_ij
             if np.log(rng.random()) < dlog:
                 X[i, j] = new
                 if i == j:
@@ -175,7 +180,5 @@ def sample_P_reversible(C, nsteps=1000, P0=None, rng=None):
                 else:
                     X[j, i] = new
                     rows[i], rows[j] = ri, rj
-        tot = rows.sum()
-        X /= tot
-        rows /= tot
+        rows = X.sum(axis=1)                             # (recomputed once per sweep: no drift of the running sums)
     return X / rows[:, None]

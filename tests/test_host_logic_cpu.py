@@ -283,3 +283,31 @@ def test_reference_arm_runs_without_the_product_library(tmp_path):
     assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['cores'] >= 1
     assert line['cpu_baseline']['single_core_as_shipped'] > 0 and line['e2e']['h2d_bytes_per_step'] == 0
     assert 'CLEAN' in r.stdout
+
+
+def test_reversible_sampler_matches_numerical_integration_at_small_counts():
+    """util/tmatrix.sample_P_reversible against its documented target on a 2 x 2 count matrix with SMALL counts (where the
+    prior matters: large-count tests cannot tell a flat prior on the simplex from a 1/x-type prior -- round-1 advisor
+    finding).  Target: prod T_ij^c_ij under the flat measure on the normalised symmetric weights (x00, x01, x11);
+    T01 = x01 / (x00 + x01), T10 = x01 / (x01 + x11).  Reference values by a 600 x 600 grid on the simplex."""
+    from bhmm_b200.util import tmatrix
+    Cm = np.array([[2.0, 1.0], [1.0, 3.0]])
+    g = (np.arange(600) + 0.5) / 600.0
+    x00, x01 = np.meshgrid(g, g, indexing='ij')
+    x11 = 1.0 - x00 - x01
+    ok = x11 > 0
+    with np.errstate(invalid='ignore', divide='ignore'):
+        t01 = x01 / (x00 + x01)
+        t10 = x01 / (x01 + x11)
+        dens = np.where(ok, (1 - t01) ** Cm[0, 0] * t01 ** Cm[0, 1] * t10 ** Cm[1, 0] * (1 - t10) ** Cm[1, 1], 0.0)
+    dens = np.nan_to_num(dens)
+    want01 = float((dens * np.nan_to_num(t01)).sum() / dens.sum())
+    want10 = float((dens * np.nan_to_num(t10)).sum() / dens.sum())
+    rng = np.random.default_rng(12)
+    draws = np.array([tmatrix.sample_P_reversible(Cm, nsteps=12, rng=rng) for _ in range(2500)])
+    got01, got10 = draws[:, 0, 1].mean(), draws[:, 1, 0].mean()
+    assert abs(got01 - want01) < 0.02 and abs(got10 - want10) < 0.02, ((got01, got10), (want01, want10))
+    for T in draws[:50]:                                   # every draw is stochastic and reversible
+        assert np.allclose(T.sum(axis=1), 1.0)
+        pi = tmatrix.stationary_vector(T)
+        assert np.allclose(pi[:, None] * T, (pi[:, None] * T).T)
