@@ -1662,22 +1662,40 @@ __global__ void __launch_bounds__(((NMAX + 31) / 32) * 32) k_viterbi_regs(const 
 // v_i A_ij, first maximum with strict '>', (p_j v_best) A_best,j, j-sequential sum, true division: bit-exact.
 // Output: the shifted back-pointer map of k_viterbi_team's CHASE mode (uint8), resolved by the k_chase_* kernels.
 // ================================================================================================
+// SUB independent groups of `sthr` threads ("sub-blocks") share ONE copy of the transition matrix in shared memory: the
+// matrix (83 KB at N = 100) limits an SM to two blocks, and with one group per block that is two warps per scheduler; four
+// groups per block make it eight.  The groups synchronise among themselves with named barriers (bar.sync id, sthr).
+__device__ __forceinline__ void sub_barrier(int sub, int sthr, int nsub)
+{
+#ifdef PANEL_HOST_EMU
+    __syncthreads();                                        // the emulated build runs one group per block
+#else
+    if (nsub == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "r"(sthr) : "memory");
+#endif
+}
+
+#ifndef VITERBI_MULTI_MINB
+#define VITERBI_MULTI_MINB 1
+#endif
 template <int EM, int R>
-__global__ void __launch_bounds__(128) k_viterbi_multi(const VitArgs a, int NPS)
+__global__ void __launch_bounds__(512, VITERBI_MULTI_MINB) k_viterbi_multi(const VitArgs a, int NPS, int sthr)
 {
     extern __shared__ double vsm[];
-    const int N = a.N, j = threadIdx.x, nthr = blockDim.x, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    double* const As = vsm;                                 // [N][NPS]
-    double* const vb = As + (size_t)N * NPS;                // [R][NPS] normalised rows
+    const int N = a.N, nsub = blockDim.x / sthr, sub = threadIdx.x / sthr;
+    const int j = threadIdx.x - sub * sthr, nthr = sthr, wid = j >> 5, nwarp = sthr >> 5;
+    double* const As = vsm;                                 // [N][NPS], shared by the groups
+    const size_t per_sub = 2 * (size_t)R * NPS + R + 2 * R; // doubles per group: vb, ub, ssum, anynz (as 4 R ints)
+    double* const vb = As + (size_t)N * NPS + sub * per_sub;   // [R][NPS] normalised rows
     double* const ub = vb + R * NPS;                        // [R][NPS] unnormalised rows
     double* const ssum = ub + R * NPS;                      // [R]
     int* const anynz = reinterpret_cast<int*>(ssum + R);    // [R][4] per warp: any density != 0 (outlier rule)
     const bool jv = j < N;
-    for (int k = threadIdx.x; k < N * NPS; k += nthr) {
+    for (int k = threadIdx.x; k < N * NPS; k += blockDim.x) {
         const int i = k / NPS, c = k - i * NPS;
         As[k] = (c < N) ? a.A[i * N + c] : 0.0;
     }
-    for (int k = threadIdx.x; k < 2 * R * NPS; k += nthr) vb[k] = 0.0;
+    for (int k = j; k < 2 * R * NPS; k += nthr) vb[k] = 0.0;
     double mu = 0.0, sigma = 1.0;
     if (EM == EM_GAUSS && jv) { mu = a.em.mu[j]; sigma = a.em.sigma[j]; }
     const double pi_j = jv ? a.pi[j] : 0.0;
@@ -1685,7 +1703,7 @@ __global__ void __launch_bounds__(128) k_viterbi_multi(const VitArgs a, int NPS)
     const bool outl = (EM != EM_POBS) && a.em.ignore_outliers;
     __syncthreads();
 
-    for (int k0 = blockIdx.x * R; k0 < a.K; k0 += gridDim.x * R) {
+    for (int k0 = (blockIdx.x * nsub + sub) * R; k0 < a.K; k0 += gridDim.x * nsub * R) {
         long long row0[R];
         int T[R], Tmax = 0;
 #pragma unroll
@@ -1718,9 +1736,9 @@ __global__ void __launch_bounds__(128) k_viterbi_multi(const VitArgs a, int NPS)
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const unsigned nzw = __ballot_sync(FULL, p[r] != 0.0);
-                    if ((threadIdx.x & 31) == 0) anynz[r * 4 + wid] = nzw != 0u;
+                    if ((j & 31) == 0) anynz[r * 4 + wid] = nzw != 0u;
                 }
-                __syncthreads();
+                sub_barrier(sub, sthr, nsub);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     int any = 0;
@@ -1736,13 +1754,35 @@ __global__ void __launch_bounds__(128) k_viterbi_multi(const VitArgs a, int NPS)
                 int bi[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) { m[r] = __dmul_rn(vb[r * NPS], As[j]); bi[r] = 0; }
-#pragma unroll 4
-                for (int i = 1; i < N; ++i) {
-                    const double aij = As[i * NPS + j];
+                // two predecessor states per step: the rows' entries arrive as one 16-byte broadcast load per trajectory (the
+                // scan is bound by the LSU wavefronts of these loads, 2 per LDS.64 against 2.4 per LDS.128)
+                int i = 1;
+                if (N > 1) {
+                    const double a1 = As[NPS + j];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const double h = __dmul_rn(vb[r * NPS + i], aij);
-                        if (h > m[r]) { m[r] = h; bi[r] = i; }              // first maximum, _hidden.c:186-200
+                        const double h = __dmul_rn(vb[r * NPS + 1], a1);
+                        if (h > m[r]) { m[r] = h; bi[r] = 1; }              // first maximum, _hidden.c:186-200
+                    }
+                    i = 2;
+                }
+#pragma unroll 2
+                for (; i + 1 < N; i += 2) {
+                    const double a0 = As[i * NPS + j], a1 = As[(i + 1) * NPS + j];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double2 v2 = *reinterpret_cast<const double2*>(vb + r * NPS + i);
+                        const double h0 = __dmul_rn(v2.x, a0), h1 = __dmul_rn(v2.y, a1);
+                        if (h0 > m[r]) { m[r] = h0; bi[r] = i; }
+                        if (h1 > m[r]) { m[r] = h1; bi[r] = i + 1; }
+                    }
+                }
+                if (i < N) {
+                    const double a0 = As[i * NPS + j];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double h = __dmul_rn(vb[r * NPS + i], a0);
+                        if (h > m[r]) { m[r] = h; bi[r] = i; }
                     }
                 }
 #pragma unroll
@@ -1756,19 +1796,33 @@ __global__ void __launch_bounds__(128) k_viterbi_multi(const VitArgs a, int NPS)
 #pragma unroll
                 for (int r = 0; r < R; ++r) ub[r * NPS + j] = (jv && t < T[r]) ? vn[r] : 0.0;
             }
-            __syncthreads();
-            for (int r = wid; r < R; r += nwarp) {          // j-sequential sum (_hidden.c:254-259), one warp per trajectory
-                double sacc = 0.0;
-                for (int i = 0; i < N; ++i) sacc = __dadd_rn(sacc, ub[r * NPS + i]);
-                if ((threadIdx.x & 31) == 0) ssum[r] = sacc;
+            sub_barrier(sub, sthr, nsub);
+            {   // j-sequential sums (_hidden.c:254-259): warp w adds up the rows w, w + nwarp, ... -- up to four independent
+                // chains of additions interleaved in one loop
+                constexpr int RW = (R + 1) / 2;             // rows per warp at two warps per block (the fewest)
+                double sacc[RW];
+#pragma unroll
+                for (int q = 0; q < RW; ++q) sacc[q] = 0.0;
+                for (int i = 0; i < N; ++i) {
+#pragma unroll
+                    for (int q = 0; q < RW; ++q) {
+                        const int r = wid + q * nwarp;
+                        if (r < R) sacc[q] = __dadd_rn(sacc[q], ub[r * NPS + i]);
+                    }
+                }
+                if ((j & 31) == 0) {
+#pragma unroll
+                    for (int q = 0; q < RW; ++q)
+                        if (wid + q * nwarp < R) ssum[wid + q * nwarp] = sacc[q];
+                }
             }
-            __syncthreads();
+            sub_barrier(sub, sthr, nsub);
             if (j < NPS) {
 #pragma unroll
                 for (int r = 0; r < R; ++r)
                     if (t < T[r]) vb[r * NPS + j] = jv ? __ddiv_rn(vn[r], ssum[r]) : 0.0;
             }
-            __syncthreads();
+            sub_barrier(sub, sthr, nsub);
         }
         // path[T-1] = first maximum of the last row (_hidden.c:268): the last row of the map holds it for every s'
 #pragma unroll
@@ -1782,9 +1836,9 @@ __global__ void __launch_bounds__(128) k_viterbi_multi(const VitArgs a, int NPS)
             }
             if (jv) bp[(row0[r] + T[r] - 1) * N + j] = (unsigned char)best;
         }
-        __syncthreads();
-        for (int k = threadIdx.x; k < 2 * R * NPS; k += nthr) vb[k] = 0.0;
-        __syncthreads();
+        sub_barrier(sub, sthr, nsub);
+        for (int k = j; k < 2 * R * NPS; k += nthr) vb[k] = 0.0;
+        sub_barrier(sub, sthr, nsub);
     }
 }
 
@@ -2132,17 +2186,23 @@ static int launch_viterbi_regs_em(const VitArgs& a, cudaStream_t st)
     if (use_regs < 0) { const char* e = getenv("BHMM_B200_VITERBI_REGS"); use_regs = (e && e[0] == '1') ? 1 : 0; }
     if (!use_regs) {
         constexpr int R = VITERBI_MULTI_R;
-        const int threads = a.N <= 64 ? 64 : 128;
+        const int sthr = a.N <= 64 ? 64 : 128;              // threads of a group: one per state
+#ifdef PANEL_HOST_EMU
+        const int nsub = 1;
+#else
+        const long long groups_all = ((long long)a.K + R - 1) / R;
+        const int nsub = (int)std::max<long long>(1, std::min<long long>(512 / sthr, (groups_all + panel_sms() - 1) / panel_sms()));
+#endif
         const int NPS = (a.N + 1) & ~1;
-        const size_t smem = sizeof(double) * ((size_t)a.N * NPS + 2 * (size_t)R * NPS + R) + sizeof(int) * 4 * R;
+        const size_t smem = sizeof(double) * ((size_t)a.N * NPS + (size_t)nsub * (2 * (size_t)R * NPS + R + 2 * R));
         if (cudaFuncSetAttribute(k_viterbi_multi<EM, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             bhmm_set_error(BHMM_ERR_CUDA, "cudaFuncSetAttribute failed for k_viterbi_multi");
             return BHMM_ERR_CUDA;
         }
         int per = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_viterbi_multi<EM, R>, threads, smem) != cudaSuccess || per <= 0) per = 1;
-        const long long groups = ((long long)a.K + R - 1) / R;
-        k_viterbi_multi<EM, R><<<(int)std::min<long long>(groups, (long long)panel_sms() * per), threads, smem, st>>>(a, NPS);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_viterbi_multi<EM, R>, nsub * sthr, smem) != cudaSuccess || per <= 0) per = 1;
+        const long long groups = ((long long)a.K + (long long)R * nsub - 1) / ((long long)R * nsub);
+        k_viterbi_multi<EM, R><<<(int)std::min<long long>(groups, (long long)panel_sms() * per), nsub * sthr, smem, st>>>(a, NPS, sthr);
         return BHMM_OK;
     }
     int per = 0;
