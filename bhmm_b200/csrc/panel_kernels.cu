@@ -41,6 +41,13 @@ constexpr int PSTRIDE = 36;       // doubles per chain row of the transposition 
                                   // half warp, so the operand loads of the xi product are bank-conflict free
 constexpr unsigned FULL = 0xffffffffu;
 
+// dynamic shared memory of a kernel; the CPU emulation (tests/emu) hands out its own buffer
+#ifdef PANEL_HOST_EMU
+#define PANEL_DYN_SMEM(name) double* name = reinterpret_cast<double*>(emu::dyn_smem())
+#else
+#define PANEL_DYN_SMEM(name) extern __shared__ double name[]
+#endif
+
 // PANEL_HOST_EMU: the kernels' source compiled for the CPU by tests/emu (every CUDA thread a fiber, collectives emulated)
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 {
@@ -1061,7 +1068,7 @@ template <int EM, int NT, bool OUTL>
 __global__ void WIDE_KERNEL_ATTR(NT) k_forward_wide2(const FwdArgs a)
 {
     constexpr int KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS, NR = OUTL ? 3 : 1, ROW = PCH * NPS;
-    extern __shared__ double wsm[];
+    PANEL_DYN_SMEM(wsm);
     double* const Sx = wsm;                                 // [WS][2][ROW]   the frame's vector with the densities ...
     double* const Sd = Sx + WS * 2 * ROW;                   // [WS][2][ROW]   ... and with all densities set to one (OUTL only)
     double* const red = Sd + (OUTL ? WS * 2 * ROW : 0);     // [WS][2][NR][NT][PCH] per tile and chain: sum of Sx (, sum of Sd, any density != 0)
@@ -1268,7 +1275,7 @@ template <int EM, int NT, bool OUTL, bool BSM, int WS>
 __global__ void WIDE_KERNEL_ATTR(NT) k_backward_stats_wide2(const BwdArgs a)
 {
     constexpr int KS = WideGeom<NT>::KS, NPS = WideGeom<NT>::NPS, ROW = PCH * NPS;
-    extern __shared__ double wsm[];
+    PANEL_DYN_SMEM(wsm);
     double* const Sw = wsm;                                 // [WS][2][ROW]
     double* const Sb = Sw + WS * 2 * ROW;                   // [WS][2][ROW]  (OUTL only)
     double* const Su = Sb + (OUTL ? WS * 2 * ROW : 0);      // [WS][ROW]
@@ -1681,7 +1688,7 @@ __device__ __forceinline__ void sub_barrier(int sub, int sthr, int nsub)
 template <int EM, int R>
 __global__ void __launch_bounds__(512, VITERBI_MULTI_MINB) k_viterbi_multi(const VitArgs a, int NPS, int sthr)
 {
-    extern __shared__ double vsm[];
+    PANEL_DYN_SMEM(vsm);
     const int N = a.N, nsub = blockDim.x / sthr, sub = threadIdx.x / sthr;
     const int j = threadIdx.x - sub * sthr, nthr = sthr, wid = j >> 5, nwarp = sthr >> 5;
     double* const As = vsm;                                 // [N][NPS], shared by the groups

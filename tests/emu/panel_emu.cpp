@@ -5,6 +5,11 @@
 #define PANEL_HOST_NO_LAUNCHERS 1   // no <<<>>> launchers, no CUDA runtime: the kernels are called directly below
 #include "warp_emu.h"
 
+#include <vector>
+// dynamic shared memory of the kernels that use it (wide2, k_viterbi_multi: not driven from this file, they only have to
+// compile here; tests/test_engine_emulated_cpu.py runs them through the hostified launchers and cuda_fake.h)
+namespace emu { inline double* dyn_smem() { static std::vector<double> b(1 << 16); return b.data(); } }
+
 #include "../../bhmm_b200/csrc/panel_kernels.cu"
 
 namespace {

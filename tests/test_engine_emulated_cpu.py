@@ -31,8 +31,12 @@ def engine_emu():
     return so
 
 
-def _drive(mode, specs, trace=False, tiled_chase=False):
+def _drive(mode, specs, trace=False, tiled_chase=False, exact_scan=False):
     env = dict(os.environ, BHMM_B200_PANEL=str(mode))
+    if not exact_scan:
+        # the slowly mixing specs are there for the repair-sweep paths; the exact scan (which would replace most of those
+        # sweeps, and whose N x 32-thread operator blocks are slow to emulate) has its own small test below
+        env['BHMM_B200_EXACT_SCAN'] = '0'
     if tiled_chase:
         env['BHMM_B200_CHASE_TILED'] = '1'              # the link kernel for batches with very many segments, forced
     if trace:
@@ -72,6 +76,13 @@ def test_wide_kernels_at_n32_and_n100_through_the_engine(engine_emu):
     _drive(2, ['32,40,40', '32,40,2,300', 'v32', 'w32'])
     r = _drive(1, ['100,40,40'], trace=True)
     assert 'block 416 ' in r.stderr
+
+
+def test_exact_scan_on_the_emulator(engine_emu):
+    """A slowly mixing 6-state model with a two-frame warm-up: the first repair sweep does not clear the failed hand-overs, the
+    transfer-operator scan (scan_kernels.cu) supplies exact starts in both directions, and the E-step still equals the oracle."""
+    r = _drive(0, ['6,40,2,300'], trace=True, exact_scan=True)
+    assert r.stderr.count('block 192 ') >= 2             # k_chain_operator: 32 N threads, forward and backward
 
 
 def test_tiled_chase_link_forced(engine_emu):
