@@ -778,20 +778,31 @@ class TimeShardedTrajectories(object):
 
     def viterbi_resolve(self, model, end_states, kind='gaussian'):
         """Phase 2: resolve the paths given the state of every trajectory at this shard's last owned frame (None / -1: the
-        shard holds the trajectory's end).  Returns (list of owned-range paths (int32 numpy), states at frame lo - 1)."""
+        shard holds the trajectory's end).  Returns the states at frame lo - 1 (what the shard to the left needs); the paths
+        stay on the GPU until ``viterbi_paths`` (so that the hops from shard to shard do not wait for bulk copies)."""
         vb = self._viterbi_batch()
         vb.set_viterbi_phase(2)
         for k in range(self.K):
             vb.set_viterbi_end_state(k, -1 if end_states is None else int(end_states[k]))
-        flat = self._viterbi_call(model, kind).cpu().numpy()
-        paths, left = [], []
+        flat = self._viterbi_call(model, kind)               # device tensor: only the states handed to the left leave the GPU here
+        idx = [int(vb.offsets[k]) + vb._own_ranges[k][0] - 1 for k in range(self.K)]
+        take = self.batch.torch.tensor([max(i, 0) for i in idx], dtype=self.batch.torch.int64, device=flat.device)
+        got = flat[take].cpu().numpy()
+        left = [int(got[k]) if vb._own_ranges[k][0] > 0 else -1 for k in range(self.K)]
+        self._vflat = flat
+        return left
+
+    def viterbi_paths(self):
+        """The owned-range paths of the last ``viterbi_resolve`` as int32 numpy arrays (one device-to-host copy)."""
+        vb = self._viterbi_batch()
+        flat = self._vflat.cpu().numpy()
+        paths = []
         for k in range(self.K):
             lo_l, hi_l = vb._own_ranges[k]
             r0 = int(vb.offsets[k])
             lo_g, hi_g, _ = self.global_ranges[k]
             paths.append(flat[r0 + lo_l:r0 + hi_l].copy() if hi_g > lo_g else np.zeros(0, dtype=np.int32))
-            left.append(int(flat[r0 + lo_l - 1]) if lo_l > 0 else -1)
-        return paths, left
+        return paths
 
     @staticmethod
     def certify_viterbi(borders_by_rank, ranges_by_rank, tol):
@@ -817,7 +828,8 @@ class TimeShardedTrajectories(object):
         end = None
         for r in range(len(shards) - 1, -1, -1):
             own = [shards[r].global_ranges[k][1] > shards[r].global_ranges[k][0] for k in range(K)]
-            paths, left = shards[r].viterbi_resolve(model, end, kind)
+            left = shards[r].viterbi_resolve(model, end, kind)
+            paths = shards[r].viterbi_paths()
             for k in range(K):
                 parts[k][r] = paths[k]
             # a shard that owns nothing of trajectory k passes the state it received on to the left
@@ -837,15 +849,14 @@ class TimeShardedTrajectories(object):
                   for r in range(self.world)]
         worst = self.certify_viterbi([g.cpu().numpy() for g in gathered], ranges, self.tol)
         end = torch.full((self.K,), -1, dtype=torch.int64, device=dev)
-        paths = None
         for r in range(self.world - 1, -1, -1):
             if r == self.rank:
                 e = end.cpu().numpy()
-                paths, left = self.viterbi_resolve(model, None if r == self.world - 1 else e, kind)
+                left = self.viterbi_resolve(model, None if r == self.world - 1 else e, kind)
                 own = [ranges[r][k][1] > ranges[r][k][0] for k in range(self.K)]
                 end = torch.tensor([left[k] if own[k] else int(e[k]) for k in range(self.K)], dtype=torch.int64, device=dev)
             td.broadcast(end, src=r)
-        return paths, worst
+        return self.viterbi_paths(), worst              # all shards copy their paths to the host at the same time
 
     def viterbi_gaussian(self, A, pi, means, sigmas, ignore_outliers=True):
         return self.viterbi((A, pi, means, sigmas, ignore_outliers), 'gaussian')
