@@ -368,14 +368,23 @@ class Timer(object):
         return float(t.item())
 
 
+PHASE = {'estep': 0.0, 'reduce_mstep_readback': 0.0, 'n': 0}   # host-side phase times of em_step (both phases end synchronised)
+
+
 def em_step(batch, model, dist, N):
     """One Baum-Welch iteration through the public pieces: fused E-step, all-reduce of the packed statistics, M-step ON THE
     GPU (engine.mstep_device), one small device-to-host copy of the updated parameters + log-likelihood."""
     from bhmm_b200.engine import mstep_device, unpack_mstep
     A, pi, means, sigmas = model
+    t0 = time.perf_counter()
     stats = batch.estep_gaussian(A, pi, means, sigmas)
+    t1 = time.perf_counter()
     stats = dist.allreduce_sum(stats)
     res = unpack_mstep(mstep_device(stats, N, means_old=means).cpu().numpy(), N)
+    t2 = time.perf_counter()
+    PHASE['estep'] += t1 - t0
+    PHASE['reduce_mstep_readback'] += t2 - t1
+    PHASE['n'] += 1
     if res['flags']:
         raise RuntimeError('M-step flagged an empty count or a collapsed sigma (flags=%d)' % res['flags'])
     return (res['A'], res['pi'], res['means'], res['sigmas']), res['loglik']
@@ -431,6 +440,7 @@ def run_gaussian_em(args, torch, td, dev, world, rank, local):
     tm.barrier()
     launches0 = _lib.lib.bhmm_b200_launch_count()
     kms = {'forward': 0.0, 'backward_stats': 0.0}
+    PHASE.update(estep=0.0, reduce_mstep_readback=0.0, n=0)
     tm.start()
     for _ in range(args.steps):
         model, ll = em_step(batch, model, dist, N)
@@ -442,10 +452,16 @@ def run_gaussian_em(args, torch, td, dev, world, rank, local):
     clocks = sampler.stop() if rank == 0 else None
     value = world * rows * args.steps / (ms * 1e-3)
     info = batch.info()
-    rk = torch.tensor([float(launches), kms['forward'] + kms['backward_stats']], dtype=torch.float64, device=dev)
+    phase0 = {'estep_call_ms': 1e3 * PHASE['estep'] / args.steps, 'allreduce_mstep_readback_ms': 1e3 * PHASE['reduce_mstep_readback'] / args.steps}
+    rk = torch.tensor([float(launches), kms['forward'] + kms['backward_stats'], phase0['estep_call_ms'],
+                       phase0['allreduce_mstep_readback_ms'], -phase0['estep_call_ms'], -phase0['allreduce_mstep_readback_ms']],
+                      dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(rk, op=td.ReduceOp.MAX)
     max_rank_launches, max_rank_kernel_ms = int(rk[0].item()), float(rk[1].item()) / args.steps
+    # rank 0's phases and the spread over ranks: a fast rank waits for the slowest one inside its all-reduce
+    phases = {'rank0': phase0, 'estep_call_ms_min_max': [-float(rk[4].item()), float(rk[2].item())],
+              'allreduce_mstep_readback_ms_min_max': [-float(rk[5].item()), float(rk[3].item())]}
 
     # ---- Gibbs sweeps (second half of the metric), device resident, through the public sampler: forward + backward
     # sampling + path statistics on the GPU, all-reduce, read-back, and the HOST parameter draw
@@ -525,7 +541,8 @@ def run_gaussian_em(args, torch, td, dev, world, rank, local):
                    'certification': {'fixups_fwd': info['fixups_fwd'], 'fixups_bwd': info['fixups_bwd'],
                                      'worst_fwd': info['worst_fwd'], 'worst_bwd': info['worst_bwd'],
                                      'max_rank_launches': max_rank_launches,
-                                     'max_rank_kernel_ms_per_step': max_rank_kernel_ms}},
+                                     'max_rank_kernel_ms_per_step': max_rank_kernel_ms},
+                   'phases_ms_per_step': phases},
         'roofline': {'bound': 'hbm', 'kernel': ('k_backward_stats_%s' if dom == 'backward_stats' else 'k_forward_%s') % family,
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'peak_source': peak_src,
