@@ -416,6 +416,7 @@ def run_gaussian_em(args, torch, td, dev, world, rank, local):
     N, K, T, desc = WORKLOADS[args.workload]
     if args.trajectories:
         K = args.trajectories
+    dist.tune_for_world()
     Ktotal = K * world if args.scaling == 'weak' else K
     if args.scaling == 'strong':
         K = max(1, K // world)             # BASELINE config 3: 1024 trajectories in total, sharded over the GPUs

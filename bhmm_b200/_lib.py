@@ -47,6 +47,7 @@ _proto('bhmm_b200_device_count', C.c_int)
 _proto('bhmm_b200_launch_count', C.c_ulonglong)
 _proto('bhmm_b200_set_chunking', None, C.c_int, C.c_int)
 _proto('bhmm_b200_set_certify_tolerance', None, C.c_double)
+_proto('bhmm_b200_set_warm_margin', None, C.c_double)
 _proto('bhmm_b200_last_info', None, _dp)
 # host-pointer drop-ins
 _proto('bhmm_b200_forward', C.c_double, _dp, _dp, _dp, _dp, C.c_int, C.c_int)

@@ -17,6 +17,7 @@ static thread_local char t_msg[512] = "";
 static std::mutex g_lit_mutex;          // the literal API shares one scratch arena
 static Arena g_lit_arena;
 static int g_chunk_override = 0, g_warm_override = 0;
+static double g_warm_margin = 0.0;      // added to the safety factors of adapt_warm (bhmm_b200_set_warm_margin)
 static RunInfo g_last_info;
 static GlibcRand g_rand;
 static unsigned long long* g_pinned_cert = nullptr;
@@ -159,11 +160,11 @@ int adapt_warm(int current, double need, double worst, bool failed, int warm_min
     } else if (worst <= 1e-14) {
         edge[1] += 1.0;
         if (edge[1] > 20.0) edge[0] *= 0.97;
-        target = std::max(0.95 * current, 1.12 * edge[0]);
+        target = std::max(0.95 * current, (1.12 + g_warm_margin) * edge[0]);
     } else {
         edge[0] = std::max(need, 0.97 * edge[0]);
         edge[1] = 0.0;
-        target = std::max(std::max(1.15 * need, 1.12 * edge[0]), 0.95 * current);
+        target = std::max(std::max((1.15 + g_warm_margin) * need, (1.12 + g_warm_margin) * edge[0]), 0.95 * current);
     }
     int w = (int)std::ceil(target / 16.0 - 1e-9) * 16;        // (1.12 x 300 is 336.00000000000006)
     w = std::max(w, warm_min);
@@ -185,7 +186,7 @@ size_t chainwork_bytes(int n, int N)
     cv.add<double>(n);
     for (int k = 0; k < 4; ++k) cv.add<double>((size_t)n * N);
     cv.add<int>(n);
-    cv.add<unsigned long long>(4);
+    cv.add<unsigned long long>(8);
     return cv.off + 256;
 }
 
@@ -203,7 +204,7 @@ int chainwork_setup(ChainWork& w, const HostPlan& p, int N, int warm, char* base
     w.hu_b = (double*)(base + cv.add<double>((size_t)n * N));
     w.he_b = (double*)(base + cv.add<double>((size_t)n * N));
     w.fail_list = (int*)(base + cv.add<int>(n));
-    w.cert_out = (unsigned long long*)(base + cv.add<unsigned long long>(4));
+    w.cert_out = (unsigned long long*)(base + cv.add<unsigned long long>(8));
     w.warm_cap = std::max(1, p.maxT);
     CUDA_TRY(cudaMemcpyAsync(row0, p.row0.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(len, p.len.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
@@ -225,7 +226,7 @@ int chainwork_setup(ChainWork& w, const HostPlan& p, int N, int warm, char* base
 long long certify_sync(ChainWork& w, int N, int dir, double* worst, cudaStream_t st, double tol_floor)
 {
     if (!g_pinned_cert) {
-        if (cudaMallocHost(&g_pinned_cert, 4 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+        if (cudaMallocHost(&g_pinned_cert, 8 * sizeof(unsigned long long)) != cudaSuccess) return -1;
     }
     Chains full = w.ch;
     full.list = nullptr;
@@ -244,6 +245,36 @@ long long certify_sync(ChainWork& w, int N, int dir, double* worst, cudaStream_t
     double& need = dir > 0 ? w.need_f : w.need_b;
     need = std::max(need, (double)g_pinned_cert[2]);       // callers reset it at the start of a pass
     return (long long)g_pinned_cert[0];
+}
+
+// Certification WITHOUT a host round trip: the verdict of direction `dir` goes to slot (dir > 0 ? 0 : 1) of the pinned result
+// buffer; certify_collect reads it after the caller's next synchronisation of the stream.
+int certify_async(ChainWork& w, int N, int dir, cudaStream_t st)
+{
+    if (!g_pinned_cert) {
+        if (cudaMallocHost(&g_pinned_cert, 8 * sizeof(unsigned long long)) != cudaSuccess) return BHMM_ERR_NO_MEM;
+    }
+    const int slot = dir > 0 ? 0 : 1;
+    Chains full = w.ch;
+    full.list = nullptr;
+    full.n = w.n_total;
+    full.warmv = nullptr;
+    launch_certify(full, w.n_total, N, dir, dir > 0 ? w.hu_f : w.hu_b, dir > 0 ? w.he_f : w.he_b, g_cert_tol, w.fail_list,
+                   w.cert_out + 4 * slot, st);
+    LAUNCHED(1);
+    CUDA_TRY(cudaMemcpyAsync(g_pinned_cert + 4 * slot, w.cert_out + 4 * slot, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    return BHMM_OK;
+}
+
+long long certify_collect(ChainWork& w, int dir, double* worst)
+{
+    const int slot = dir > 0 ? 0 : 1;
+    double wv;
+    memcpy(&wv, &g_pinned_cert[4 * slot + 1], sizeof(double));
+    if (worst) *worst = std::max(*worst, wv);
+    double& need = dir > 0 ? w.need_f : w.need_b;
+    need = std::max(need, (double)g_pinned_cert[4 * slot + 2]);
+    return (long long)g_pinned_cert[4 * slot];
 }
 
 int run_chains_certified(ChainWork& w, int N, int dir, const ChainLauncher& launch, RunInfo& info, cudaStream_t st)
@@ -365,6 +396,7 @@ extern "C" int bhmm_b200_device_count(void)
 extern "C" unsigned long long bhmm_b200_launch_count(void) { return g_launches.load(); }
 extern "C" void bhmm_b200_set_chunking(int chunk, int warm) { g_chunk_override = chunk; g_warm_override = warm; }
 extern "C" void bhmm_b200_set_certify_tolerance(double tol) { g_cert_tol = tol; }
+extern "C" void bhmm_b200_set_warm_margin(double extra) { g_warm_margin = extra < 0.0 ? 0.0 : (extra > 2.0 ? 2.0 : extra); }
 extern "C" void bhmm_b200_last_info(double info[8])
 {
     info[0] = g_last_info.chains; info[1] = g_last_info.chunk; info[2] = g_last_info.warm;

@@ -101,6 +101,8 @@ int run_backward(ChainWork& w, const Emission& em, int emkind, int N, const doub
 // certification read-back: returns number of failing chains (or <0 on CUDA error), updates worst
 constexpr double EXACT_SCAN_TOL = 1e-11;   // hand-over tolerance of the pass that follows the exact scan (capi.cu)
 long long certify_sync(ChainWork& w, int N, int dir, double* worst, cudaStream_t st, double tol_floor = 0.0);
+int certify_async(ChainWork& w, int N, int dir, cudaStream_t st);     // verdict into a pinned slot, no synchronisation
+long long certify_collect(ChainWork& w, int dir, double* worst);       // ... read after the stream was synchronised
 
 // glibc srand()/rand() restatement (TYPE_3, r[i] = r[i-31] + r[i-3]); reproduces the reference's uniforms
 struct GlibcRand {

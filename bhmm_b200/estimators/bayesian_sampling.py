@@ -43,6 +43,7 @@ class BayesianHMMSampler(object):
         self._np_rng = np.random.default_rng(self._rng.randint(0, 2 ** 31 - 1))
         self.stationary = stationary
         self.nstates = nstates
+        dist.tune_for_world()
         if shard and dist.world_size() > 1:
             lo, hi = dist.shard_bounds([len(o) for o in observations], dist.rank(), dist.world_size())
         else:

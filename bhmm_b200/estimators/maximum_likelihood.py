@@ -43,6 +43,7 @@ class MaximumLikelihoodEstimator(object):
         self._all_lengths = [len(o) for o in observations]
         self._nobs_total = len(observations)
         # trajectories of this rank
+        dist.tune_for_world()
         if shard and dist.world_size() > 1:
             lo, hi = dist.shard_bounds(self._all_lengths, dist.rank(), dist.world_size())
         else:

@@ -65,6 +65,10 @@ unsigned long long bhmm_b200_launch_count(void);
 void bhmm_b200_set_chunking(int chunk, int warm);
 /* Relative hand-over tolerance used by the certification (default 1e-13). */
 void bhmm_b200_set_certify_tolerance(double tol);
+/* Extra safety margin of the adaptive warm-up length (added to the factors 1.12 / 1.15 by which the warm-up is kept above the
+ * measured need).  A failed certification costs a repair sweep on ONE rank and a wait on all the others, so a job on W ranks
+ * wants failures W times rarer than a single process does: bhmm_b200.dist.tune_for_world() sets 0.04 log2(W). */
+void bhmm_b200_set_warm_margin(double extra);
 /* Diagnostics of the last chunked call: info[0]=chains, [1]=chunk, [2]=warm, [3]=fix-up sweeps (fwd),
  * [4]=fix-up sweeps (bwd), [5]=largest hand-over mismatch fwd, [6]= ... bwd, [7]=chains re-run. */
 void bhmm_b200_last_info(double info[8]);
