@@ -47,6 +47,7 @@ _proto('bhmm_b200_device_count', C.c_int)
 _proto('bhmm_b200_launch_count', C.c_ulonglong)
 _proto('bhmm_b200_set_chunking', None, C.c_int, C.c_int)
 _proto('bhmm_b200_set_certify_tolerance', None, C.c_double)
+_proto('bhmm_b200_set_repair_tolerance', None, C.c_double)
 _proto('bhmm_b200_set_warm_margin', None, C.c_double)
 _proto('bhmm_b200_last_info', None, _dp)
 # host-pointer drop-ins
@@ -106,7 +107,12 @@ _proto('bhmm_b200_gibbs_discrete', C.c_int, _vp, _vp, _dp, _dp, _dp, C.c_int, C.
        C.c_ulonglong, _vp, _vp, _dp, _vp)
 _proto('bhmm_b200_mstep_dev', C.c_int, _vp, _vp, C.c_int, C.c_double, _vp, _vp)
 _proto('bhmm_b200_mstep_discrete_dev', C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp)
+_proto('bhmm_b200_upload_ragged', C.c_int, _vp, C.POINTER(C.c_void_p), _llp, C.c_int, C.c_int, _vp)
+_proto('bhmm_b200_download_ragged', C.c_int, C.POINTER(C.c_void_p), _vp, _llp, C.c_int, C.c_int, _vp)
 _proto('bhmm_b200_path_symbol_histogram', C.c_int, _vp, _vp, C.c_longlong, C.c_int, C.c_int, _vp, _vp)
+
+if os.environ.get('BHMM_B200_REPAIR_TOL'):      # A/B measurements: 0 = repair every hand-over above the certification tolerance
+    lib.bhmm_b200_set_repair_tolerance(float(os.environ['BHMM_B200_REPAIR_TOL']))
 
 #: every symbol include/bhmm_b200.h declares (tests check that the library exports all of them)
 EXPORTED = [n for n in dir(lib) if n.startswith('bhmm_b200_')]

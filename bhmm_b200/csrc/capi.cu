@@ -10,7 +10,8 @@
 #include "../../include/bhmm_b200.h"
 
 std::atomic<unsigned long long> g_launches{0};
-double g_cert_tol = 1e-13;
+double g_cert_tol = 1e-13;      // the mismatch the warm-up length is steered to (bhmm_b200_set_certify_tolerance)
+double g_repair_tol = 1e-11;    // E-step hand-overs above this are repaired (bhmm_b200_set_repair_tolerance)
 
 static thread_local int t_err = BHMM_OK;
 static thread_local char t_msg[512] = "";
@@ -233,7 +234,7 @@ long long certify_sync(ChainWork& w, int N, int dir, double* worst, cudaStream_t
     full.n = w.n_total;
     full.warmv = nullptr;
     launch_certify(full, w.n_total, N, dir, dir > 0 ? w.hu_f : w.hu_b, dir > 0 ? w.he_f : w.he_b, std::max(g_cert_tol, tol_floor),
-                   w.fail_list, w.cert_out, st);
+                   std::max(w.repair_tol, tol_floor), w.fail_list, w.cert_out, st);
     LAUNCHED(1);
     if (cudaMemcpyAsync(g_pinned_cert, w.cert_out, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) !=
         cudaSuccess)
@@ -259,7 +260,7 @@ int certify_async(ChainWork& w, int N, int dir, cudaStream_t st)
     full.list = nullptr;
     full.n = w.n_total;
     full.warmv = nullptr;
-    launch_certify(full, w.n_total, N, dir, dir > 0 ? w.hu_f : w.hu_b, dir > 0 ? w.he_f : w.he_b, g_cert_tol, w.fail_list,
+    launch_certify(full, w.n_total, N, dir, dir > 0 ? w.hu_f : w.hu_b, dir > 0 ? w.he_f : w.he_b, g_cert_tol, w.repair_tol, w.fail_list,
                    w.cert_out + 4 * slot, st);
     LAUNCHED(1);
     CUDA_TRY(cudaMemcpyAsync(g_pinned_cert + 4 * slot, w.cert_out + 4 * slot, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -396,6 +397,7 @@ extern "C" int bhmm_b200_device_count(void)
 extern "C" unsigned long long bhmm_b200_launch_count(void) { return g_launches.load(); }
 extern "C" void bhmm_b200_set_chunking(int chunk, int warm) { g_chunk_override = chunk; g_warm_override = warm; }
 extern "C" void bhmm_b200_set_certify_tolerance(double tol) { g_cert_tol = tol; }
+extern "C" void bhmm_b200_set_repair_tolerance(double tol) { g_repair_tol = tol > 0.0 ? tol : 0.0; }
 extern "C" void bhmm_b200_set_warm_margin(double extra) { g_warm_margin = extra < 0.0 ? 0.0 : (extra > 2.0 ? 2.0 : extra); }
 extern "C" void bhmm_b200_last_info(double info[8])
 {

@@ -15,9 +15,10 @@ namespace {
 // Besides pass / fail the kernel estimates how long a warm-up each hand-over NEEDS: the mismatch decays geometrically
 // with the warm-up length (m ~ rho^w), so w' = w log(tol) / log(m) frames would have sufficed.  The maximum over all
 // chains (out[2]) lets the host keep the warm-up a safety factor above the need instead of discovering it by failing
-// (a failed backward pass costs a whole extra pass).
+// (a failed backward pass costs a whole extra pass).  Two tolerances: `tol` is what the warm-up length is steered to (the
+// need estimate), `tol_fail` >= tol is the mismatch above which a chain is listed for repair.
 __global__ void k_certify(Chains ch, int n_total, int N, int dir, const double* __restrict__ hand_used,
-                          const double* __restrict__ hand_end, double tol, int* __restrict__ fail_list,
+                          const double* __restrict__ hand_end, double tol, double tol_fail, int* __restrict__ fail_list,
                           unsigned long long* __restrict__ out)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -39,7 +40,7 @@ __global__ void k_certify(Chains ch, int n_total, int N, int dir, const double* 
     double worst = 0.0;
     for (int i = 0; i < N; ++i) worst = fmax(worst, rel_mismatch(u[i], v[i]));
     atomicMax(out + 1, (unsigned long long)__double_as_longlong(worst));   // non-negative doubles order like their bits
-    if (worst > tol) {
+    if (worst > tol_fail) {
         const unsigned long long slot = atomicAdd(out, 1ULL);
         fail_list[slot] = c;
     }
@@ -91,11 +92,11 @@ __global__ void k_finalize_stats(const double* __restrict__ partials, int grid, 
 }  // namespace
 
 int launch_certify(const Chains& ch, int n_total, int N, int dir, const double* hand_used, const double* hand_end,
-                   double tol, int* fail_list, unsigned long long* out, cudaStream_t st)
+                   double tol, double tol_fail, int* fail_list, unsigned long long* out, cudaStream_t st)
 {
     cudaMemsetAsync(out, 0, 4 * sizeof(unsigned long long), st);
     if (n_total <= 0) return BHMM_OK;
-    k_certify<<<(n_total + 127) / 128, 128, 0, st>>>(ch, n_total, N, dir, hand_used, hand_end, tol, fail_list, out);
+    k_certify<<<(n_total + 127) / 128, 128, 0, st>>>(ch, n_total, N, dir, hand_used, hand_end, tol, fmax(tol, tol_fail), fail_list, out);
     return BHMM_OK;
 }
 

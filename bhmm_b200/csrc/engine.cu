@@ -216,6 +216,18 @@ struct ScanGuard {
     ~ScanGuard() { b->w.scan = nullptr; }
 };
 
+// The E-step's hand-overs are repaired only above the repair tolerance (default 1e-11: still an order below the 1e-10 parity
+// bar, and the map is non-expansive), while the warm-up length keeps being steered to the certification tolerance (1e-13):
+// in steady state the mismatch sits near 1e-14 and a hand-over that drifts to a few 1e-13 -- the mixing rate moves by a few
+// per cent from one EM iteration to the next -- lengthens the next warm-up instead of costing a repair sweep as long as a
+// whole kernel (forward) or a second backward pass, for which every other rank of the job would wait in the all-reduce.
+// Viterbi and the Gibbs sweep keep the strict tolerance (their outputs are discrete decisions).
+struct RepairTolGuard {
+    ChainWork& w;
+    explicit RepairTolGuard(ChainWork& w_) : w(w_) { w.repair_tol = g_repair_tol; }
+    ~RepairTolGuard() { w.repair_tol = 0.0; }
+};
+
 void begin_info(bhmm_b200_batch* b)
 {
     b->info = RunInfo();
@@ -248,6 +260,7 @@ int estep_common(bhmm_b200_batch* b, Emission& em, int emkind, const double* A, 
     RC_TRY(upload_small(b->d_pi, pi, N, st));
     b->w.ch.warm = b->warm_f;
     ScanGuard scan_guard(b, em, emkind);
+    RepairTolGuard repair_guard(b->w);
     LaneArgs la{};
     LaneHostParams hp{A, pi, mu, sigma};
     if (b->lane) {

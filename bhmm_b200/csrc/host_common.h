@@ -10,7 +10,7 @@
 #include "kernels.h"
 
 extern std::atomic<unsigned long long> g_launches;
-extern double g_cert_tol;
+extern double g_cert_tol, g_repair_tol;
 #define LAUNCHED(n) (g_launches.fetch_add((unsigned long long)(n), std::memory_order_relaxed))
 
 #define RC_TRY(expr)                        \
@@ -69,6 +69,7 @@ struct ChainWork {
     int* fail_list = nullptr;
     unsigned long long* cert_out = nullptr;   // device [n_fail, worst bits, sum warm, count]
     int warm_cap = 1;            // longest trajectory: a warm-up that long is an exact start
+    double repair_tol = 0.0;     // hand-overs above max(g_cert_tol, this) are repaired (0: the certification tolerance itself)
     double need_f = 0, need_b = 0;   // certification's estimate of the warm-up the hardest hand-over needs
     // Exact fallback for models whose filter does not forget (scan_kernels.cu): fills he_f (dir > 0) or he_b (dir < 0) with
     // the exact hand-over vectors of every chain; set by the engine around a pass, empty when unavailable (N > 32)

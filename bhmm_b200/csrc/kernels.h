@@ -168,9 +168,10 @@ int launch_transpose(const double* in, int R, int Cc, double* out, cudaStream_t 
 // ---- certification of chain hand-overs (certify.cu)
 // dir = +1 forward (chain c against c-1), -1 backward (chain c against c+1).
 // out[0] = number of failing chains, out[1] = bits of the largest mismatch seen, out[2] = largest estimate of the
-// warm-up length a hand-over needs (frames); fail_list receives the ids of the failing chains.
+// warm-up length a hand-over needs (frames) to reach `tol`; fail_list receives the ids of the chains whose mismatch
+// exceeds max(tol, tol_fail).
 int launch_certify(const Chains& ch, int n_total, int N, int dir, const double* hand_used, const double* hand_end,
-                   double tol, int* fail_list, unsigned long long* out, cudaStream_t st);
+                   double tol, double tol_fail, int* fail_list, unsigned long long* out, cudaStream_t st);
 // deterministic reduction of the E-step: stats = [loglik | gamma0 (N) | C (N*N) | sum gamma | sum gamma d | sum gamma d^2]
 int launch_finalize_stats(const double* partials, int grid, const double* chain_ll, int n_chains, const double* A,
                           int N, double* stats, cudaStream_t st);

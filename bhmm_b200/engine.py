@@ -81,6 +81,54 @@ def mstep_discrete_device(Bnum, out=None):
     return out
 
 
+def transfer_threads():
+    """Worker threads of the host <-> device mover: BHMM_B200_TRANSFER_THREADS, else up to 8 of this process's share of the
+    host cores (the ranks of one box upload at the same time)."""
+    env = os.environ.get('BHMM_B200_TRANSFER_THREADS')
+    if env:
+        return max(1, int(env))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    local = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+    return max(1, min(8, cores // local))
+
+
+def upload_arrays(dst, arrays):
+    """Concatenate C-contiguous host arrays (all of dst's dtype) into the 1-D device tensor ``dst`` (bhmm_b200_upload_ragged)."""
+    torch = _torch()
+    K = len(arrays)
+    ptrs = (C.c_void_p * K)(*[a.ctypes.data for a in arrays])
+    nbytes = np.ascontiguousarray([a.nbytes for a in arrays], dtype=np.int64)
+    if int(nbytes.sum()) != dst.numel() * dst.element_size():
+        raise ValueError('upload: %d bytes of host arrays for a device array of %d' % (int(nbytes.sum()), dst.numel() * dst.element_size()))
+    want = torch.empty(0, dtype=dst.dtype).numpy().dtype
+    for a in arrays:
+        if a.dtype != want or not a.flags.c_contiguous:
+            raise TypeError('upload: C-contiguous %s arrays expected, got %s' % (want, a.dtype))
+    with torch.cuda.device(dst.device):
+        check(lib.bhmm_b200_upload_ragged(C.c_void_p(dst.data_ptr()), ptrs, nbytes.ctypes.data_as(C.POINTER(C.c_longlong)), K,
+                                          transfer_threads(), C.c_void_p(torch.cuda.current_stream(dst.device).cuda_stream)))
+
+
+def download_array(src):
+    """One fresh host numpy array with the contents of the contiguous device tensor ``src`` (bhmm_b200_download_ragged: the
+    worker threads also first-touch the destination's pages, which is most of what a plain .cpu() of 410 MB costs)."""
+    torch = _torch()
+    out = np.empty(tuple(src.shape), dtype=torch.empty(0, dtype=src.dtype).numpy().dtype)
+    if out.nbytes == 0:
+        return out
+    if not src.is_contiguous():
+        src = src.contiguous()
+    ptrs = (C.c_void_p * 1)(out.ctypes.data)
+    nbytes = np.asarray([out.nbytes], dtype=np.int64)
+    with torch.cuda.device(src.device):
+        check(lib.bhmm_b200_download_ragged(ptrs, C.c_void_p(src.data_ptr()), nbytes.ctypes.data_as(C.POINTER(C.c_longlong)), 1,
+                                            transfer_threads(), C.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)))
+    return out
+
+
 class TrajectoryBatch(object):
     """All trajectories of one data set (or of one rank's shard of it), resident on one GPU.
 
@@ -105,20 +153,14 @@ class TrajectoryBatch(object):
         if len(lengths) == 0 or min(lengths) <= 0:
             raise ValueError('every trajectory needs at least one frame')
         rows = int(np.sum(lengths))
-        if len(lengths) <= 8192 and rows // len(lengths) >= 16384:
-            # long trajectories: copy each one straight into its slice of the device array (no concatenated host copy:
-            # for C3 that is 0.8 GB of host traffic saved in MaximumLikelihoodEstimator(...).fit()'s one-off upload)
-            torch = _torch()
-            dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        # the list of pageable host arrays goes to its slices of ONE device array through the library's staged, multi-threaded
+        # mover (csrc/transfer.cu): no concatenated host copy, no single-threaded pageable cudaMemcpy (C3: 0.14 s -> see DESIGN)
+        torch = _torch()
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(dev):
             cat = torch.empty(rows, dtype=torch.int32 if host_dtype == np.int32 else torch.float64, device=dev)
-            off = 0
-            for o in observations:
-                a = np.ascontiguousarray(o, dtype=host_dtype)
-                cat[off:off + a.shape[0]].copy_(torch.from_numpy(a), non_blocking=False)
-                off += a.shape[0]
-            self._adopt = True
-        else:
-            cat = np.concatenate([np.asarray(o, dtype=host_dtype) for o in observations])
+            upload_arrays(cat, [np.ascontiguousarray(o, dtype=host_dtype) for o in observations])
+        self._adopt = True
         self._setup(cat, lengths, nstates, device, chunk, warm)
 
     @classmethod
@@ -432,7 +474,11 @@ class SubBatchedTrajectories(object):
         first = np.asarray(observations[0])
         host_dtype = np.int32 if np.issubdtype(first.dtype, np.integer) else np.float64
         lengths = [len(o) for o in observations]
-        cat = np.concatenate([np.asarray(o, dtype=host_dtype) for o in observations])
+        torch = _torch()
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(dev):
+            cat = torch.empty(int(np.sum(lengths)), dtype=torch.int32 if host_dtype == np.int32 else torch.float64, device=dev)
+            upload_arrays(cat, [np.ascontiguousarray(o, dtype=host_dtype) for o in observations])
         self._setup(cat, lengths, nstates, max_workspace_bytes, device, chunk, warm)
 
     @classmethod
@@ -795,7 +841,7 @@ class TimeShardedTrajectories(object):
     def viterbi_paths(self):
         """The owned-range paths of the last ``viterbi_resolve`` as int32 numpy arrays (one device-to-host copy)."""
         vb = self._viterbi_batch()
-        flat = self._vflat.cpu().numpy()
+        flat = download_array(self._vflat)
         paths = []
         for k in range(self.K):
             lo_l, hi_l = vb._own_ranges[k]

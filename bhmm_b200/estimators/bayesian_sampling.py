@@ -17,7 +17,7 @@ import time
 import numpy as np
 
 from .. import dist
-from ..engine import TrajectoryBatch, make_batch
+from ..engine import TrajectoryBatch, make_batch, download_array
 from ..util import config
 from ..util.logger import logger
 from ..util import tmatrix as _tmatrix
@@ -154,7 +154,7 @@ class BayesianHMMSampler(object):
         self._sweep += 1
         self.last_loglik = ll
         if keep_paths and self._batch is not None:
-            self.model.hidden_state_trajectories = [p.copy() for p in self._batch.split(path.cpu().numpy())]
+            self.model.hidden_state_trajectories = list(self._batch.split(download_array(path)))   # views of one fresh host copy
         return st
 
     def _updateEmissionProbabilities(self, st):

@@ -16,7 +16,7 @@ import time
 import numpy as np
 
 from .. import dist
-from ..engine import TrajectoryBatch, make_batch, unpack_stats, mstep_device, mstep_discrete_device, unpack_mstep
+from ..engine import TrajectoryBatch, make_batch, unpack_stats, mstep_device, mstep_discrete_device, unpack_mstep, download_array
 from ..util import config
 from ..util.logger import logger
 from ..util import tmatrix as _tmatrix
@@ -212,7 +212,7 @@ class MaximumLikelihoodEstimator(object):
             path = self._batch.viterbi_gaussian(A, pi, om.means, om.sigmas, ignore_outliers=om.ignore_outliers)
         else:
             path = self._batch.viterbi_discrete(A, pi, om.output_probabilities, ignore_outliers=om.ignore_outliers)
-        flat = path.cpu().numpy()
+        flat = download_array(path)       # staged, multi-threaded device-to-host copy (csrc/transfer.cu)
         paths = np.empty(self._nobs, dtype=object)
         for k, p in enumerate(self._batch.split(flat)):
             paths[k] = p          # a view of the one host copy (C3: a second 410 MB copy cost as much as the Viterbi kernels)

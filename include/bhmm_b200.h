@@ -65,6 +65,10 @@ unsigned long long bhmm_b200_launch_count(void);
 void bhmm_b200_set_chunking(int chunk, int warm);
 /* Relative hand-over tolerance used by the certification (default 1e-13). */
 void bhmm_b200_set_certify_tolerance(double tol);
+/* E-step hand-overs whose mismatch exceeds max(certification tolerance, this) are repaired (default 1e-11); below it a
+ * mismatch above the certification tolerance only lengthens the next warm-up.  0 = repair everything above the
+ * certification tolerance (round-1 behaviour). */
+void bhmm_b200_set_repair_tolerance(double tol);
 /* Extra safety margin of the adaptive warm-up length (added to the factors 1.12 / 1.15 by which the warm-up is kept above the
  * measured need).  A failed certification costs a repair sweep on ONE rank and a wait on all the others, so a job on W ranks
  * wants failures W times rarer than a single process does: bhmm_b200.dist.tune_for_world() sets 0.04 log2(W). */
@@ -237,6 +241,17 @@ int bhmm_b200_mstep_dev(const double* d_stats, const double* d_means_old, int N,
 /* DiscreteOutputModel.estimate's normalisation (discrete.py:214-215): d_B (N,M) = d_Bnum / rowsum; d_Bt (M,N), optional,
  * receives the transposed table. */
 int bhmm_b200_mstep_discrete_dev(const double* d_Bnum, int N, int M, double* d_B, double* d_Bt, void* stream);
+
+/* ---- (4) the estimators' one-off transfers -------------------------------------------------------- */
+/* The reference estimators take a LIST of host arrays (maximum_likelihood.py:60-144, bayesian_sampling.py:60-150) and return
+ * one hidden-state path per trajectory (maximum_likelihood.py:332-352).  upload_ragged concatenates K pageable host arrays
+ * (srcs[k], nbytes[k] bytes each) into device memory at d_dst; download_ragged cuts device memory back into K host arrays.
+ * `threads` worker threads (0 = automatic) each drive two pinned staging slots and a copy stream, so the host-side copy
+ * (which is also what first touches a fresh destination's pages) runs in parallel with the DMA.  `stream` is synchronised
+ * before the transfer starts (work queued on it may still use the buffers); both calls return when the data has arrived. */
+int bhmm_b200_upload_ragged(void* d_dst, const void* const* srcs, const long long* nbytes, int K, int threads, void* stream);
+int bhmm_b200_download_ragged(void* const* dsts, const void* d_src, const long long* nbytes, int K, int threads,
+                              void* stream);
 
 #ifdef __cplusplus
 }

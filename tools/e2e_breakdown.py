@@ -3,7 +3,7 @@ import os, sys, time
 import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bhmm_b200.engine import TrajectoryBatch, make_batch
+from bhmm_b200.engine import TrajectoryBatch, make_batch, download_array
 from bhmm_b200.util import testsystems as ts
 from bhmm_b200.estimators import MaximumLikelihoodEstimator
 from bhmm_b200.hmm import HMM
@@ -27,9 +27,9 @@ for rep in range(2):
     t2 = sync()
     p = b.viterbi_gaussian(A0, pi0, m0, s0)
     t3 = sync()
-    flat = p.cpu().numpy()
+    flat = download_array(p)
     t4 = sync()
-    paths = [x.copy() for x in b.split(flat)]
+    paths = list(b.split(flat))
     t5 = sync()
     print('rep %d: upload/make_batch %.3f s, first E-step %.3f s, viterbi %.3f s, D2H paths %.3f s, split+copy %.3f s; info %s'
           % (rep, t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, b.info()), flush=True)
