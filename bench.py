@@ -500,6 +500,7 @@ def run_gaussian_em(args, torch, td, dev, world, rank, local):
     tm.start()
     est = MaximumLikelihoodEstimator(host_list, N, initial_model=init, reversible=False, stationary=False, accuracy=-np.inf,
                                      maxit=e2e_iters, shard=False, chunk=args.chunk, warm=args.warm)
+    e2e_construct = time.perf_counter() - w0
     fitted = est.fit()
     e2e_ms = tm.stop()
     e2e_wall = time.perf_counter() - w0
@@ -560,6 +561,8 @@ def run_gaussian_em(args, torch, td, dev, world, rank, local):
                 'd2h_bytes_per_step': (rows * 4) // e2e_iters + 8 * (N * N + 3 * N + 2), 'steps': e2e_iters,
                 'seconds': max(e2e_ms * 1e-3, e2e_wall), 'gpu_launches': int(e2e_launches), 'loglik': e2e_ll,
                 'device_msteps': int(est.device_msteps),
+                'phases_s': {'constructor_upload': e2e_construct, 'esteps': est.timings['estep'], 'msteps': est.timings['mstep'],
+                             'viterbi_and_paths_to_host': est.timings['viterbi']},
                 'note': 'MaximumLikelihoodEstimator(list of host numpy arrays).fit() with maxit=%d: ONE upload of the '
                         'observations (pageable host memory, %d bytes) inside the timed region, %d EM iterations, then the '
                         'Viterbi paths of all trajectories copied back (%d bytes) as fit() does (maximum_likelihood.py:439)'

@@ -53,6 +53,13 @@ constexpr unsigned FULL = 0xffffffffu;
 #define LANE_EXP_TABLE 1     // exp() of the Gaussian emission: 0 = degree-11 polynomial on |r| <= ln2/2; 1 = 32-entry table of
 #endif                       // 2^(j/32) in shared memory + degree-5 polynomial on |r| <= ln2/64 (6 FP64 instructions less
                              // per state; fetching the entry with warp shuffles instead was measured slower)
+#ifndef LANE_EXP_REPL
+#define LANE_EXP_REPL 0      // 1: the exp table is stored 16 times, lane l reads copy l & 15: every look-up is conflict free
+#endif                       //    (2 wavefronts per LDS.64) whatever the 32 indices are; 0: one copy, the lanes' indices collide
+constexpr int kExpCopies = LANE_EXP_REPL ? 16 : 1;
+#ifndef LANE_AT_B
+#define LANE_AT_B 0          // 1: the backward kernel reads a TRANSPOSED copy of A, so that the N entries one column step of
+#endif                       //    b = A w needs are contiguous (whole LDS.128 pairs consumed at once)
 #ifndef LANE_UNROLL_F
 #define LANE_UNROLL_F 1      // unroll factor of the run loops over the chain fast path (forward / backward kernel)
 #endif
@@ -189,7 +196,7 @@ __device__ __forceinline__ void emission_gauss(const CV& P, double o, int ignore
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             const int kk = __double2loint(t[j]);
-            const double e = P.tab[kk & 31];
+            const double e = LANE_EXP_REPL ? P.tab[((kk & 31) << 4) + (threadIdx.x & 15)] : P.tab[kk & 31];
             tb[j] = __hiloint2double(__double2hiint(e) + (kk << 15), __double2loint(e));
         }
 #pragma unroll
@@ -349,9 +356,10 @@ struct ConstView {
     const double* nrm;
     const double* nrml;
     const double* tab;      // 2^(j/32), j = 0..31, in shared memory (high words pre-shifted, see emission_gauss)
+    const double* At;       // LANE_AT_B: A transposed
 };
 template <int N>
-constexpr int lane_const_doubles() { return (int)(sizeof(LaneParams<N>) / sizeof(double)) + 32; }
+constexpr int lane_const_doubles() { return (int)(sizeof(LaneParams<N>) / sizeof(double)) + 32 * kExpCopies + (LANE_AT_B ? N * N : 0); }
 template <int N>
 __device__ __forceinline__ ConstView<N> make_const_view(const LaneParams<N>& P, double* smem)
 {
@@ -359,13 +367,18 @@ __device__ __forceinline__ ConstView<N> make_const_view(const LaneParams<N>& P, 
     constexpr int TOT = sizeof(LaneParams<N>) / sizeof(double);
     const double* src = reinterpret_cast<const double*>(&P);
     for (int k = threadIdx.x; k < TOT; k += blockDim.x) smem[k] = src[k];
-    if (threadIdx.x < 32) {
-        const double e = EXPT[threadIdx.x];
-        smem[TOT + threadIdx.x] = __hiloint2double(__double2hiint(e) - (threadIdx.x << 15), __double2loint(e));
+    for (int k = threadIdx.x; k < 32 * kExpCopies; k += blockDim.x) {
+        const int j = k / kExpCopies;
+        const double e = EXPT[j];
+        smem[TOT + k] = __hiloint2double(__double2hiint(e) - (j << 15), __double2loint(e));
+    }
+    if (LANE_AT_B) {
+        for (int k = threadIdx.x; k < N * N; k += blockDim.x) smem[TOT + 32 * kExpCopies + k] = src[(k % N) * N + k / N];
     }
     __syncthreads();
     ConstView<N> v;
     v.tab = smem + TOT;
+    v.At = smem + TOT + 32 * kExpCopies;
 
 #if LANE_CONST_SMEM == 2
     v.A = P.A;
@@ -726,11 +739,11 @@ k_backward_stats_lane(const __grid_constant__ LaneParams<N> Pk, const LaneArgs a
 #pragma unroll
         for (int j = 0; j < N; ++j) w[j] = p[j] * bt[j];
 #pragma unroll
-        for (int i = 0; i < N; ++i) b[i] = P.A[i * N] * w[0];
+        for (int i = 0; i < N; ++i) b[i] = (LANE_AT_B ? P.At[i] : P.A[i * N]) * w[0];
 #pragma unroll
         for (int j = 1; j < N; ++j) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) b[i] = fma(P.A[i * N + j], w[j], b[i]);
+            for (int i = 0; i < N; ++i) b[i] = fma(LANE_AT_B ? P.At[j * N + i] : P.A[i * N + j], w[j], b[i]);
         }
     };
 

@@ -510,6 +510,8 @@ class SubBatchedTrajectories(object):
                 raise MemoryError('trajectory %d (%d frames, %d states) needs %d bytes of workspace, more than the '
                                   'budget of %d' % (a, lengths[a], nstates, need(a, a + 1), max_workspace_bytes))
             lo, hi = a + 1, K                    # largest b in [lo, hi] with need(a, b) <= budget (need is monotone)
+            if need(a, K) <= max_workspace_bytes:
+                lo = K                           # the usual case, tried first: each probe plans all the chains of its range
             while lo < hi:
                 mid = (lo + hi + 1) // 2
                 if need(a, mid) <= max_workspace_bytes:

@@ -69,7 +69,7 @@ class MaximumLikelihoodEstimator(object):
         self._hmm.output_model.set_implementation(config.kernel)
         self.count_matrix = None
         self.initial_count = None
-        self.timings = {'estep': 0.0, 'mstep': 0.0}
+        self.timings = {'estep': 0.0, 'mstep': 0.0, 'viterbi': 0.0}
         self._device_mstep = bool(device_mstep)
         self.device_msteps = 0          # iterations whose M-step ran on the GPU
         self._dev = None                # device tensors of the last E-step (reduced statistics, B numerators)
@@ -261,5 +261,7 @@ class MaximumLikelihoodEstimator(object):
             st = self._host_stats()      # statistics of the last E-step (count matrix, initial counts), read once
         self.count_matrix = st['C']
         self.initial_count = st['gamma0']
+        t4 = time.time()
         self._hmm.hidden_state_trajectories = self.compute_viterbi_paths()
+        self.timings['viterbi'] += time.time() - t4
         return self._hmm

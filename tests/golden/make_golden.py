@@ -228,7 +228,68 @@ def main():
         d['obs_in_state_msd%d' % i] = np.float64(np.mean((oi - means[i]) ** 2))
     out['gibbs_gauss3'] = d
 
+    # 8. The public entry point bhmm.estimate_hmm (api.py:309-372) with an initial model (the reference's own initial-model
+    #    heuristics need msmtools): lagged observations (api.py:70-94), the estimator's real convergence test
+    #    (accuracy=1e-3), non-reversible; Gaussian with lag 3 and discrete with lag 2.  Also lag_observations with a stride.
+    rng = np.random.default_rng(8)
+    n = 3
+    Atrue = transition_matrix(n, rng, lmin=30.0, lmax=200.0)
+    pitrue = msmtools_stub.stationary_distribution(Atrue)
+    mt, st = np.array([-3.0, 0.5, 4.0]), np.array([0.8, 1.1, 0.6])
+    lengths = [2400, 1501, 999, 3]
+    observations = []
+    for L in lengths:
+        s = simulate(Atrue, pitrue, L, rng)
+        observations.append(mt[s] + st[s] * rng.standard_normal(L))
+    A0 = np.array([[0.80, 0.15, 0.05], [0.10, 0.80, 0.10], [0.04, 0.16, 0.80]])
+    init = HMM(np.ones(n) / n, A0, GaussianOutputModel(n, means=mt - 0.4, sigmas=np.ones(n)))
+    model = bhmm.estimate_hmm(observations, n, lag=3, initial_model=init, reversible=False, stationary=False,
+                              accuracy=1e-3, maxit=200)
+    lagged = bhmm.lag_observations(observations, 3)
+    strided = bhmm.lag_observations(observations, 4, stride=2)
+    d = dict(A0=A0, pi0=np.ones(n) / n, means0=mt - 0.4, sigmas0=np.ones(n), lengths=np.array(lengths), lag=np.int64(3),
+             A=model.transition_matrix, pi=model.initial_distribution, means=model.output_model.means,
+             sigmas=model.output_model.sigmas, likelihood=np.float64(model.likelihood), model_lag=np.int64(model.lag),
+             n_lagged=np.int64(len(lagged)), lagged_lengths=np.array([len(o) for o in lagged]),
+             strided_lengths=np.array([len(o) for o in strided]),
+             strided_heads=np.array([o[0] for o in strided]), strided_tails=np.array([o[-1] for o in strided]))
+    for k, o in enumerate(observations):
+        d['obs%d' % k] = o
+    for k, pth in enumerate(model.hidden_state_trajectories):
+        d['viterbi%d' % k] = np.asarray(pth)
+    out['api_estimate_gauss3'] = d
+
+    rng = np.random.default_rng(9)
+    n, m = 3, 9
+    Atrue = transition_matrix(n, rng, lmin=20.0, lmax=100.0)
+    pitrue = msmtools_stub.stationary_distribution(Atrue)
+    centers = np.linspace(1, m - 2, n)
+    Btrue = np.exp(-0.5 * ((np.arange(m)[None, :] - centers[:, None]) / 1.0) ** 2) + 1e-3
+    Btrue /= Btrue.sum(axis=1)[:, None]
+    lengths = [1800, 1203]
+    dobservations = []
+    for L in lengths:
+        s = simulate(Atrue, pitrue, L, rng)
+        dobservations.append(np.array([rng.choice(m, p=Btrue[k]) for k in s], dtype=np.int32))
+    A0 = transition_matrix(n, np.random.default_rng(99), lmin=5, lmax=20)
+    B0 = np.exp(-0.5 * ((np.arange(m)[None, :] - centers[:, None]) / 2.0) ** 2) + 1e-2
+    B0 /= B0.sum(axis=1)[:, None]
+    init = HMM(np.ones(n) / n, A0, DiscreteOutputModel(B0.copy()))
+    model = bhmm.estimate_hmm(dobservations, n, lag=2, initial_model=init, reversible=False, stationary=False,
+                              accuracy=1e-3, maxit=200)
+    d = dict(A0=A0, pi0=np.ones(n) / n, B0=B0, lengths=np.array(lengths), lag=np.int64(2), A=model.transition_matrix,
+             pi=model.initial_distribution, B=model.output_model.output_probabilities,
+             likelihood=np.float64(model.likelihood), model_lag=np.int64(model.lag))
+    for k, o in enumerate(dobservations):
+        d['obs%d' % k] = o
+    for k, pth in enumerate(model.hidden_state_trajectories):
+        d['viterbi%d' % k] = np.asarray(pth)
+    out['api_estimate_discrete'] = d
+
+    only = [a.split('=', 1)[1] for a in sys.argv[2:] if a.startswith('--only=')]
     for name, arrays in out.items():
+        if only and name not in only:
+            continue
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **arrays)
         print('%-18s %8.1f KB' % (name, os.path.getsize(path) / 1024.0))

@@ -16,6 +16,19 @@ def test_lag_observations_matches_reference_rule():
     assert [list(o) for o in api.lag_observations([np.arange(4)], 1)] == [[0, 1, 2, 3]]
 
 
+def test_lag_observations_matches_the_reference_fixture():
+    """bhmm.lag_observations of the reference on four ragged trajectories (tests/golden/make_golden.py section 8): number and
+    lengths of the lagged trajectories at lag 3, and lengths / first / last frames at lag 4 with stride 2."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'api_estimate_gauss3.npz'))
+    obs = [g['obs%d' % k] for k in range(len(g['lengths']))]
+    out = api.lag_observations(obs, 3)
+    assert len(out) == int(g['n_lagged']) and [len(o) for o in out] == list(g['lagged_lengths'])
+    st = api.lag_observations(obs, 4, stride=2)
+    assert [len(o) for o in st] == list(g['strided_lengths'])
+    assert np.array_equal([o[0] for o in st], g['strided_heads']) and np.array_equal([o[-1] for o in st], g['strided_tails'])
+
+
 def test_guess_output_type():
     assert api._guess_output_type([np.array([0, 1, 2])]) == 'discrete'
     assert api._guess_output_type([np.array([0.0, 1.0, 2.0])]) == 'discrete'

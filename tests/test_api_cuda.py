@@ -69,3 +69,46 @@ def test_estimate_hmm_discrete():
     order = np.argsort(Bh.dot(np.arange(6)))
     np.testing.assert_allclose(Bh[order], B, atol=0.03)
     np.testing.assert_allclose(hmm.transition_matrix[np.ix_(order, order)], A, atol=0.02)
+
+
+def _golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name + '.npz'))
+
+
+def test_estimate_hmm_matches_the_reference_entry_point_gaussian():
+    """bhmm.estimate_hmm(observations, 3, lag=3, initial_model=..., reversible=False, accuracy=1e-3) of the REFERENCE
+    (tests/golden/make_golden.py section 8, api.py:309-372): lagged observations, the estimator's own convergence test,
+    fitted parameters to 1e-10, Viterbi paths of the nine lagged trajectories identical."""
+    import bhmm_b200
+    g = _golden('api_estimate_gauss3')
+    obs = [g['obs%d' % k] for k in range(len(g['lengths']))]
+    init = bhmm_b200.gaussian_hmm(g['pi0'], g['A0'], g['means0'], g['sigmas0'])
+    hmm = bhmm_b200.estimate_hmm(obs, 3, lag=int(g['lag']), initial_model=init, reversible=False, stationary=False,
+                                 accuracy=1e-3, maxit=200)
+    assert hmm.lag == int(g['model_lag']) == 3
+    assert abs(hmm.likelihood - float(g['likelihood'])) <= 1e-10 * abs(float(g['likelihood']))
+    np.testing.assert_allclose(hmm.transition_matrix, g['A'], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(hmm.initial_distribution, g['pi'], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(hmm.output_model.means, g['means'], rtol=1e-10)
+    np.testing.assert_allclose(hmm.output_model.sigmas, g['sigmas'], rtol=1e-10)
+    paths = hmm.hidden_state_trajectories
+    assert len(paths) == int(g['n_lagged']) == 9            # the 3-frame trajectory survives only at shift 0 (api.py:91)
+    for k in range(len(paths)):
+        assert np.array_equal(np.asarray(paths[k]), g['viterbi%d' % k])
+
+
+def test_estimate_hmm_matches_the_reference_entry_point_discrete():
+    import bhmm_b200
+    g = _golden('api_estimate_discrete')
+    obs = [g['obs%d' % k] for k in range(len(g['lengths']))]
+    init = bhmm_b200.discrete_hmm(g['pi0'], g['A0'], g['B0'])
+    hmm = bhmm_b200.estimate_hmm(obs, 3, lag=int(g['lag']), initial_model=init, reversible=False, stationary=False,
+                                 accuracy=1e-3, maxit=200)
+    assert hmm.lag == 2
+    assert abs(hmm.likelihood - float(g['likelihood'])) <= 1e-10 * abs(float(g['likelihood']))
+    np.testing.assert_allclose(hmm.transition_matrix, g['A'], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(hmm.initial_distribution, g['pi'], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(hmm.output_model.output_probabilities, g['B'], rtol=1e-10, atol=1e-14)
+    for k in range(4):
+        assert np.array_equal(np.asarray(hmm.hidden_state_trajectories[k]), g['viterbi%d' % k])
