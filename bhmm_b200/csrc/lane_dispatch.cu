@@ -47,11 +47,13 @@ bool lane_supported(int N, int em) { return N >= 1 && N <= LANE_MAX_N && (em == 
 int launch_lane(const LaneArgs& a, const LaneHostParams& hp, int N, int em, int what, cudaStream_t st)
 {
     if (em == EM_GAUSS && hp.sigma) {
-        // the lazily rescaled recursion leaves 2^(1024 - LANE_LAZY) of head-room for one step's growth, which is at most
-        // N times the largest emission density 1 / (sigma sqrt(2 pi))
+        // the lane kernels reproduce the reference's zero densities (and its outlier rule) exactly only while the logarithm
+        // of the normalisation constant stays below 37 (lane_kernels.cuh:emission_gauss), and the lazily rescaled recursion
+        // has head-room for one step's growth of N / (sigma sqrt(2 pi)) up to 1e100: smaller sigmas belong to the team
+        // kernels (bhmm_b200_batch_set_family(b, 0); engine.TrajectoryBatch switches by itself)
         for (int j = 0; j < N; ++j) {
-            if (!(hp.sigma[j] >= 1e-100)) {
-                bhmm_set_error(BHMM_ERR_UNSUPPORTED, "Gaussian output model: every sigma must be >= 1e-100 (and not NaN)");
+            if (!(hp.sigma[j] >= 1e-16)) {
+                bhmm_set_error(BHMM_ERR_UNSUPPORTED, "lane kernels: every sigma must be >= 1e-16 (and not NaN); use the team family (bhmm_b200_batch_set_family)");
                 return BHMM_ERR_UNSUPPORTED;
             }
         }

@@ -232,9 +232,20 @@ __device__ __forceinline__ void emission_gauss(const CV& P, double o, int ignore
             // Far states are common (any state more than 37.6 sigma away from the observation lands here), so the
             // usual case is cheap: x <= -746 underflows to exactly zero.  Only the thin band whose result is
             // denormal, overflow and non-finite arguments go through the library exp(), out of line.
+            // The reference multiplies exp(-d^2) by the normalisation constant (_gaussian.c:18-20): its density is exactly zero
+            // as soon as exp(-d^2) underflows (-d^2 < -745.13...), whatever the constant -- and an all-zero row is what fires
+            // the outlier rule (outputmodel.py:119-131).  With the constant folded into the argument a narrow state (constant
+            // > 1) would keep a denormal density in the band in between and the frame would not count as an outlier, so the
+            // zero is decided from the un-normalised argument here, off the fast path.  (The band is reachable only through
+            // this block while log(constant) < 37, i.e. sigma > 3e-17; smaller sigmas run on the team kernels.)
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const unsigned hx = (unsigned)__double2hiint(x[j]);
+#if LANE_FOLD_NRM
+                if (x[j] - P.nrm[j] < -745.1332191019412) {
+                    p[j] = 0.0;
+                } else
+#endif
                 if (hx >= 0xC0875000u && hx <= 0xFFF00000u) {
                     p[j] = 0.0;
                 } else if ((hx & 0x7fffffffu) > 0x40862000u) {

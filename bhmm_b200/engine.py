@@ -323,10 +323,13 @@ class TrajectoryBatch(object):
         if self.discrete:
             raise TypeError('this batch holds integer symbols; a Gaussian output model needs float observations')
         if sigmas is not None and self.N <= 16:
-            # The lane kernels' lazily rescaled recursion has head-room for densities up to 1 / (1e-100 sqrt(2 pi)); a
-            # smaller sigma runs on the team kernels, which normalise every frame like the reference (no limit there,
-            # _gaussian.c:18-20).  The batch returns to its own family with the next ordinary model.
-            tiny = bool(np.any(~(np.asarray(sigmas, dtype=np.float64) >= 1e-100)))
+            # The lane kernels fold the Gaussian normalisation constant into the exponent's argument; their rare-tail block,
+            # which reproduces the reference's "exp(-d^2) underflowed: density exactly zero" (and with it the outlier rule),
+            # is reached for every such frame only while log(constant) < 37, and the lazily rescaled recursion has head-room
+            # for densities up to 1e100.  A sigma below 1e-16 therefore runs on the team kernels, which evaluate and
+            # normalise every frame like the reference (no limit there, _gaussian.c:18-20).  The batch returns to its own
+            # family with the next ordinary model.
+            tiny = bool(np.any(~(np.asarray(sigmas, dtype=np.float64) >= 1e-16)))
             want_team = tiny or os.environ.get('BHMM_B200_FAMILY') == 'team'
             if want_team == self.uses_lane_kernels:
                 check(lib.bhmm_b200_batch_set_family(self._handle, 0 if want_team else 1))

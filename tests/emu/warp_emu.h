@@ -155,6 +155,18 @@ inline double __shfl_xor_sync(unsigned, double v, int off)
     emu::rendezvous(w.g);
     return r;
 }
+inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long v, int off)
+{
+    // 64-bit integer payload through the same slots, bit for bit (memcpy: no conversion, no NaN canonicalisation)
+    emu::Warp& w = emu::my_warp();
+    const int l = emu::lane_id();
+    memcpy(&w.sd[l], &v, sizeof(v));
+    emu::rendezvous(w.g);
+    unsigned long long r;
+    memcpy(&r, &w.sd[l ^ off], sizeof(r));
+    emu::rendezvous(w.g);
+    return r;
+}
 inline unsigned __ballot_sync(unsigned, bool pred)
 {
     emu::Warp& w = emu::my_warp();

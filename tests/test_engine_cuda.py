@@ -429,6 +429,40 @@ def test_scaling_and_tail_extremes(eng, oracle_port, case):
     batch.close()
 
 
+def test_outlier_rule_with_narrow_states(eng, oracle_port):
+    """The reference multiplies exp(-z^2/2) by 1/(sigma sqrt(2 pi)) (_gaussian.c:18-20): once the exponential underflows
+    (z > 38.6) the density is exactly zero whatever the constant, and a frame whose densities are ALL zero gets the outlier
+    rule (outputmodel.py:119-131).  The lane kernels fold the constant into the exponent's argument; for narrow states
+    (constant 399 here) that would keep a denormal density up to z = 38.76 and the frame would not be an outlier.  Frames
+    placed in that band must be treated like the reference treats them, on both kernel families."""
+    import torch
+    rng = np.random.default_rng(17)
+    N = 4
+    X = rng.random((N, N)) + 0.05
+    A = X / X.sum(axis=1)[:, None]
+    pi = np.ones(N) / N
+    means, sigmas = 1e-3 * np.array([-3.0, -1.0, 1.0, 3.0]), np.full(N, 1e-3)
+    obs = []
+    for T in (3000, 1200):
+        s = rng.integers(0, N, size=T)
+        obs.append(means[s] + sigmas[s] * rng.standard_normal(T))
+    obs[0][100] = 3e-3 + 38.65e-3       # z = 38.65 for the nearest state: exp(-z^2/2) = 0, exp(log 399 - z^2/2) is denormal
+    obs[0][2500] = -3e-3 - 38.72e-3
+    obs[1][50] = 3e-3 + 38.70e-3
+    for k, t in ((0, 100), (0, 2500), (1, 50)):
+        assert not oracle_port.gaussian_p_obs(obs[k][t:t + 1], means, sigmas, ignore_outliers=False).any()     # the reference sees an all-zero row
+    batch = eng.TrajectoryBatch(obs, N, chunk=400, warm=64)
+    gam = torch.zeros((batch.rows, N), dtype=torch.float64, device='cuda')
+    st = eng.unpack_stats(batch.estep_gaussian(A, pi, means, sigmas, gamma_out=gam).cpu().numpy(), N)
+    ref, wd, wdd = oracle_stats_gaussian(oracle_port, obs, A, pi, means, sigmas)
+    assert np.isfinite(ref['loglik'])
+    assert abs(st['loglik'] - ref['loglik']) <= RTOL * abs(ref['loglik'])
+    np.testing.assert_allclose(st['C'], ref['C'], rtol=1e-9, atol=1e-9 * ref['C'].max())
+    np.testing.assert_allclose(st['wsum'], ref['wsum'], rtol=1e-9)
+    assert np.max(np.abs(gam.cpu().numpy() - np.concatenate(ref['gammas']))) <= RTOL
+    batch.close()
+
+
 def test_degenerate_sigma_runs_on_the_team_family(eng, oracle_port, family):
     """sigma below 1e-100 could overflow the lane kernels' lazily scaled band.  The reference has no such limit
     (_gaussian.c:18-20), so the batch switches to the team kernels for that call instead of refusing it."""
