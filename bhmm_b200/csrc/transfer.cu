@@ -17,7 +17,42 @@
 
 #include "host_common.h"
 
+#if defined(__x86_64__) || defined(__SSE2__)
+#include <emmintrin.h>
+#define BHMM_HAVE_SSE2 1
+#endif
+
 namespace {
+
+// memcpy with streaming (non-temporal) stores.  Neither destination is read again by this CPU -- a staging slot is consumed
+// by the DMA engine, a caller's fresh array by whoever uses the paths later -- so ordinary stores would first fetch every
+// destination line into the cache (read-for-ownership) and evict it again: one extra pass over the data through the host's
+// memory system, which is what the transfers of 8 ranks on one host compete for.  BHMM_B200_NT_COPY=0: plain memcpy.
+int g_nt_copy = -1;
+void stream_copy(char* dst, const char* src, size_t n)
+{
+#ifdef BHMM_HAVE_SSE2
+    if (g_nt_copy && n >= 4096) {
+        const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+        if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+        size_t blocks = n / 64;
+        while (blocks--) {
+            const __m128i a = _mm_loadu_si128((const __m128i*)src), b = _mm_loadu_si128((const __m128i*)(src + 16));
+            const __m128i c = _mm_loadu_si128((const __m128i*)(src + 32)), d = _mm_loadu_si128((const __m128i*)(src + 48));
+            _mm_stream_si128((__m128i*)dst, a);
+            _mm_stream_si128((__m128i*)(dst + 16), b);
+            _mm_stream_si128((__m128i*)(dst + 32), c);
+            _mm_stream_si128((__m128i*)(dst + 48), d);
+            src += 64; dst += 64;
+        }
+        n &= 63;
+        if (n) memcpy(dst, src, n);
+        _mm_sfence();
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
 
 size_t SLOT_BYTES = (size_t)2 << 20;               // one staging slot, 2 per worker (BHMM_B200_STAGE_KB overrides, first use)
 constexpr int MAX_WORKERS = 16;
@@ -45,11 +80,16 @@ int stage_ensure(int workers)
         cudaFreeHost(g_stage.base);
         g_stage = Staging();
     }
-    if (!g_stage.base) {
+    if (g_nt_copy < 0) { const char* e = getenv("BHMM_B200_NT_COPY"); g_nt_copy = (e && e[0] == '0') ? 0 : 1; }
+    static bool env_read = false;
+    if (!env_read) {
+        env_read = true;
         if (const char* e = getenv("BHMM_B200_STAGE_KB")) {
             const long kb = atol(e);
             if (kb >= 64 && kb <= (1 << 20)) SLOT_BYTES = (size_t)kb << 10;
         }
+    }
+    if (!g_stage.base) {
         CUDA_TRY(cudaHostAlloc((void**)&g_stage.base, SLOT_BYTES * 2 * workers, cudaHostAllocDefault));
         for (int w = 0; w < workers; ++w) {
             CUDA_TRY(cudaStreamCreateWithFlags(&g_stage.stream[w], cudaStreamNonBlocking));
@@ -84,8 +124,8 @@ struct Ragged {
             const long long in = off - start[k];
             const long long take = std::min(n, start[k + 1] - off);
             char* host = (char*)ptr[k] + in;
-            if (TO_STAGE) memcpy(buf, host, (size_t)take);
-            else memcpy(host, buf, (size_t)take);
+            if (TO_STAGE) stream_copy(buf, host, (size_t)take);
+            else stream_copy(host, buf, (size_t)take);
             buf += take; off += take; n -= take;
             ++k;
             while (n > 0 && k < K && start[k + 1] == start[k]) ++k;
@@ -173,6 +213,25 @@ int make_ragged(Ragged& rg, const void* const* ptrs, const long long* nbytes, in
 }
 
 }  // namespace
+
+// Tuning knobs of the mover (measurement scripts; the defaults are what the estimators use): staging slot size in KiB
+// (0 = keep) and streaming stores on / off (negative = keep).  Frees the staging slots; the next transfer re-creates them.
+extern "C" int bhmm_b200_transfer_config(int stage_kb, int nt_copy)
+{
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    if (g_stage.base) {
+        for (int w = 0; w < g_stage.workers; ++w) {
+            cudaStreamDestroy(g_stage.stream[w]);
+            cudaEventDestroy(g_stage.done[w][0]);
+            cudaEventDestroy(g_stage.done[w][1]);
+        }
+        cudaFreeHost(g_stage.base);
+        g_stage = Staging();
+    }
+    if (stage_kb >= 64 && stage_kb <= (1 << 20)) SLOT_BYTES = (size_t)stage_kb << 10;
+    if (nt_copy >= 0) g_nt_copy = nt_copy ? 1 : 0;
+    return BHMM_OK;
+}
 
 // Concatenate K host arrays into device memory: d_dst[sum_{k'<k} nbytes[k'] ...] = srcs[k].  `stream` (may be NULL) is
 // synchronised first: work queued on it may still be using the destination.  Returns after the data has arrived.

@@ -582,7 +582,7 @@ def test_time_sharded_trajectories(eng, oracle_port, N, world):
         s.close()
 
 
-@pytest.mark.parametrize('N', [4, 12, 20, 32])
+@pytest.mark.parametrize('N', [4, 12, 20, 32, 40, 100])
 def test_exact_scan_for_models_that_do_not_forget(eng, oracle_port, N):
     """North star (4): a nearly reducible transition matrix with uninformative emissions never forgets its start, so the
     warm-up starts of the chains fail their certification and chain-by-chain repairs would walk the trajectory

@@ -85,6 +85,15 @@ def test_exact_scan_on_the_emulator(engine_emu):
     assert r.stderr.count('block 192 ') >= 2             # k_chain_operator: 32 N threads, forward and backward
 
 
+def test_exact_scan_wide_on_the_emulator(engine_emu):
+    """The same with 40 states: k_chain_operator_wide / k_scan_starts_wide (two columns per lane, 32 warps taking the operator's
+    rows in turn), on the team kernels and on the tensor-pipe kernels."""
+    for mode in (0, 1):
+        r = _drive(mode, ['40,40,2,300'], trace=True, exact_scan=True)
+        assert r.stderr.count('block 1024 ') >= 2        # k_chain_operator_wide, forward and backward
+        assert r.stderr.count('block 64 ') >= 2          # k_scan_starts_wide<2>
+
+
 def test_tiled_chase_link_forced(engine_emu):
     """k_chase_link_tiled (chosen on its own only from 65536 segments, i.e. for C5-sized trajectories) forced for every
     batch: batched Viterbi and Gibbs paths with several ragged trajectories, and a literal Viterbi over 36 segments (two
