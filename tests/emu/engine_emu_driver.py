@@ -66,7 +66,7 @@ def unpack(st, N):
     return out
 
 
-def run(N, chunk, warm, diag=2.0):
+def run(N, chunk, warm, diag=2.0, estep_only=False):
     orc = Oracle('port')
     rng = np.random.default_rng(N)
     X = rng.random((N, N)) + diag * np.eye(N)              # a heavy diagonal mixes slowly: short warm-ups fail
@@ -98,6 +98,9 @@ def run(N, chunk, warm, diag=2.0):
     check(tag + 'plan cut the trajectories into chains', info['chains'] > len(lengths) if chunk else True, str(info))
     if diag > 10 and warm < 8:
         check(tag + 'the short warm-up needed fix-ups', info['fix_f'] + info['fix_b'] > 0, str(info))
+    if estep_only:                                  # spec 'eN,chunk,warm,diag': the Gaussian E-step alone (slow emulations)
+        b.close()
+        return
     path = np.zeros(b.rows, dtype=np.int32)
     rc_ok(lib.bhmm_b200_viterbi_gaussian(b.h, d(cat), d(A), d(pi), d(means), d(sigmas), 1, path.ctypes.data_as(C.POINTER(C.c_int)), None))
     ok = True
@@ -304,6 +307,7 @@ if __name__ == '__main__':
         if spec.startswith('v'):
             run_viterbi_only(int(spec[1:]))
             continue
-        parts = [float(x) for x in spec.split(',')]
-        run(int(parts[0]), int(parts[1]), int(parts[2]), *(parts[3:4]))
+        estep_only = spec.startswith('e')
+        parts = [float(x) for x in spec.lstrip('e').split(',')]
+        run(int(parts[0]), int(parts[1]), int(parts[2]), *(parts[3:4]), estep_only=estep_only)
     sys.exit(1 if failures else 0)
