@@ -214,6 +214,28 @@ int make_ragged(Ragged& rg, const void* const* ptrs, const long long* nbytes, in
 
 }  // namespace
 
+// Write-touch every page of a fresh host allocation with `threads` threads (0 = 2), so that its page faults -- most of what
+// copying 410 MB of paths into a new array costs, and on a busy host by far the most variable part -- happen while the GPU is
+// still iterating: MaximumLikelihoodEstimator.fit() calls this from a helper thread on the array it will return the paths in.
+// Pure host code (no CUDA call).
+extern "C" int bhmm_b200_prefault(void* p, long long nbytes, int threads)
+{
+    if (nbytes <= 0) return BHMM_OK;
+    if (!p) { bhmm_set_error(BHMM_ERR_INVALID, "prefault: null pointer"); return BHMM_ERR_INVALID; }
+    const int W = std::max(1, std::min(threads > 0 ? threads : 2, MAX_WORKERS));
+    const long long page = 4096, pages = (nbytes + page - 1) / page;
+    auto work = [&](int w) {
+        volatile char* c = (volatile char*)p;
+        const long long lo = pages * w / W, hi = pages * (w + 1) / W;
+        for (long long k = lo; k < hi; ++k) c[std::min(k * page, nbytes - 1)] = 0;
+    };
+    std::vector<std::thread> pool;
+    for (int w = 1; w < W; ++w) pool.emplace_back(work, w);
+    work(0);
+    for (auto& t : pool) t.join();
+    return BHMM_OK;
+}
+
 // Tuning knobs of the mover (measurement scripts; the defaults are what the estimators use): staging slot size in KiB
 // (0 = keep) and streaming stores on / off (negative = keep).  Frees the staging slots; the next transfer re-creates them.
 extern "C" int bhmm_b200_transfer_config(int stage_kb, int nt_copy)

@@ -112,11 +112,38 @@ def upload_arrays(dst, arrays):
                                           transfer_threads(), C.c_void_p(torch.cuda.current_stream(dst.device).cuda_stream)))
 
 
-def download_array(src):
-    """One fresh host numpy array with the contents of the contiguous device tensor ``src`` (bhmm_b200_download_ragged: the
-    worker threads also first-touch the destination's pages, which is most of what a plain .cpu() of 410 MB costs)."""
+class HostBufferInBackground(object):
+    """A host array of the given shape whose pages are faulted in by a helper thread (bhmm_b200_prefault, GIL released) while
+    the caller keeps the GPU busy; ``get()`` joins the thread and returns the array.  The estimators allocate the array that
+    will receive the hidden-state paths this way at the start of ``fit``."""
+
+    def __init__(self, shape, dtype, threads=2):
+        import threading
+        self._arr = np.empty(shape, dtype=dtype)
+        self._thread = None
+        if self._arr.nbytes >= (1 << 22):
+            a = self._arr
+            self._thread = threading.Thread(target=lambda: lib.bhmm_b200_prefault(C.c_void_p(a.ctypes.data), a.nbytes, int(threads)),
+                                            daemon=True)
+            self._thread.start()
+
+    def get(self):
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+        return self._arr
+
+
+def download_array(src, out=None):
+    """A host numpy array with the contents of the contiguous device tensor ``src`` (bhmm_b200_download_ragged: the worker
+    threads also first-touch the destination's pages, which is most of what a plain .cpu() of 410 MB costs).  ``out``: an
+    existing C-contiguous array of the same shape and dtype to fill instead of a fresh one."""
     torch = _torch()
-    out = np.empty(tuple(src.shape), dtype=torch.empty(0, dtype=src.dtype).numpy().dtype)
+    want = torch.empty(0, dtype=src.dtype).numpy().dtype
+    if out is None:
+        out = np.empty(tuple(src.shape), dtype=want)
+    elif out.dtype != want or tuple(out.shape) != tuple(src.shape) or not out.flags.c_contiguous:
+        raise ValueError('download: destination does not match the device tensor')
     if out.nbytes == 0:
         return out
     if not src.is_contiguous():

@@ -16,7 +16,8 @@ import time
 import numpy as np
 
 from .. import dist
-from ..engine import TrajectoryBatch, make_batch, unpack_stats, mstep_device, mstep_discrete_device, unpack_mstep, download_array
+from ..engine import (TrajectoryBatch, make_batch, unpack_stats, mstep_device, mstep_discrete_device, unpack_mstep, download_array,
+                      HostBufferInBackground)
 from ..util import config
 from ..util.logger import logger
 from ..util import tmatrix as _tmatrix
@@ -212,7 +213,10 @@ class MaximumLikelihoodEstimator(object):
             path = self._batch.viterbi_gaussian(A, pi, om.means, om.sigmas, ignore_outliers=om.ignore_outliers)
         else:
             path = self._batch.viterbi_discrete(A, pi, om.output_probabilities, ignore_outliers=om.ignore_outliers)
-        flat = download_array(path)       # staged, multi-threaded device-to-host copy (csrc/transfer.cu)
+        # staged, multi-threaded device-to-host copy (csrc/transfer.cu) into the array fit() had faulted in meanwhile
+        out = self._path_host.get() if getattr(self, '_path_host', None) is not None else None
+        self._path_host = None
+        flat = download_array(path, out=out if out is not None and out.shape == tuple(path.shape) else None)
         paths = np.empty(self._nobs, dtype=object)
         for k, p in enumerate(self._batch.split(flat)):
             paths[k] = p          # a view of the one host copy (C3: a second 410 MB copy cost as much as the Viterbi kernels)
@@ -227,6 +231,8 @@ class MaximumLikelihoodEstimator(object):
         tmatrix_nonzeros = self.hmm.transition_matrix.nonzero()
         converged = False
         st = None
+        # the array that will hold the Viterbi paths: its pages are faulted in by a helper thread while the GPU iterates
+        self._path_host = HostBufferInBackground((int(self._batch.rows),), np.int32) if self._batch is not None else None
         while not converged and it < self.maxit:
             t1 = time.time()
             st = self._estep()

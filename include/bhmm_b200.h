@@ -252,6 +252,9 @@ int bhmm_b200_mstep_discrete_dev(const double* d_Bnum, int N, int M, double* d_B
 int bhmm_b200_upload_ragged(void* d_dst, const void* const* srcs, const long long* nbytes, int K, int threads, void* stream);
 int bhmm_b200_download_ragged(void* const* dsts, const void* d_src, const long long* nbytes, int K, int threads,
                               void* stream);
+/* Write-touches every page of a fresh host allocation (threads = 0: two threads); host code only.  The estimators call it from a
+ * helper thread on the array that will receive the paths, so that the page faults happen while the GPU is busy. */
+int bhmm_b200_prefault(void* p, long long nbytes, int threads);
 /* Tuning knobs of the two calls above (measurement scripts): staging slot size in KiB (0 = keep; default 2048, or
  * BHMM_B200_STAGE_KB) and streaming stores for the host-side copy on / off (negative = keep; default on, or
  * BHMM_B200_NT_COPY=0).  The pinned staging slots are released and re-created by the next transfer. */

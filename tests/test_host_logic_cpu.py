@@ -311,3 +311,20 @@ def test_reversible_sampler_matches_numerical_integration_at_small_counts():
         assert np.allclose(T.sum(axis=1), 1.0)
         pi = tmatrix.stationary_vector(T)
         assert np.allclose(pi[:, None] * T, (pi[:, None] * T).T)
+
+
+def test_prefault_touches_pages_without_changing_zeros_and_rejects_null():
+    """bhmm_b200_prefault (host code of csrc/transfer.cu): write-touches one byte per page of a fresh allocation; the estimators
+    run it on a helper thread (engine.HostBufferInBackground) while the GPU iterates.  No device needed."""
+    import ctypes as C
+    from bhmm_b200 import _lib
+    a = np.zeros(3 * 4096 + 17, dtype=np.uint8)
+    assert _lib.lib.bhmm_b200_prefault(C.c_void_p(a.ctypes.data), a.nbytes, 3) == _lib.OK
+    assert not a.any()
+    assert _lib.lib.bhmm_b200_prefault(C.c_void_p(a.ctypes.data), 0, 0) == _lib.OK
+    assert _lib.lib.bhmm_b200_prefault(None, 100, 1) == _lib.ERR_INVALID
+    # the background wrapper hands back an array of the requested shape and dtype after its thread has finished
+    import bhmm_b200.engine as eng
+    h = eng.HostBufferInBackground((2_000_000,), np.int32, threads=2)
+    out = h.get()
+    assert out.shape == (2_000_000,) and out.dtype == np.int32 and h.get() is out
