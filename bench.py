@@ -494,6 +494,15 @@ def run_gaussian_em(args, torch, td, dev, world, rank, local):
     torch.cuda.empty_cache()
     host_list = [host_obs[k] for k in range(K)]
     init = HMM(pi0, A0, GaussianOutputModel(N, means=m0, sigmas=s0))
+    # Warm-up of the end-to-end path (what the W warm-up steps are to the device-resident loop): one tiny fit through the same
+    # public API, outside the timed region, pays the once-per-process costs -- the mover's pinned staging slots (5-40 ms, once
+    # 0.3 s on a box of the pool), the first launches of the Viterbi / path kernels.
+    tiny = MaximumLikelihoodEstimator([host_obs[k][:4000] for k in range(min(K, 4))], N, initial_model=init, reversible=False,
+                                      stationary=False, accuracy=-np.inf, maxit=2, shard=False)
+    tiny.fit()
+    tiny._batch.close()
+    del tiny
+    torch.cuda.empty_cache()
     l0 = _lib.lib.bhmm_b200_launch_count()
     tm.barrier()
     w0 = time.perf_counter()
@@ -563,6 +572,7 @@ def run_gaussian_em(args, torch, td, dev, world, rank, local):
                 'device_msteps': int(est.device_msteps),
                 'phases_s': {'constructor_upload': e2e_construct, 'esteps': est.timings['estep'], 'msteps': est.timings['mstep'],
                              'viterbi_and_paths_to_host': est.timings['viterbi']},
+                'warmup': 'one fit of 4 x 4000 frames through the same API before the timed region (once-per-process costs)',
                 'note': 'MaximumLikelihoodEstimator(list of host numpy arrays).fit() with maxit=%d: ONE upload of the '
                         'observations (pageable host memory, %d bytes) inside the timed region, %d EM iterations, then the '
                         'Viterbi paths of all trajectories copied back (%d bytes) as fit() does (maximum_likelihood.py:439)'

@@ -102,12 +102,18 @@ int stage_ensure(int workers)
     return BHMM_OK;
 }
 
+// workers the caller asked for (slots are allocated for all of them at the first transfer, however small that one is: a tiny
+// first transfer must not leave the pinned allocation of the other workers' slots to the first big one)
+int asked_workers(int threads)
+{
+    const int w = threads > 0 ? threads : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    return std::max(1, std::min(w, MAX_WORKERS));
+}
+// ... and those that have a piece to move
 int pick_workers(int threads, long long total_bytes)
 {
-    int w = threads > 0 ? threads : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
-    w = std::min(w, MAX_WORKERS);
     const long long pieces = (total_bytes + (long long)SLOT_BYTES - 1) / (long long)SLOT_BYTES;
-    return (int)std::max<long long>(1, std::min<long long>(w, pieces));
+    return (int)std::max<long long>(1, std::min<long long>(asked_workers(threads), pieces));
 }
 
 // The concatenated byte stream of K host arrays, addressed by global offset.
@@ -139,8 +145,8 @@ int run_transfer(bool upload, char* d_base, const Ragged& rg, int threads)
     const long long total = rg.start[rg.K];
     if (total == 0) return BHMM_OK;
     std::lock_guard<std::mutex> lock(g_stage_mutex);
+    RC_TRY(stage_ensure(asked_workers(threads)));          // (may change SLOT_BYTES at the first call: before pick_workers)
     const int W = pick_workers(threads, total);
-    RC_TRY(stage_ensure(W));
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     const long long pieces = (total + (long long)SLOT_BYTES - 1) / (long long)SLOT_BYTES;
