@@ -286,6 +286,30 @@ def main():
         d['viterbi%d' % k] = np.asarray(pth)
     out['api_estimate_discrete'] = d
 
+    # 9. The Gibbs emission-parameter draws: GaussianOutputModel.sample (gaussian.py:274-320) and
+    #    DiscreteOutputModel.sample (discrete.py:217-251) consume numpy's global stream in a fixed order, so with
+    #    np.random.seed they are reproducible: states with many, with one and with no observation.
+    rng = np.random.default_rng(10)
+    m0, s0 = np.array([-1.0, 0.5, 2.0, 7.0]), np.array([0.5, 1.0, 2.0, 0.3])
+    obs_by_state = [m0[0] + s0[0] * rng.standard_normal(5000), m0[1] + s0[1] * rng.standard_normal(37),
+                    np.array([2.25]), np.zeros(0)]
+    gom = GaussianOutputModel(4, means=m0.copy(), sigmas=s0.copy())
+    np.random.seed(123)
+    gom.sample(obs_by_state)
+    d = dict(means0=m0, sigmas0=s0, seed=np.int64(123), means=gom.means.copy(), sigmas=gom.sigmas.copy())
+    for i, o in enumerate(obs_by_state):
+        d['obs_in_state%d' % i] = o
+    B0 = np.array([[0.5, 0.2, 0.1, 0.1, 0.05, 0.05], [0.05, 0.05, 0.1, 0.1, 0.2, 0.5], [0.2, 0.2, 0.2, 0.2, 0.1, 0.1]])
+    sym_by_state = [rng.choice(6, size=800, p=B0[0]).astype(np.int32), np.array([5, 5, 4, 5], dtype=np.int32),
+                    np.zeros(0, dtype=np.int32)]
+    dom = DiscreteOutputModel(B0.copy())
+    np.random.seed(77)
+    dom.sample(sym_by_state)
+    d.update(B0=B0, dseed=np.int64(77), B=dom.output_probabilities.copy())
+    for i, o in enumerate(sym_by_state):
+        d['sym_in_state%d' % i] = o
+    out['gibbs_emission_draws'] = d
+
     only = [a.split('=', 1)[1] for a in sys.argv[2:] if a.startswith('--only=')]
     for name, arrays in out.items():
         if only and name not in only:

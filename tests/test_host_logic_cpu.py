@@ -328,3 +328,29 @@ def test_prefault_touches_pages_without_changing_zeros_and_rejects_null():
     h = eng.HostBufferInBackground((2_000_000,), np.int32, threads=2)
     out = h.get()
     assert out.shape == (2_000_000,) and out.dtype == np.int32 and h.get() is out
+
+
+def test_gibbs_emission_draws_match_the_reference_with_the_same_seed(golden):
+    """SURVEY 8f N1, the sampling half: GaussianOutputModel.sample / DiscreteOutputModel.sample of the reference
+    (gaussian.py:274-320, discrete.py:217-251; fixture from the reference package, make_golden.py section 9) consume numpy's
+    global stream in a fixed order.  The draws here work from the path statistics the GPU returns (count, sum o, sum o^2 /
+    symbol histogram) and reproduce the reference's parameters for the same seed: states with 5000, 37, one and no frames."""
+    from bhmm_b200.output_models import GaussianOutputModel, DiscreteOutputModel
+    g = golden('gibbs_emission_draws')
+    obs = [g['obs_in_state%d' % i] for i in range(4)]
+    om = GaussianOutputModel(4, means=g['means0'].copy(), sigmas=g['sigmas0'].copy())
+    count = np.array([len(o) for o in obs])
+    so = np.array([o.sum() for o in obs])
+    soo = np.array([(o * o).sum() for o in obs])
+    np.random.seed(int(g['seed']))
+    om.sample_from_statistics(count, so, soo)
+    np.testing.assert_allclose(om.means, g['means'], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(om.sigmas, g['sigmas'], rtol=1e-10)
+    assert om.means[3] == g['means0'][3] and om.sigmas[3] == g['sigmas0'][3]       # no frames: untouched
+    assert om.sigmas[2] == g['sigmas0'][2]                                          # one frame: mean only
+    sym = [g['sym_in_state%d' % i] for i in range(3)]
+    dm = DiscreteOutputModel(g['B0'].copy())
+    hist = np.array([np.bincount(s, minlength=6) for s in sym])
+    np.random.seed(int(g['dseed']))
+    dm.sample_from_histogram(hist)
+    np.testing.assert_allclose(dm.output_probabilities, g['B'], rtol=1e-12, atol=1e-15)
