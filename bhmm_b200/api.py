@@ -132,7 +132,8 @@ def init_discrete_hmm(observations, nstates, lag=1, reversible=True, stationary=
     C, _ = _counts_from_assignments(obs, nsym, lag)
     visited = np.where(C.sum(axis=0) + C.sum(axis=1) > 0)[0]
     if len(visited) < nstates:
-        raise ValueError('fewer visited symbols (%d) than hidden states (%d)' % (len(visited), nstates))
+        # the reference refuses this with NotImplementedError (init/discrete.py:270-272; bhmm/tests/test_mlhmm_patho.py:39-42)
+        raise NotImplementedError('Trying to initialize %d-state HMM from smaller %d-state MSM.' % (nstates, len(visited)))
     Cv = C[np.ix_(visited, visited)] + 1e-3 / len(visited)
     Cs = 0.5 * (Cv + Cv.T)                                    # reversible estimate: real spectrum
     Pv = Cs / Cs.sum(axis=1)[:, None]

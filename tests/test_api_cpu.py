@@ -94,7 +94,7 @@ def test_init_discrete_hmm_finds_the_metastable_lumping():
     assert all(len(b) == 1 for b in blocks) and len(set.union(*blocks)) == 3
     P = m.transition_matrix
     assert np.allclose(P.sum(axis=1), 1.0) and np.all(np.diag(P) > 0.9)
-    with pytest.raises(ValueError):
+    with pytest.raises(NotImplementedError):      # like the reference: init/discrete.py:270-272, test_mlhmm_patho.py:39-42
         api.init_discrete_hmm([np.array([0, 1, 0, 1])], 3)
 
 
