@@ -248,6 +248,34 @@ class SampledModels(object):
     def output_probabilities(self):
         return self._summary(lambda m: m.output_model.output_probabilities)
 
+    @property
+    def lifetimes(self):
+        return self._summary(lambda m: m.lifetimes)
+
+    @property
+    def stationary_distribution(self):
+        return self._summary(lambda m: m.stationary_distribution)
+
+    # the reference's attribute names (bhmm/hmm/generic_sampled_hmm.py:69-252, gaussian_hmm.py:66-113, discrete_hmm.py:62-84):
+    # <quantity>_samples / _mean / _std / _conf
+    _QUANTITIES = ('transition_matrix', 'initial_distribution', 'stationary_distribution', 'lifetimes', 'means', 'sigmas',
+                   'output_probabilities')
+
+    def __getattr__(self, name):
+        for q in SampledModels._QUANTITIES:
+            if name.startswith(q + '_'):
+                what = name[len(q) + 1:]
+                if what in ('samples', 'mean', 'std', 'conf'):
+                    return getattr(self, q)[what]
+        raise AttributeError(name)
+
+    @property
+    def confidence_interval(self):
+        return self.conf
+
+    def set_confidence(self, conf):
+        self.conf = conf
+
 
 def bayesian_hmm(observations, estimated_hmm, nsample=100, reversible=True, stationary=False, p0_prior='mixed',
                  transition_matrix_prior='mixed', store_hidden=False, call_back=None):

@@ -55,3 +55,36 @@ def test_2state_2step():
     assert _either(hmm.initial_distribution, p0_ref, p0_ref[perm])
     assert _either(hmm.transition_matrix, A_ref, A_ref[np.ix_(perm, perm)])
     assert _either(hmm.output_model.output_probabilities, B_ref, B_ref[perm])
+
+
+# ---- bhmm/tests/test_bhmm_patho.py:29-50: the Bayesian sampler on the same pathological inputs
+
+def test_bayesian_2state_rev_step_refuses_disconnected_counts():
+    import bhmm_b200
+    obs = np.array([0, 0, 0, 0, 0, 1, 1, 1, 1], dtype=int)
+    mle = bhmm_b200.estimate_hmm([obs], nstates=2, lag=1)
+    with pytest.raises(NotImplementedError):      # disconnected count matrices with reversible sampling and no prior
+        bhmm_b200.bayesian_hmm([obs], mle, reversible=True, p0_prior=None, transition_matrix_prior=None)
+
+
+def test_bayesian_2state_nonrev_step():
+    import bhmm_b200
+    obs = np.array([0, 0, 0, 0, 0, 1, 1, 1, 1], dtype=int)
+    mle = bhmm_b200.estimate_hmm([obs], nstates=2, lag=1)
+    np.random.seed(20)            # the parameter draws use numpy's global stream like the reference: a fixed outcome
+    sampled = bhmm_b200.bayesian_hmm([obs], mle, reversible=False, nsample=2000, p0_prior='mixed',
+                                     transition_matrix_prior='mixed')
+    # the absorbing state is whichever hidden state emits symbol 1 (the reference's test assumes it is state 1)
+    absorbing = int(np.argmax(mle.output_model.output_probabilities[:, 1]))
+    assert np.all(sampled.transition_matrix_std[1 - absorbing] > 0)
+    assert np.max(np.abs(sampled.transition_matrix_std[absorbing])) < 1e-3
+
+
+def test_bayesian_2state_rev_2step():
+    import bhmm_b200
+    obs = np.array([0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0], dtype=int)
+    mle = bhmm_b200.estimate_hmm([obs], nstates=2, lag=1)
+    np.random.seed(21)
+    sampled = bhmm_b200.bayesian_hmm([obs], mle, reversible=False, nsample=100, p0_prior='mixed',
+                                     transition_matrix_prior='mixed')
+    assert np.all(sampled.transition_matrix_std > 0)
