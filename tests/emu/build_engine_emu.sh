@@ -8,7 +8,7 @@ GEN="$HERE/_gen"
 mkdir -p "$GEN"
 INC="-I${CUDA_HOME:-/usr/local/cuda}/include -I$ROOT/bhmm_b200/csrc -I$HERE"
 OBJS=""
-for f in capi engine certify team_kernels panel_kernels lane_viterbi scan_kernels frame_kernels sample_kernels; do
+for f in capi engine certify team_kernels panel_kernels lane_viterbi scan_kernels frame_kernels sample_kernels transfer; do
     python "$HERE/hostify.py" "$ROOT/bhmm_b200/csrc/$f.cu" > "$GEN/$f.cpp"
     g++ -O1 -std=c++17 -fPIC -w $INC -DPANEL_HOST_EMU=1 -include "$HERE/cuda_fake.h" -c "$GEN/$f.cpp" -o "$GEN/$f.o" &
     OBJS="$OBJS $GEN/$f.o"

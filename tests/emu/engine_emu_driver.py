@@ -286,11 +286,44 @@ def run_time_sharded(N, world=3, halo=90, chunk=40, warm=40):
     check(tag + 'sum gamma', rel(st['wsum'], ref['wsum']) <= 1e-9)
 
 
+def run_transfer():
+    """The estimators' mover (csrc/transfer.cu) on the fake runtime: its piece / slot / worker logic with host memory standing in
+    for the device -- ragged, empty and slot-straddling arrays, 64 KiB slots so that small arrays make many pieces."""
+    lib.bhmm_b200_transfer_config.argtypes = [C.c_int, C.c_int]
+    vp, llp = C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)
+    rng = np.random.default_rng(1)
+    for nt in (1, 0):
+        rc_ok(lib.bhmm_b200_transfer_config(64, nt))
+        slot = 65536 // 8
+        lengths = [1, 0, 7, slot - 1, slot, slot + 1, 0, 3 * slot + 17, 5, 12345, 9 * slot + 3, 0, 2]
+        arrays = [np.ascontiguousarray(rng.standard_normal(n)) for n in lengths]
+        ref = np.concatenate(arrays)
+        nbytes = np.asarray([a.nbytes for a in arrays], dtype=np.int64)
+        for threads in (1, 3, 8):
+            dev = np.full(ref.shape[0] + 3, np.nan)                     # "device" memory, with a guard band
+            ptrs = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+            rc_ok(lib.bhmm_b200_upload_ragged(C.c_void_p(dev.ctypes.data), ptrs, nbytes.ctypes.data_as(llp), len(arrays), threads, None))
+            check('mover upload: %d threads, nt %d' % (threads, nt), np.array_equal(dev[:-3], ref) and np.isnan(dev[-3:]).all())
+            outs = [np.full(n + 2, 77.0) for n in lengths]              # two guard elements each
+            optrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+            rc_ok(lib.bhmm_b200_download_ragged(optrs, C.c_void_p(dev.ctypes.data), nbytes.ctypes.data_as(llp), len(outs), threads, None))
+            ok = all(np.array_equal(o[:-2], a) and (o[-2:] == 77.0).all() for o, a in zip(outs, arrays))
+            check('mover download: %d threads, nt %d' % (threads, nt), ok)
+    check('mover rejects a null table', lib.bhmm_b200_upload_ragged(None, None, None, 3, 0, None) == 1)
+    lib.bhmm_b200_prefault.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
+    z = np.zeros(40000, dtype=np.uint8)
+    check('prefault leaves zeros alone', lib.bhmm_b200_prefault(C.c_void_p(z.ctypes.data), z.nbytes, 3) == 0 and not z.any())
+    rc_ok(lib.bhmm_b200_transfer_config(2048, 1))
+
+
 if __name__ == '__main__':
     print('BHMM_B200_PANEL =', os.environ.get('BHMM_B200_PANEL'), flush=True)
     for spec in sys.argv[1:]:
         if spec.startswith('s'):
             run_time_sharded(int(spec[1:]))
+            continue
+        if spec == 'mover':
+            run_transfer()
             continue
         if spec == 'ties':
             run_literal_viterbi_ties()

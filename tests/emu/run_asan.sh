@@ -22,7 +22,7 @@ LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect
 E="$W/engine"
 mkdir -p "$E/emu"
 INC="-I${CUDA_HOME:-/usr/local/cuda}/include -I$ROOT/bhmm_b200/csrc -I$ROOT/tests/emu"
-for f in capi engine certify team_kernels panel_kernels lane_viterbi scan_kernels frame_kernels sample_kernels; do
+for f in capi engine certify team_kernels panel_kernels lane_viterbi scan_kernels frame_kernels sample_kernels transfer; do
     python "$ROOT/tests/emu/hostify.py" "$ROOT/bhmm_b200/csrc/$f.cu" > "$E/$f.cpp"
     g++ -O1 -g -fsanitize=address -fno-omit-frame-pointer -std=c++17 -fPIC -w $INC -DPANEL_HOST_EMU=1 \
         -include "$ROOT/tests/emu/cuda_fake.h" -c "$E/$f.cpp" -o "$E/$f.o" &

@@ -95,6 +95,13 @@ def test_exact_scan_wide_on_the_emulator(engine_emu):
         assert r.stderr.count('block 64 ') >= 2          # k_scan_starts_wide<2>
 
 
+def test_mover_on_the_fake_runtime(engine_emu):
+    """csrc/transfer.cu compiled against the fake CUDA runtime: pieces that straddle arrays and slots, empty arrays, 1 / 3 / 8
+    worker threads, streaming and plain stores, guard bands around every destination.  (tests/test_transfer_cuda.py does the
+    same through a real GPU.)"""
+    _drive(0, ['mover'])
+
+
 def test_tiled_chase_link_forced(engine_emu):
     """k_chase_link_tiled (chosen on its own only from 65536 segments, i.e. for C5-sized trajectories) forced for every
     batch: batched Viterbi and Gibbs paths with several ragged trajectories, and a literal Viterbi over 36 segments (two
