@@ -167,3 +167,21 @@ def test_gibbs_path_statistics_fixture(oracle_port, golden):
         mu = g['means'][i]
         msd = (st['soo'][i] - 2 * mu * st['so'][i] + n * mu * mu) / n
         np.testing.assert_allclose(msd, float(g['obs_in_state_msd%d' % i]), rtol=1e-9)
+
+
+@pytest.mark.parametrize('name', ['hidden_toy', 'hidden_gauss3'])
+def test_reference_acceptance_against_its_numpy_twin(oracle_port, golden, name):
+    """SURVEY 8c protocol (3): the reference accepts impl 'c' when it is np.allclose to impl 'python'
+    (bhmm/tests/test_hidden.py:240-256).  The same acceptance for the restatement every GPU test is compared with, against
+    the numpy twin's outputs (fixture from the reference package, make_golden.py section 10)."""
+    g, tw = golden(name), golden('hidden_python_twin')
+    A, pi, pobs = g['A'], g['pi'], g['pobs']
+    lp, alpha = oracle_port.forward(A, pobs, pi)
+    beta = oracle_port.backward(A, pobs)
+    gamma = oracle_port.state_probabilities(alpha, beta)
+    assert np.allclose(lp, tw[name + '_logprob'])
+    assert np.allclose(alpha, tw[name + '_alpha']) and np.allclose(beta, tw[name + '_beta'])
+    assert np.allclose(gamma, tw[name + '_gamma'])
+    assert np.allclose(oracle_port.state_counts(gamma), tw[name + '_counts'])
+    assert np.allclose(oracle_port.transition_counts(alpha, beta, A, pobs), tw[name + '_C'])
+    assert np.array_equal(oracle_port.viterbi(A, pobs, pi), tw[name + '_viterbi'])
